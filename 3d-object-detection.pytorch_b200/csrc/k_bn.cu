@@ -1,0 +1,109 @@
+// BatchNorm finalize kernels (reference: nn.BatchNorm2d/1d after every conv / classifier linear,
+// torchdet3d/models/mobilenetv3.py:113,121,137,143,149,153,159,193).
+//
+// The conv kernels accumulate per-slot float partial sums [slots][2][C]; these kernels reduce the
+// slots in double and emit the folded per-channel constants that consumers apply lazily:
+//   forward : scale = gamma*invstd, shift = beta - mean*scale      (x_hat*gamma+beta == scale*y+shift)
+//   backward: g_y = alpha[b,c]*g_u + beta[c]*y + gammac[b,c]        (BN backward incl. SE pooled path)
+#include "td3d_kernels.h"
+
+namespace td3d {
+
+__global__ void bn_finalize_fwd_kernel(BnFwdArgs a) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int s = 0; s < a.slots; ++s) {
+    s1 += (double)a.stats[((size_t)s * 2 + 0) * a.C + c];
+    s2 += (double)a.stats[((size_t)s * 2 + 1) * a.C + c];
+  }
+  double mean = s1 / a.count;
+  double var = s2 / a.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = 1.0 / sqrt(var + (double)a.eps);
+  float sc = (float)((double)a.gamma[c] * invstd);
+  a.scale[c] = sc;
+  a.shift[c] = (float)((double)a.beta[c] - mean * (double)a.gamma[c] * invstd);
+  a.mean[c] = (float)mean;
+  a.invstd[c] = (float)invstd;
+  if (a.running_mean) {
+    double unb = a.count > 1.0 ? var * (a.count / (a.count - 1.0)) : var;
+    a.running_mean[c] = (float)((1.0 - a.momentum) * (double)a.running_mean[c] + a.momentum * mean);
+    a.running_var[c] = (float)((1.0 - a.momentum) * (double)a.running_var[c] + a.momentum * unb);
+    if (c == 0 && a.nbt) *a.nbt += 1;
+  }
+}
+
+int launch_bn_finalize_fwd(const BnFwdArgs& a, cudaStream_t st) {
+  bn_finalize_fwd_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+__global__ void bn_eval_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    float* scale, float* shift, int C, float eps) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // same operation order as ATen's eval-mode batch_norm: (x - mean) * (gamma / sqrt(var + eps)) + beta
+  float invstd = 1.f / sqrtf(rv[c] + eps);
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+int launch_bn_eval_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
+                        float* shift, int C, float eps, cudaStream_t st) {
+  bn_eval_fold_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, rm, rv, scale, shift, C, eps);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+// z = a*y + b (a = gamma*invstd), u = se*z, x = act(u). Given per-(slot,c) sums P1 = sum g_u,
+// P2 = sum g_u*y, the SE gate se[b,c], the gradient g_pool[b,c] w.r.t. the pooled mean of z and
+// the forward pooled sums P0 = sum_HW y:
+//   g_z = se*g_u + g_pool/HW
+//   g_y = a*(g_z - mean_M(g_z) - x_hat*mean_M(g_z*x_hat))
+//       = alpha[b,c]*g_u + beta[c]*y + gammac[b,c]
+__global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const double mu = a.mean[c], is = a.invstd[c];
+  const double M = (double)a.B * (double)a.HW;
+  double S1 = 0.0, S2 = 0.0;
+  const bool se_mode = a.se != nullptr;
+  for (int s = 0; s < a.slots; ++s) {
+    double p1 = a.stats[((size_t)s * 2 + 0) * a.C + c];
+    double p2 = a.stats[((size_t)s * 2 + 1) * a.C + c];
+    double gate = 1.0, gp = 0.0, p0 = 0.0;
+    if (se_mode) {  // slots == B by construction
+      gate = a.se[(size_t)s * a.C + c];
+      gp = a.g_pool[(size_t)s * a.C + c];
+      p0 = a.fwd_pool[((size_t)s * 2 + 0) * a.C + c];
+    }
+    S1 += gate * p1 + gp;
+    S2 += gate * (p2 - mu * p1) * is + (gp / a.HW) * (p0 - a.HW * mu) * is;
+  }
+  const double c1 = S1 / M, c2 = S2 / M;
+  const double aa = (double)a.gamma[c] * is;
+  a.beta[c] = (float)(-aa * c2 * is);
+  a.dgamma[c] = (float)S2;
+  a.dbeta[c] = (float)S1;
+  for (int b = 0; b < a.B; ++b) {
+    double gate = 1.0, gp = 0.0;
+    if (se_mode) {
+      gate = a.se[(size_t)b * a.C + c];
+      gp = a.g_pool[(size_t)b * a.C + c];
+    }
+    a.alpha[(size_t)b * a.C + c] = (float)(aa * gate);
+    a.gammac[(size_t)b * a.C + c] = (float)(aa * (gp / a.HW - c1 + c2 * mu * is));
+  }
+}
+
+int launch_bn_bwd_finalize(const BnBwdArgs& a, cudaStream_t st) {
+  TD3D_REQUIRE(!a.se || a.slots == a.B, "bn_bwd_finalize: SE mode needs slots == B");
+  bn_bwd_finalize_kernel<<<ceil_div(a.C, 64), 64, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+}  // namespace td3d

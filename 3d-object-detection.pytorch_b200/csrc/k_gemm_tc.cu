@@ -1,0 +1,576 @@
+// tcgen05 / TMEM / TMA GEMMs for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   NT  Y[M,N]   = A[M,K] W[N,K]^T (+bias)(+addend)   1x1 convs fwd + dgrad, classifier Linear
+//                  (reference mobilenetv3.py:120,142,148,158,192); both operands K-major
+//   TN  C[N1,N2] += A[M,N1]^T B[M,N2]                  weight gradients; both operands MN-major
+//
+// These GEMMs stream a huge M (= B*H*W pixels) against small K/N (16..960 channels): they are
+// HBM-bound (arithmetic intensity 9-140 flop/B vs a ridge of ~217), so the design goal is bytes in
+// flight, not tensor-pipe occupancy:
+//   * persistent CTAs, one per SM, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer
+//     (one elected thread, tcgen05.mma), warps 2-5 = epilogue (tcgen05.ld -> registers -> global)
+//   * operands are staged by TMA (cp.async.bulk.tensor, hardware swizzle chosen from K so that a
+//     16-channel layer does not waste 7/8 of each shared-memory row) in a multi-stage mbarrier ring
+//   * the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
+//     tile i+1; BatchNorm statistics are reduced in the epilogue with a 31-shuffle transpose-sum
+//   * M/N/K tails are handled by TMA out-of-bounds zero fill + masked epilogue stores
+// Every mbarrier wait is bounded (trap instead of hanging the GPU).
+#include "td3d_kernels.h"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace td3d {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
+//  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D:
+//  [4,6) D fmt=1(f32) | [7,10) A fmt=1(bf16) | [10,13) B fmt=1 | 15 A major | 16 B major |
+//  [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ float warp_transpose_sum32_tc(float v[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      float keep = hi ? v[i + n] : v[i];
+      float send = hi ? v[i] : v[i + n];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// NT kernel
+// ------------------------------------------------------------------------------------------------
+static const int TC_THREADS = 192;          // 6 warps
+static const int TC_BLOCK_M = 128;
+static const int TC_MAX_STAGES = 12;
+static const int TC_TMEM_COLS = 512;
+static const int TC_ACC_STRIDE = 256;       // TMEM columns between the two accumulator stages
+
+struct TcNtParams {
+  int M, N, K;
+  int block_n;          // UMMA N (multiple of 16, <= 256)
+  int block_k;          // elements per k block (16 / 32 / 64) == swizzle span
+  int swizzle_bytes;    // 32 / 64 / 128
+  int stages;
+  int a_stage_bytes, b_stage_bytes;   // ring slot sizes (b padded to 1024 B)
+  int tx_bytes;         // bytes TMA actually delivers per stage (A box + W box)
+  int m_tiles, n_tiles;
+  bf16* y; float* yf;
+  const bf16* addend; const float* bias; const bf16* ysaved;
+  float* stats; int slots;
+  int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcNtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_stat[2][256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms must be 1024B aligned)
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)(p.a_stage_bytes + p.b_stage_bytes);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&s_tfull[s]), 1); mbar_init(smem_u32(&s_tempty[s]), 4); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_stat[0][0])[i] = 0.f;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.K + p.block_k - 1) / p.block_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&s_full[stage]);
+          const uint32_t a_dst = ring + stage * stage_bytes, b_dst = a_dst + p.a_stage_bytes;
+          mbar_expect_tx(full, (uint32_t)p.tx_bytes);
+          tma_load_2d(a_dst, &map_a, full, kb * p.block_k, m0);
+          tma_load_2d(b_dst, &map_w, full, kb * p.block_k, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)p.block_n, 0, 0);
+      const uint32_t layout_type = p.swizzle_bytes == 128 ? 2u : (p.swizzle_bytes == 64 ? 4u : 6u);
+      const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_ACC_STRIDE);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&s_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_src = ring + stage * stage_bytes, b_src = a_src + p.a_stage_bytes;
+          const int k_left = p.K - kb * p.block_k;
+          const int k_steps = ((k_left < p.block_k ? k_left : p.block_k) + 15) >> 4;   // UMMA_K = 16 (bf16)
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const uint64_t da = make_smem_desc(a_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
+            const uint64_t db = make_smem_desc(b_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
+            umma_bf16(d_tmem, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&s_empty[stage]));                 // frees the smem slot when MMAs retire
+          if (kb == k_blocks - 1) umma_commit(smem_u32(&s_tfull[as]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
+    int as = 0; uint32_t aphase = 0;
+    const int n_chunks = (p.block_n + 31) >> 5;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int m0 = m_tile * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
+      mbar_wait(smem_u32(&s_tfull[as]), aphase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_ACC_STRIDE + ch * 32), r);
+        const int nb = n0 + ch * 32;
+        float v[32], w2[32];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = nb + g * 8;
+          const bool ok = row_ok && n < p.N && (n - n0) < p.block_n;
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[g * 8 + i]);
+          if (ok) {
+            if (p.bias) {
+              float bb[8];
+              loadf8(p.bias + n, bb);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] += bb[i];
+            }
+            const size_t off = (size_t)m * p.N + n;
+            if (p.addend) {
+              float ad[8];
+              load8(p.addend + off, ad);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] += ad[i];
+            }
+            if (p.yf) {
+              store8(p.yf + off, x);
+            } else {
+              store8(p.y + off, x);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+            }
+            float ys[8];
+            if (p.ysaved) load8(p.ysaved + off, ys);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[g * 8 + i] = x[i];
+              w2[g * 8 + i] = x[i] * (p.ysaved ? ys[i] : x[i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[g * 8 + i] = 0.f; w2[g * 8 + i] = 0.f; }
+          }
+        }
+        if (p.stats) {
+          float t1 = warp_transpose_sum32_tc(v);
+          float t2 = warp_transpose_sum32_tc(w2);
+          atomicAdd(&s_stat[0][ch * 32 + lane], t1);
+          atomicAdd(&s_stat[1][ch * 32 + lane], t2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_tempty[as]));
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int slot = m_tile % p.slots;
+        for (int j = et; j < 2 * p.block_n; j += 128) {
+          const int which = j / p.block_n, nn = j % p.block_n;
+          if (n0 + nn < p.N) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], s_stat[which][nn]);
+          s_stat[which][nn] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN kernel (weight gradients): C[N1,N2] += A[M,N1]^T B[M,N2], one output tile + one M slice per CTA
+// ------------------------------------------------------------------------------------------------
+static const int TN_BK = 64;                // M rows per stage (4 UMMA_K steps)
+static const int TN_STAGES = 4;
+static const int TN_BOX_BYTES = TN_BK * 128;   // one [64 rows x 64 channels] box
+
+struct TcTnParams {
+  int M, N1, N2;
+  int n2_block;         // UMMA N (multiple of 16, <= 256)
+  int n2_boxes;         // ceil(n2_block / 64)
+  int m_per_part;       // multiple of TN_BK
+  float* c;
+  int swap_lbo_sbo;     // debugging aid: exchange the LBO/SBO roles
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcTnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[TN_STAGES], s_empty[TN_STAGES], s_tfull;
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 2 * TN_BOX_BYTES, b_bytes = (uint32_t)p.n2_boxes * TN_BOX_BYTES;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TN_STAGES; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
+    mbar_init(smem_u32(&s_tfull), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int n1_0 = blockIdx.x * 128, n2_0 = blockIdx.y * p.n2_block;
+  const int ms = blockIdx.z * p.m_per_part;
+  const int me = min(p.M, ms + p.m_per_part);
+  const int k_blocks = (me - ms + TN_BK - 1) / TN_BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
+        const uint32_t full = smem_u32(&s_full[stage]);
+        const uint32_t a_dst = ring + stage * stage_bytes, b_dst = a_dst + a_bytes;
+        mbar_expect_tx(full, stage_bytes);
+        const int row = ms + kb * TN_BK;
+        tma_load_2d(a_dst, &map_a, full, n1_0, row);
+        tma_load_2d(a_dst + TN_BOX_BYTES, &map_a, full, n1_0 + 64, row);
+        for (int j = 0; j < p.n2_boxes; ++j) tma_load_2d(b_dst + j * TN_BOX_BYTES, &map_b, full, n2_0 + j * 64, row);
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, (uint32_t)p.n2_block, 1, 1);
+      // MN-major, 128B swizzle: atom = 64 channels x 8 rows (1024 B). Rows (the contraction index)
+      // advance by 128 B; 8-row groups are SBO apart; 64-channel blocks are LBO apart.
+      uint32_t lbo = TN_BOX_BYTES, sbo = 1024;
+      if (p.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(smem_u32(&s_full[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_src = ring + stage * stage_bytes, b_src = a_src + a_bytes;
+        for (int ks = 0; ks < TN_BK / 16; ++ks) {
+          const uint64_t da = make_smem_desc(a_src + ks * 2048, lbo, sbo, 2u);
+          const uint64_t db = make_smem_desc(b_src + ks * 2048, lbo, sbo, 2u);
+          umma_bf16(tmem_base, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&s_empty[stage]));
+        if (kb == k_blocks - 1) umma_commit(smem_u32(&s_tfull));
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (k_blocks > 0) {
+    const int q = warp & 3;
+    mbar_wait(smem_u32(&s_tfull), 0);
+    tc_fence_after();
+    const int n1 = n1_0 + q * 32 + lane;
+    const int n_chunks = (p.n2_block + 31) >> 5;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+      if (n1 < p.N1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int nn = ch * 32 + i;
+          const int n2 = n2_0 + nn;
+          if (nn < p.n2_block && n2 < p.N2) atomicAdd(&p.c[(size_t)n1 * p.N2 + n2], __uint_as_float(r[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D row-major bf16 tensor [rows][cols], box [box_rows][box_cols]
+static int make_map_2d(CUtensorMap* map, const void* base, int rows, int cols, int box_rows, int box_cols,
+                       int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return TD3D_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box=%dx%d sw=%d base=%p", (int)r, rows, cols,
+                   box_rows, box_cols, swizzle_bytes, base);
+    return TD3D_ECUDA;
+  }
+  return TD3D_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N >= 8 && K >= 8 && (N % 8) == 0 && (K % 8) == 0; }
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
+  TD3D_REQUIRE(tc_gemm_supported(g.M, g.N, g.K), "gemm_nt_tc: unsupported shape M=%d N=%d K=%d", g.M, g.N, g.K);
+  TD3D_REQUIRE(((uintptr_t)g.a & 15) == 0 && ((uintptr_t)g.w & 15) == 0, "gemm_nt_tc: operands must be 16B aligned");
+  TcNtParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  int sw = 128;
+  if (!env_int("TD3D_TC_FORCE_SW128", 0)) {
+    if (g.K <= 16) sw = 32;
+    else if (g.K <= 32) sw = 64;
+  }
+  p.swizzle_bytes = sw;
+  p.block_k = sw / 2;
+  // N tiling: equal tiles of <= 256 columns, each a multiple of 16
+  int n_tiles = ceil_div(g.N, 256);
+  int bn = ceil_div(ceil_div(g.N, n_tiles), 16) * 16;
+  p.block_n = bn;
+  p.n_tiles = ceil_div(g.N, bn);
+  p.m_tiles = ceil_div(g.M, TC_BLOCK_M);
+  p.a_stage_bytes = TC_BLOCK_M * sw;
+  p.b_stage_bytes = ceil_div(bn * sw, 1024) * 1024;
+  p.tx_bytes = TC_BLOCK_M * sw + bn * sw;
+  int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  int budget = 200 * 1024;
+  p.stages = budget / stage_bytes;
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.y = g.out_f32 ? nullptr : (bf16*)g.y;
+  p.yf = g.out_f32 ? (float*)g.y : nullptr;
+  p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
+  p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
+  p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
+  CUtensorMap map_a, map_w;
+  TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
+  TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
+  size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    attr_set = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  gemm_nt_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_w, p);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
+  TD3D_REQUIRE(g.M > 0 && g.N1 % 8 == 0 && g.N2 % 8 == 0, "gemm_tn_tc: unsupported shape M=%d N1=%d N2=%d", g.M, g.N1, g.N2);
+  TcTnParams p;
+  p.M = g.M; p.N1 = g.N1; p.N2 = g.N2;
+  int n2_tiles = ceil_div(g.N2, 256);
+  p.n2_block = ceil_div(ceil_div(g.N2, n2_tiles), 16) * 16;
+  n2_tiles = ceil_div(g.N2, p.n2_block);
+  p.n2_boxes = ceil_div(p.n2_block, 64);
+  int n1_tiles = ceil_div(g.N1, 128);
+  int tiles = n1_tiles * n2_tiles;
+  int parts = ceil_div(num_sms() * 2, tiles);
+  int max_parts = ceil_div(g.M, TN_BK * 4);
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  p.m_per_part = ceil_div(ceil_div(g.M, parts), TN_BK) * TN_BK;
+  parts = ceil_div(g.M, p.m_per_part);
+  p.c = g.c;
+  p.swap_lbo_sbo = env_int("TD3D_TC_TN_SWAP", 0);
+  CUtensorMap map_a, map_b;
+  TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.N1, TN_BK, 64, 128));
+  TD3D_TRY(make_map_2d(&map_b, g.b, g.M, g.N2, TN_BK, 64, 128));
+  size_t smem = (size_t)TN_STAGES * (2 + p.n2_boxes) * TN_BOX_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    attr_set = true;
+  }
+  dim3 grid(n1_tiles, n2_tiles, parts);
+  gemm_tn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+}  // namespace td3d

@@ -1,0 +1,936 @@
+// Plan = the native runtime of the regressor hot path: layer table, memory planner for the
+// caller-owned arenas, and the forward / backward / optimizer orchestration that walks the network
+// launching the sm_100a kernels on one stream (CUDA-graph capturable, no host synchronisation).
+//
+// Mirrors, as one object, what the reference spreads over
+//   build_model            torchdet3d/builders/model_builder.py:25-71
+//   MobileNetV3.__init__   torchdet3d/models/mobilenetv3.py:169-197
+//   ModelWrapper.forward   torchdet3d/builders/model_builder.py:126-146
+//   loss.backward()/step() torchdet3d/trainer/train.py:50-52
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "td3d_kernels.h"
+
+namespace td3d {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_last_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return TD3D_ECUDA;
+}
+
+static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
+
+struct Bn {
+  std::string name;
+  int C = 0;
+  int64_t gamma = 0, beta = 0;          // param arena offsets
+  int64_t rm = 0;                       // bn arena offset (running_mean; running_var = rm + C)
+  size_t scale = 0, shift = 0, mean = 0, invstd = 0;   // workspace (float) train-mode constants
+  size_t escale = 0, eshift = 0;                       // packed arena (float) eval-mode constants
+  size_t fstats = 0, bstats = 0;                       // workspace float [B][2][C]
+};
+
+struct Block {
+  td3d_block_desc d;
+  bool expand, residual;
+  int Hin, Win, Hout, Wout;
+  int bn1, bn2, bn3;                    // indices into bns (-1 if absent)
+  int64_t w1 = -1, wdw = -1, w3 = -1;   // param offsets
+  int64_t se_w1 = -1, se_b1 = -1, se_w2 = -1, se_b2 = -1;
+  size_t pw1 = 0, pw1t = 0, pdw = 0, pw3 = 0, pw3t = 0;   // packed offsets
+  size_t y1 = 0, y2 = 0, h = 0, h2 = 0, y3 = 0, out = 0;  // workspace activations (T)
+  size_t hstats = 0, hbstats = 0;       // dw-first + SE: pool sums of H and their backward twin
+  size_t zbar = 0, hid = 0, pre = 0, gate = 0;
+  int64_t first_param = 0;
+};
+
+struct Param {
+  td3d_param_info info;
+};
+
+}  // namespace td3d
+
+using namespace td3d;
+
+struct td3d_plan {
+  td3d_net_desc net;
+  std::vector<td3d_block_desc> block_descs;
+  int B, H, W, dtype, gemm_impl;
+  size_t esz;                            // bytes per activation element
+  std::vector<Param> params;
+  std::vector<Bn> bns;
+  std::vector<Block> blocks;
+  int64_t param_floats = 0, bn_floats = 0;
+  size_t packed_bytes = 0, ws_bytes = 0;
+  // stem / tail
+  int H1, W1;                            // stem output resolution
+  int bn_stem, bn_last, bn_fc;
+  int64_t w_stem, w_last, w_fc, b_fc, w_reg0, w_cls, b_cls;
+  int64_t head_stride;
+  size_t p_stem, p_last, p_lastt, p_fc, p_fct;
+  size_t y0, x0, yc, pooled, yfc, feat, kp_saved, logits_saved, pool_stats, pool_bstats_unused;
+  int Hl, Wl;                            // final resolution
+  int64_t first_param_tail;
+  // backward scratch
+  size_t g_narrow[2], g_y3, g_wide_a, g_wide_b, g_feat, g_pool_f, g_pre_heads;
+  size_t alpha, beta, gammac, zeros_c, se_gpre, se_ghid, se_gpool, se_gpool_scaled;
+  size_t fstats_begin = 0, fstats_end = 0, bstats_begin = 0, bstats_end = 0;
+  // bound buffers
+  float* P = nullptr; float* G = nullptr; float* BNB = nullptr; int64_t* NBT = nullptr;
+  uint8_t* PK = nullptr; uint8_t* WS = nullptr;
+  // last forward
+  const float* last_img = nullptr; const int64_t* last_cats = nullptr; const float* last_keep = nullptr;
+  uint64_t last_seed = 0; int last_training = 0;
+  const int32_t* dropout_counter = nullptr;
+};
+
+namespace td3d {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+static int64_t add_param(td3d_plan* pl, const std::string& name, std::vector<int64_t> shape, int bn_index = -1) {
+  Param p;
+  memset(&p.info, 0, sizeof(p.info));
+  snprintf(p.info.name, sizeof(p.info.name), "%s", name.c_str());
+  int64_t n = 1;
+  for (size_t i = 0; i < shape.size(); ++i) { p.info.shape[i] = shape[i]; n *= shape[i]; }
+  p.info.ndim = (int)shape.size();
+  p.info.numel = n;
+  p.info.offset = pl->param_floats;
+  p.info.bn_index = bn_index;
+  pl->param_floats = (int64_t)align_up((size_t)(pl->param_floats + n), 4);
+  pl->params.push_back(p);
+  return p.info.offset;
+}
+
+static int add_bn(td3d_plan* pl, const std::string& prefix, int C) {
+  Bn b;
+  b.name = prefix;
+  b.C = C;
+  int idx = (int)pl->bns.size();
+  b.gamma = add_param(pl, prefix + ".weight", {C}, idx);
+  b.beta = add_param(pl, prefix + ".bias", {C}, idx);
+  b.rm = pl->bn_floats;
+  pl->bn_floats += 2 * (int64_t)C;
+  pl->bns.push_back(b);
+  return idx;
+}
+
+static int build(td3d_plan* pl) {
+  const td3d_net_desc& n = pl->net;
+  const int B = pl->B;
+  pl->H1 = (pl->H - 1) / 2 + 1;
+  pl->W1 = (pl->W - 1) / 2 + 1;
+  // ---- parameter table in reference state_dict order ----
+  pl->w_stem = add_param(pl, "features.0.0.weight", {n.stem_ch, 3, 3, 3});
+  pl->bn_stem = add_bn(pl, "features.0.1", n.stem_ch);
+  int h = pl->H1, w = pl->W1;
+  int cin = n.stem_ch;
+  for (int i = 0; i < n.n_blocks; ++i) {
+    Block b;
+    b.d = pl->block_descs[i];
+    TD3D_REQUIRE(b.d.in_ch == cin, "block %d: in_ch=%d does not chain from %d", i, b.d.in_ch, cin);
+    TD3D_REQUIRE(b.d.in_ch % 8 == 0 && b.d.exp_ch % 8 == 0 && b.d.out_ch % 8 == 0, "block %d: channels must be multiples of 8", i);
+    TD3D_REQUIRE((b.d.kernel == 3 || b.d.kernel == 5) && (b.d.stride == 1 || b.d.stride == 2), "block %d: bad kernel/stride", i);
+    b.expand = b.d.in_ch != b.d.exp_ch;
+    b.residual = b.d.stride == 1 && b.d.in_ch == b.d.out_ch;
+    b.Hin = h; b.Win = w;
+    b.Hout = (h - 1) / b.d.stride + 1; b.Wout = (w - 1) / b.d.stride + 1;
+    std::string pre = "features." + std::to_string(i + 1) + ".conv.";
+    b.first_param = pl->param_floats;
+    b.bn1 = -1;
+    int j = 0;
+    if (b.expand) {
+      b.w1 = add_param(pl, pre + "0.weight", {b.d.exp_ch, b.d.in_ch, 1, 1});
+      b.bn1 = add_bn(pl, pre + "1", b.d.exp_ch);
+      j = 3;
+    }
+    b.wdw = add_param(pl, pre + std::to_string(j) + ".weight", {b.d.exp_ch, 1, b.d.kernel, b.d.kernel});
+    b.bn2 = add_bn(pl, pre + std::to_string(j + 1), b.d.exp_ch);
+    int se_idx = b.expand ? j + 2 : j + 3, pw_idx = b.expand ? 7 : 4;
+    if (b.d.use_se) {
+      std::string sp = pre + std::to_string(se_idx) + ".fc.";
+      b.se_w1 = add_param(pl, sp + "0.weight", {b.d.se_hidden, b.d.exp_ch});
+      b.se_b1 = add_param(pl, sp + "0.bias", {b.d.se_hidden});
+      b.se_w2 = add_param(pl, sp + "2.weight", {b.d.exp_ch, b.d.se_hidden});
+      b.se_b2 = add_param(pl, sp + "2.bias", {b.d.exp_ch});
+    }
+    b.w3 = add_param(pl, pre + std::to_string(pw_idx) + ".weight", {b.d.out_ch, b.d.exp_ch, 1, 1});
+    b.bn3 = add_bn(pl, pre + std::to_string(pw_idx + 1), b.d.out_ch);
+    pl->blocks.push_back(b);
+    h = b.Hout; w = b.Wout; cin = b.d.out_ch;
+  }
+  pl->Hl = h; pl->Wl = w;
+  pl->first_param_tail = pl->param_floats;
+  pl->w_last = add_param(pl, "conv.0.weight", {n.last_ch, cin, 1, 1});
+  pl->bn_last = add_bn(pl, "conv.1", n.last_ch);
+  pl->w_fc = add_param(pl, "classifier.0.weight", {n.head_ch, n.last_ch});
+  pl->b_fc = add_param(pl, "classifier.0.bias", {n.head_ch});
+  pl->bn_fc = add_bn(pl, "classifier.1", n.head_ch);
+  pl->head_stride = 0;
+  for (int k = 0; k < n.max_classes; ++k) {
+    int64_t wo = add_param(pl, "regressors." + std::to_string(k) + ".0.weight", {n.num_points, n.head_ch});
+    add_param(pl, "regressors." + std::to_string(k) + ".0.bias", {n.num_points});
+    if (k == 0) pl->w_reg0 = wo;
+    if (k == 1) pl->head_stride = wo - pl->w_reg0;
+  }
+  if (n.max_classes == 1) pl->head_stride = pl->param_floats - pl->w_reg0;
+  pl->w_cls = add_param(pl, "cls_fc.1.weight", {n.num_classes, n.head_ch});
+  pl->b_cls = add_param(pl, "cls_fc.1.bias", {n.num_classes});
+
+  // ---- packed weights ----
+  Bump pk;
+  const size_t e = pl->esz;
+  pl->p_stem = pk.take(sizeof(float) * 27 * n.stem_ch);
+  for (auto& b : pl->blocks) {
+    if (b.expand) {
+      b.pw1 = pk.take(e * b.d.exp_ch * b.d.in_ch);
+      b.pw1t = pk.take(e * b.d.exp_ch * b.d.in_ch);
+    }
+    b.pdw = pk.take(sizeof(float) * b.d.kernel * b.d.kernel * b.d.exp_ch);
+    b.pw3 = pk.take(e * b.d.out_ch * b.d.exp_ch);
+    b.pw3t = pk.take(e * b.d.out_ch * b.d.exp_ch);
+  }
+  pl->p_last = pk.take(e * n.last_ch * cin);
+  pl->p_lastt = pk.take(e * n.last_ch * cin);
+  pl->p_fc = pk.take(e * n.head_ch * n.last_ch);
+  pl->p_fct = pk.take(e * n.head_ch * n.last_ch);
+  for (auto& bn : pl->bns) {
+    bn.escale = pk.take(sizeof(float) * bn.C);
+    bn.eshift = pk.take(sizeof(float) * bn.C);
+  }
+  pl->packed_bytes = pk.off;
+
+  // ---- workspace ----
+  Bump ws;
+  auto act = [&](int64_t rows, int C) { return ws.take(e * (size_t)rows * C); };
+  auto f32 = [&](int64_t nelem) { return ws.take(sizeof(float) * (size_t)nelem); };
+  // statistics first (two contiguous regions so one memset clears each)
+  pl->fstats_begin = ws.off;
+  for (auto& bn : pl->bns) bn.fstats = f32((int64_t)B * 2 * bn.C);
+  for (auto& b : pl->blocks)
+    if (!b.expand && b.d.use_se) b.hstats = f32((int64_t)B * 2 * b.d.exp_ch);
+  pl->pool_stats = f32((int64_t)B * 2 * n.last_ch);
+  pl->fstats_end = ws.off;
+  pl->bstats_begin = ws.off;
+  for (auto& bn : pl->bns) bn.bstats = f32((int64_t)B * 2 * bn.C);
+  for (auto& b : pl->blocks)
+    if (!b.expand && b.d.use_se) b.hbstats = f32((int64_t)B * 2 * b.d.exp_ch);
+  pl->bstats_end = ws.off;
+  for (auto& bn : pl->bns) {
+    bn.scale = f32(bn.C); bn.shift = f32(bn.C); bn.mean = f32(bn.C); bn.invstd = f32(bn.C);
+  }
+  const int64_t M1 = (int64_t)B * pl->H1 * pl->W1;
+  pl->y0 = act(M1, n.stem_ch);
+  pl->x0 = act(M1, n.stem_ch);
+  int64_t max_narrow = M1 * n.stem_ch, max_wide = 0;
+  int maxC = n.stem_ch;
+  for (auto& b : pl->blocks) {
+    const int64_t Mi = (int64_t)B * b.Hin * b.Win, Mo = (int64_t)B * b.Hout * b.Wout;
+    if (b.expand) b.y1 = act(Mi, b.d.exp_ch);
+    b.y2 = act(Mo, b.d.exp_ch);
+    if (!b.expand && b.d.use_se) b.h = act(Mo, b.d.exp_ch);
+    b.h2 = act(Mo, b.d.exp_ch);
+    b.y3 = act(Mo, b.d.out_ch);
+    b.out = act(Mo, b.d.out_ch);
+    if (b.d.use_se) {
+      b.zbar = f32((int64_t)B * b.d.exp_ch); b.hid = f32((int64_t)B * b.d.se_hidden);
+      b.pre = f32((int64_t)B * b.d.exp_ch); b.gate = f32((int64_t)B * b.d.exp_ch);
+    }
+    if (Mi * b.d.in_ch > max_narrow) max_narrow = Mi * b.d.in_ch;
+    if (Mo * b.d.out_ch > max_narrow) max_narrow = Mo * b.d.out_ch;
+    if (Mi * b.d.exp_ch > max_wide) max_wide = Mi * b.d.exp_ch;
+    if (b.d.exp_ch > maxC) maxC = b.d.exp_ch;
+  }
+  const int64_t Ml = (int64_t)B * pl->Hl * pl->Wl;
+  pl->yc = act(Ml, n.last_ch);
+  pl->pooled = act(B, n.last_ch);
+  pl->yfc = act(B, n.head_ch);
+  pl->feat = act(B, n.head_ch);
+  pl->kp_saved = f32((int64_t)B * n.num_points);
+  pl->logits_saved = f32((int64_t)B * n.num_classes);
+  if (Ml * n.last_ch > max_wide) max_wide = Ml * n.last_ch;
+  if ((int64_t)B * n.head_ch > max_wide) max_wide = (int64_t)B * n.head_ch;
+  if (n.last_ch > maxC) maxC = n.last_ch;
+  if (n.head_ch > maxC) maxC = n.head_ch;
+  pl->g_narrow[0] = act(max_narrow, 1);
+  pl->g_narrow[1] = act(max_narrow, 1);
+  pl->g_y3 = act(max_narrow, 1);
+  pl->g_wide_a = act(max_wide, 1);
+  pl->g_wide_b = act(max_wide, 1);
+  pl->g_feat = f32((int64_t)B * n.head_ch);
+  pl->g_pool_f = f32((int64_t)B * n.last_ch);
+  pl->g_pre_heads = f32((int64_t)B * n.num_points);
+  pl->alpha = f32((int64_t)B * maxC);
+  pl->gammac = f32((int64_t)B * maxC);
+  pl->beta = f32(maxC);
+  pl->zeros_c = f32(maxC);
+  pl->se_gpre = f32((int64_t)B * maxC);
+  pl->se_ghid = f32((int64_t)B * maxC);
+  pl->se_gpool = f32((int64_t)B * maxC);
+  pl->se_gpool_scaled = f32((int64_t)B * maxC);
+  pl->ws_bytes = ws.off;
+  return TD3D_OK;
+}
+
+// ---- helpers --------------------------------------------------------------------------------
+struct Ctx {
+  td3d_plan* pl;
+  cudaStream_t st;
+  template <typename T = void> T* ws(size_t off) const { return reinterpret_cast<T*>(pl->WS + off); }
+  float* wsf(size_t off) const { return reinterpret_cast<float*>(pl->WS + off); }
+  void* pk(size_t off) const { return pl->PK + off; }
+  float* pkf(size_t off) const { return reinterpret_cast<float*>(pl->PK + off); }
+  float* P(int64_t off) const { return pl->P + off; }
+  float* G(int64_t off) const { return pl->G + off; }
+};
+
+static bool use_tc(const td3d_plan* pl, int M, int N, int K) {
+  if (pl->dtype != TD3D_BF16) return false;
+  if (pl->gemm_impl == TD3D_GEMM_SIMT) return false;
+  return tc_gemm_supported(M, N, K);
+}
+
+static int gemm_nt(const Ctx& c, GemmNT g) {
+  if (use_tc(c.pl, g.M, g.N, g.K)) return launch_gemm_nt_tc(g, c.st);
+  return launch_gemm_nt_simt(g, c.pl->dtype, c.st);
+}
+static int gemm_tn(const Ctx& c, GemmTN g) {
+  if (c.pl->dtype == TD3D_BF16 && c.pl->gemm_impl != TD3D_GEMM_SIMT && g.N1 % 8 == 0 && g.N2 % 8 == 0)
+    return launch_gemm_tn_tc(g, c.st);
+  return launch_gemm_tn_simt(g, c.pl->dtype, c.st);
+}
+
+// BatchNorm after a conv: training -> finalize batch statistics (and update running stats);
+// eval -> folded running statistics. Returns the (scale, shift) the consumer must apply.
+static int bn_forward(const Ctx& c, int idx, double count, int training, const float** scale, const float** shift) {
+  Bn& bn = c.pl->bns[idx];
+  if (training) {
+    BnFwdArgs a;
+    a.stats = c.wsf(bn.fstats); a.slots = c.pl->B; a.count = count;
+    a.gamma = c.P(bn.gamma); a.beta = c.P(bn.beta);
+    a.running_mean = c.pl->BNB + bn.rm; a.running_var = c.pl->BNB + bn.rm + bn.C;
+    a.nbt = c.pl->NBT ? c.pl->NBT + idx : nullptr;
+    a.scale = c.wsf(bn.scale); a.shift = c.wsf(bn.shift); a.mean = c.wsf(bn.mean); a.invstd = c.wsf(bn.invstd);
+    a.C = bn.C; a.momentum = BN_MOMENTUM; a.eps = BN_EPS;
+    TD3D_TRY(launch_bn_finalize_fwd(a, c.st));
+    *scale = a.scale; *shift = a.shift;
+  } else {
+    *scale = c.pkf(bn.escale); *shift = c.pkf(bn.eshift);
+  }
+  return TD3D_OK;
+}
+
+static XForm xf_make(const float* scale, const float* shift, const float* se, int act) {
+  XForm x; x.scale = scale; x.shift = shift; x.se = se; x.act = act;
+  return x;
+}
+
+static int forward_backbone(const Ctx& c, const float* img, int training, const void** feat_out) {
+  td3d_plan* pl = c.pl;
+  const td3d_net_desc& n = pl->net;
+  const int B = pl->B, dt = pl->dtype;
+  TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->fstats_begin, 0, pl->fstats_end - pl->fstats_begin, c.st));
+  const float *sc, *sh;
+  // stem
+  Bn& b0 = pl->bns[pl->bn_stem];
+  TD3D_TRY(launch_stem_fwd(img, c.pkf(pl->p_stem), c.ws(pl->y0), c.wsf(b0.fstats), B, pl->H, pl->W, n.stem_ch, dt, c.st));
+  TD3D_TRY(bn_forward(c, pl->bn_stem, (double)B * pl->H1 * pl->W1, training, &sc, &sh));
+  TD3D_TRY(launch_apply_xform(c.ws(pl->y0), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->x0), nullptr,
+                              B, pl->H1 * pl->W1, n.stem_ch, dt, c.st));
+  const void* cur = c.ws(pl->x0);
+  for (auto& b : pl->blocks) {
+    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
+    const int Mi = B * HWi, Mo = B * HWo;
+    const int E = b.d.exp_ch;
+    DwArgs dw;
+    if (b.expand) {
+      GemmNT g = {};
+      g.a = cur; g.w = c.pk(b.pw1); g.y = c.ws(b.y1);
+      g.stats = c.wsf(pl->bns[b.bn1].fstats); g.slots = B;
+      g.M = Mi; g.N = E; g.K = b.d.in_ch;
+      TD3D_TRY(gemm_nt(c, g));
+      TD3D_TRY(bn_forward(c, b.bn1, (double)Mi, training, &sc, &sh));
+      dw.x = c.ws(b.y1); dw.xf = xf_make(sc, sh, nullptr, act);
+    } else {
+      dw.x = cur; dw.xf = xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE);
+    }
+    dw.w_taps = c.pkf(b.pdw); dw.y = c.ws(b.y2); dw.stats = c.wsf(pl->bns[b.bn2].fstats);
+    dw.B = B; dw.H = b.Hin; dw.W = b.Win; dw.C = E; dw.k = b.d.kernel; dw.stride = b.d.stride;
+    TD3D_TRY(launch_dw_fwd(dw, dt, c.st));
+    TD3D_TRY(bn_forward(c, b.bn2, (double)Mo, training, &sc, &sh));
+    if (b.d.use_se) {
+      SeArgs s;
+      s.w1 = c.P(b.se_w1); s.b1 = c.P(b.se_b1); s.w2 = c.P(b.se_w2); s.b2 = c.P(b.se_b2);
+      s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
+      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
+      if (b.expand) {      // BN -> SE -> act (mobilenetv3.py:153-156): squeeze from the dw epilogue sums
+        s.pool_stats = c.wsf(pl->bns[b.bn2].fstats); s.scale = sc; s.shift = sh;
+        TD3D_TRY(launch_se_fwd(s, c.st));
+        TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, s.gate, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+      } else {             // BN -> act -> SE (mobilenetv3.py:137-140)
+        TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h), c.wsf(b.hstats), B, HWo, E, dt, c.st));
+        s.pool_stats = c.wsf(b.hstats); s.scale = nullptr; s.shift = nullptr;
+        TD3D_TRY(launch_se_fwd(s, c.st));
+        TD3D_TRY(launch_apply_xform(c.ws(b.h), xf_make(nullptr, nullptr, s.gate, TD3D_ACT_NONE), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+      }
+    } else {
+      TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+    }
+    GemmNT g = {};
+    g.a = c.ws(b.h2); g.w = c.pk(b.pw3); g.y = c.ws(b.y3);
+    g.stats = c.wsf(pl->bns[b.bn3].fstats); g.slots = B;
+    g.M = Mo; g.N = b.d.out_ch; g.K = E;
+    TD3D_TRY(gemm_nt(c, g));
+    TD3D_TRY(bn_forward(c, b.bn3, (double)Mo, training, &sc, &sh));
+    TD3D_TRY(launch_apply_xform(c.ws(b.y3), xf_make(sc, sh, nullptr, TD3D_ACT_NONE), b.residual ? cur : nullptr,
+                                c.ws(b.out), nullptr, B, HWo, b.d.out_ch, dt, c.st));
+    cur = c.ws(b.out);
+  }
+  // final 1x1 conv + BN + h_swish + global average pool (mobilenetv3.py:188,199-203; model_builder.py:98)
+  const int HWl = pl->Hl * pl->Wl, Ml = B * HWl;
+  const int Cl = pl->blocks.back().d.out_ch;
+  {
+    GemmNT g = {};
+    g.a = cur; g.w = c.pk(pl->p_last); g.y = c.ws(pl->yc);
+    g.stats = c.wsf(pl->bns[pl->bn_last].fstats); g.slots = B;
+    g.M = Ml; g.N = n.last_ch; g.K = Cl;
+    TD3D_TRY(gemm_nt(c, g));
+    TD3D_TRY(bn_forward(c, pl->bn_last, (double)Ml, training, &sc, &sh));
+    TD3D_TRY(launch_apply_xform(c.ws(pl->yc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, nullptr,
+                                c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
+    TD3D_TRY(launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
+  }
+  // classifier: Linear -> BatchNorm1d -> h_swish (mobilenetv3.py:191-195)
+  {
+    GemmNT g = {};
+    g.a = c.ws(pl->pooled); g.w = c.pk(pl->p_fc); g.y = c.ws(pl->yfc); g.bias = c.P(pl->b_fc);
+    g.stats = c.wsf(pl->bns[pl->bn_fc].fstats); g.slots = B;
+    g.M = B; g.N = n.head_ch; g.K = n.last_ch;
+    TD3D_TRY(gemm_nt(c, g));
+    TD3D_TRY(bn_forward(c, pl->bn_fc, (double)B, training, &sc, &sh));
+    TD3D_TRY(launch_apply_xform(c.ws(pl->yfc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->feat), nullptr,
+                                B, 1, n.head_ch, dt, c.st));
+  }
+  *feat_out = c.ws(pl->feat);
+  return TD3D_OK;
+}
+
+static HeadsArgs heads_args(const Ctx& c, const void* feat, const int64_t* cats, const float* keep, uint64_t seed,
+                            int training) {
+  td3d_plan* pl = c.pl;
+  HeadsArgs h;
+  h.feat = feat; h.cats = cats;
+  h.w_reg = c.P(pl->w_reg0); h.reg_stride = pl->head_stride;
+  h.w_cls = c.P(pl->w_cls); h.b_cls = c.P(pl->b_cls);
+  h.keep = keep; h.seed = seed; h.training = training; h.step_ptr = pl->dropout_counter;
+  h.kp = c.wsf(pl->kp_saved); h.logits = c.wsf(pl->logits_saved);
+  h.B = pl->B; h.C = pl->net.head_ch; h.P = pl->net.num_points; h.nc = pl->net.num_classes;
+  h.max_classes = pl->net.max_classes;
+  return h;
+}
+
+// ---- backward ---------------------------------------------------------------------------------
+static int bn_backward(const Ctx& c, int idx, int HW, const float* se, const float* g_pool, const float* fwd_pool) {
+  td3d_plan* pl = c.pl;
+  Bn& bn = pl->bns[idx];
+  BnBwdArgs a;
+  a.stats = c.wsf(bn.bstats); a.slots = pl->B;
+  a.mean = c.wsf(bn.mean); a.invstd = c.wsf(bn.invstd); a.gamma = c.P(bn.gamma);
+  a.se = se; a.g_pool = g_pool; a.fwd_pool = fwd_pool;
+  a.alpha = c.wsf(pl->alpha); a.beta = c.wsf(pl->beta); a.gammac = c.wsf(pl->gammac);
+  a.dgamma = c.G(bn.gamma); a.dbeta = c.G(bn.beta);
+  a.B = pl->B; a.HW = HW; a.C = bn.C;
+  return launch_bn_bwd_finalize(a, c.st);
+}
+
+__global__ void colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
+                              const float* __restrict__ gammac, const float* __restrict__ bstats,
+                              const float* __restrict__ fstats, float* __restrict__ out, int B, int C) {
+  // sum_b (alpha[b,c]*g_u + beta[c]*y + gammac[b,c]) from the per-sample sums (HW = 1)
+  int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= C) return;
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b)
+    acc += (double)alpha[(size_t)b * C + cc] * bstats[((size_t)b * 2) * C + cc] +
+           (double)beta[cc] * fstats[((size_t)b * 2) * C + cc] + (double)gammac[(size_t)b * C + cc];
+  out[cc] = (float)acc;
+}
+
+__global__ void scale_kernel(const float* __restrict__ src, float s, float* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * s;
+}
+
+static int n_stages(const td3d_plan* pl) { return (int)pl->blocks.size() + 2; }
+
+static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits, int32_t* present, int s_begin,
+                         int s_end) {
+  td3d_plan* pl = c.pl;
+  const td3d_net_desc& n = pl->net;
+  const int B = pl->B, dt = pl->dtype;
+  const int nblk = (int)pl->blocks.size();
+  TD3D_REQUIRE(pl->last_training, "backward: no training-mode forward recorded on this plan");
+  auto in_range = [&](int s) { return s >= s_begin && s < s_end; };
+  const int HWl = pl->Hl * pl->Wl, Ml = B * HWl;
+  const int Cl = pl->blocks.back().d.out_ch;
+
+  if (in_range(0)) {
+    TD3D_CUDA(cudaMemsetAsync(pl->G, 0, sizeof(float) * (size_t)pl->param_floats, c.st));
+    TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->bstats_begin, 0, pl->bstats_end - pl->bstats_begin, c.st));
+    TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->zeros_c, 0, sizeof(float) * 16, c.st));
+    // heads
+    HeadsBwdArgs hb;
+    hb.f = heads_args(c, c.ws(pl->feat), pl->last_cats, pl->last_keep, pl->last_seed, 1);
+    hb.d_kp = d_kp; hb.d_logits = d_logits;
+    hb.g_pre = c.wsf(pl->g_pre_heads); hb.g_feat = c.wsf(pl->g_feat);
+    hb.dw_reg = c.G(pl->w_reg0); hb.dw_cls = c.G(pl->w_cls); hb.db_cls = c.G(pl->b_cls);
+    hb.present = present;
+    TD3D_TRY(launch_heads_bwd(hb, dt, c.st));
+    // classifier: feat = h_swish(BN1d(yfc))
+    Bn& bfc = pl->bns[pl->bn_fc];
+    XForm xfc = xf_make(c.wsf(bfc.scale), c.wsf(bfc.shift), nullptr, TD3D_ACT_HSWISH);
+    TD3D_TRY(launch_act_bwd_stats(nullptr, c.wsf(pl->g_feat), 1.f, c.ws(pl->yfc), xfc, c.ws(pl->g_wide_a), c.wsf(bfc.bstats),
+                                  B, 1, n.head_ch, dt, c.st));
+    TD3D_TRY(bn_backward(c, pl->bn_fc, 1, nullptr, nullptr, nullptr));
+    colsum_kernel<<<ceil_div(n.head_ch, 128), 128, 0, c.st>>>(c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                                                              c.wsf(bfc.bstats), c.wsf(bfc.fstats), c.G(pl->b_fc), B, n.head_ch);
+    TD3D_LAUNCH_CHECK();
+    TD3D_TRY(launch_affine2(c.ws(pl->g_wide_a), c.ws(pl->yfc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                            c.ws(pl->g_wide_a), B, 1, n.head_ch, dt, c.st));
+    {
+      GemmTN t = {c.ws(pl->g_wide_a), c.ws(pl->pooled), c.G(pl->w_fc), B, n.head_ch, n.last_ch};
+      TD3D_TRY(gemm_tn(c, t));
+      GemmNT g = {};
+      g.a = c.ws(pl->g_wide_a); g.w = c.pk(pl->p_fct); g.y = c.wsf(pl->g_pool_f); g.out_f32 = 1;
+      g.M = B; g.N = n.last_ch; g.K = n.head_ch;
+      TD3D_TRY(gemm_nt(c, g));
+    }
+    // avg-pool backward + h_swish + BN of the final conv
+    Bn& bl = pl->bns[pl->bn_last];
+    XForm xl = xf_make(c.wsf(bl.scale), c.wsf(bl.shift), nullptr, TD3D_ACT_HSWISH);
+    TD3D_TRY(launch_act_bwd_stats(nullptr, c.wsf(pl->g_pool_f), 1.f / (float)HWl, c.ws(pl->yc), xl, c.ws(pl->g_wide_a),
+                                  c.wsf(bl.bstats), B, HWl, n.last_ch, dt, c.st));
+    TD3D_TRY(bn_backward(c, pl->bn_last, HWl, nullptr, nullptr, nullptr));
+    TD3D_TRY(launch_affine2(c.ws(pl->g_wide_a), c.ws(pl->yc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                            c.ws(pl->g_wide_a), B, HWl, n.last_ch, dt, c.st));
+    {
+      Block& lb = pl->blocks.back();
+      GemmTN t = {c.ws(pl->g_wide_a), c.ws(lb.out), c.G(pl->w_last), Ml, n.last_ch, Cl};
+      TD3D_TRY(gemm_tn(c, t));
+      GemmNT g = {};
+      g.a = c.ws(pl->g_wide_a); g.w = c.pk(pl->p_lastt); g.y = c.ws(pl->g_narrow[nblk & 1]);
+      g.ysaved = c.ws(lb.y3); g.stats = c.wsf(pl->bns[lb.bn3].bstats); g.slots = B;
+      g.M = Ml; g.N = Cl; g.K = n.last_ch;
+      TD3D_TRY(gemm_nt(c, g));
+    }
+  }
+  // blocks, last to first. Gradient w.r.t. the output of block i lives in g_narrow[(i+1)&1].
+  for (int i = nblk - 1; i >= 0; --i) {
+    if (!in_range(nblk - i)) continue;
+    Block& b = pl->blocks[i];
+    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
+    const int Mi = B * HWi, Mo = B * HWo;
+    const int E = b.d.exp_ch;
+    void* g_out = c.ws(pl->g_narrow[(i + 1) & 1]);
+    void* g_in = c.ws(pl->g_narrow[i & 1]);
+    const void* x_in = i == 0 ? c.ws(pl->x0) : c.ws(pl->blocks[i - 1].out);
+    // BN3 (linear): g_y3 = alpha*g_out + beta*y3 + gamma
+    TD3D_TRY(bn_backward(c, b.bn3, HWo, nullptr, nullptr, nullptr));
+    TD3D_TRY(launch_affine2(g_out, c.ws(b.y3), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac), c.ws(pl->g_y3), B,
+                            HWo, b.d.out_ch, dt, c.st));
+    {
+      GemmTN t = {c.ws(pl->g_y3), c.ws(b.h2), c.G(b.w3), Mo, b.d.out_ch, E};
+      TD3D_TRY(gemm_tn(c, t));
+      GemmNT g = {};
+      g.a = c.ws(pl->g_y3); g.w = c.pk(b.pw3t); g.y = c.ws(pl->g_wide_a);
+      g.M = Mo; g.N = E; g.K = b.d.out_ch;
+      TD3D_TRY(gemm_nt(c, g));
+    }
+    Bn& bn2 = pl->bns[b.bn2];
+    const float* sc2 = c.wsf(bn2.scale);
+    const float* sh2 = c.wsf(bn2.shift);
+    void* gw = c.ws(pl->g_wide_a);
+    if (b.expand) {
+      const float* gate = b.d.use_se ? c.wsf(b.gate) : nullptr;
+      TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, gate, act), gw, c.wsf(bn2.bstats), B, HWo,
+                                    E, dt, c.st));
+      if (b.d.use_se) {
+        SeBwdArgs s;
+        s.bwd_stats = c.wsf(bn2.bstats); s.scale = sc2; s.shift = sh2; s.inv_hw = 1.f / (float)HWo;
+        s.w1 = c.P(b.se_w1); s.w2 = c.P(b.se_w2);
+        s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
+        s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
+        s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
+        s.B = B; s.C = E; s.Ch = b.d.se_hidden;
+        TD3D_TRY(launch_se_bwd(s, c.st));
+        TD3D_TRY(bn_backward(c, b.bn2, HWo, gate, c.wsf(pl->se_gpool), c.wsf(bn2.fstats)));
+      } else {
+        TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
+      }
+    } else {
+      if (b.d.use_se) {
+        // x = H * gate with H = act(BN(y2)):  g_H = gate*g_x + g_pool/HW
+        TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.h), xf_make(nullptr, nullptr, c.wsf(b.gate), TD3D_ACT_NONE), gw,
+                                      c.wsf(b.hbstats), B, HWo, E, dt, c.st));
+        SeBwdArgs s;
+        s.bwd_stats = c.wsf(b.hbstats); s.scale = nullptr; s.shift = nullptr; s.inv_hw = 1.f / (float)HWo;
+        s.w1 = c.P(b.se_w1); s.w2 = c.P(b.se_w2);
+        s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
+        s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
+        s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
+        s.B = B; s.C = E; s.Ch = b.d.se_hidden;
+        TD3D_TRY(launch_se_bwd(s, c.st));
+        scale_kernel<<<ceil_div(B * E, 256), 256, 0, c.st>>>(c.wsf(pl->se_gpool), 1.f / (float)HWo, c.wsf(pl->se_gpool_scaled), B * E);
+        TD3D_LAUNCH_CHECK();
+        TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->zeros_c), 0, sizeof(float) * E, c.st));
+        TD3D_TRY(launch_affine2(gw, c.ws(b.h), c.wsf(b.gate), c.wsf(pl->zeros_c), c.wsf(pl->se_gpool_scaled), gw, B, HWo, E, dt, c.st));
+      }
+      TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
+                                    dt, c.st));
+      TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
+    }
+    // depthwise conv backward (data + weights)
+    DwBwdArgs d;
+    d.g = gw; d.y_out = c.ws(b.y2);
+    d.alpha = c.wsf(pl->alpha); d.beta = c.wsf(pl->beta); d.gamma = c.wsf(pl->gammac);
+    d.w_taps = c.pkf(b.pdw); d.dw = c.G(b.wdw);
+    d.B = B; d.H = b.Hin; d.W = b.Win; d.C = E; d.k = b.d.kernel; d.stride = b.d.stride;
+    const void* prev_y = i == 0 ? c.ws(pl->y0) : c.ws(pl->blocks[i - 1].y3);
+    float* prev_bstats = c.wsf(pl->bns[i == 0 ? pl->bn_stem : pl->blocks[i - 1].bn3].bstats);
+    if (b.expand) {
+      Bn& bn1 = pl->bns[b.bn1];
+      d.x = c.ws(b.y1); d.xf = xf_make(c.wsf(bn1.scale), c.wsf(bn1.shift), nullptr, act);
+      d.gx = c.ws(pl->g_wide_b); d.stats = c.wsf(bn1.bstats);
+      TD3D_TRY(launch_dw_bwd(d, dt, c.st));
+      TD3D_TRY(bn_backward(c, b.bn1, HWi, nullptr, nullptr, nullptr));
+      TD3D_TRY(launch_affine2(c.ws(pl->g_wide_b), c.ws(b.y1), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                              c.ws(pl->g_wide_b), B, HWi, E, dt, c.st));
+      GemmTN t = {c.ws(pl->g_wide_b), x_in, c.G(b.w1), Mi, E, b.d.in_ch};
+      TD3D_TRY(gemm_tn(c, t));
+      GemmNT g = {};
+      g.a = c.ws(pl->g_wide_b); g.w = c.pk(b.pw1t); g.y = g_in;
+      g.addend = b.residual ? g_out : nullptr;
+      if (i > 0) { g.ysaved = prev_y; g.stats = prev_bstats; g.slots = B; }
+      g.M = Mi; g.N = b.d.in_ch; g.K = E;
+      TD3D_TRY(gemm_nt(c, g));
+    } else {
+      d.x = x_in; d.xf = xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE);
+      d.gx = g_in; d.stats = nullptr;
+      TD3D_TRY(launch_dw_bwd(d, dt, c.st));
+      if (i > 0) {
+        // previous block output is linear in y3: g_u = g (+ residual), statistics for its BN3
+        TD3D_TRY(launch_act_bwd_stats(g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
+                                      prev_bstats, B, HWi, b.d.in_ch, dt, c.st, b.residual ? g_out : nullptr));
+      } else if (b.residual) {
+        // folded into the stem stage below (needs act'); add the residual gradient now
+        TD3D_TRY(launch_act_bwd_stats(g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
+                                      nullptr, B, HWi, b.d.in_ch, dt, c.st, g_out));
+      }
+    }
+  }
+  if (in_range(nblk + 1)) {
+    // stem: x0 = h_swish(BN(y0)); gradient w.r.t. x0 is in g_narrow[0]
+    Bn& b0 = pl->bns[pl->bn_stem];
+    const int HW1 = pl->H1 * pl->W1;
+    void* g0 = c.ws(pl->g_narrow[0]);
+    TD3D_TRY(launch_act_bwd_stats(g0, nullptr, 1.f, c.ws(pl->y0), xf_make(c.wsf(b0.scale), c.wsf(b0.shift), nullptr, TD3D_ACT_HSWISH),
+                                  g0, c.wsf(b0.bstats), B, HW1, n.stem_ch, dt, c.st));
+    TD3D_TRY(bn_backward(c, pl->bn_stem, HW1, nullptr, nullptr, nullptr));
+    TD3D_TRY(launch_stem_wgrad(pl->last_img, g0, c.ws(pl->y0), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                               c.G(pl->w_stem), B, pl->H, pl->W, n.stem_ch, dt, c.st));
+  }
+  return TD3D_OK;
+}
+
+static int pack_impl(const Ctx& c) {
+  td3d_plan* pl = c.pl;
+  const td3d_net_desc& n = pl->net;
+  const int dt = pl->dtype;
+  TD3D_TRY(launch_transpose_cast(c.P(pl->w_stem), c.pk(pl->p_stem), n.stem_ch, 27, TD3D_F32, c.st));
+  for (auto& b : pl->blocks) {
+    const int E = b.d.exp_ch, kk = b.d.kernel * b.d.kernel;
+    if (b.expand) {
+      TD3D_TRY(launch_cast(c.P(b.w1), c.pk(b.pw1), (int64_t)E * b.d.in_ch, dt, c.st));
+      TD3D_TRY(launch_transpose_cast(c.P(b.w1), c.pk(b.pw1t), E, b.d.in_ch, dt, c.st));
+    }
+    TD3D_TRY(launch_transpose_cast(c.P(b.wdw), c.pk(b.pdw), E, kk, TD3D_F32, c.st));
+    TD3D_TRY(launch_cast(c.P(b.w3), c.pk(b.pw3), (int64_t)E * b.d.out_ch, dt, c.st));
+    TD3D_TRY(launch_transpose_cast(c.P(b.w3), c.pk(b.pw3t), b.d.out_ch, E, dt, c.st));
+  }
+  const int Cl = pl->blocks.back().d.out_ch;
+  TD3D_TRY(launch_cast(c.P(pl->w_last), c.pk(pl->p_last), (int64_t)n.last_ch * Cl, dt, c.st));
+  TD3D_TRY(launch_transpose_cast(c.P(pl->w_last), c.pk(pl->p_lastt), n.last_ch, Cl, dt, c.st));
+  TD3D_TRY(launch_cast(c.P(pl->w_fc), c.pk(pl->p_fc), (int64_t)n.head_ch * n.last_ch, dt, c.st));
+  TD3D_TRY(launch_transpose_cast(c.P(pl->w_fc), c.pk(pl->p_fct), n.head_ch, n.last_ch, dt, c.st));
+  for (auto& bn : pl->bns)
+    TD3D_TRY(launch_bn_eval_fold(c.P(bn.gamma), c.P(bn.beta), pl->BNB + bn.rm, pl->BNB + bn.rm + bn.C, c.pkf(bn.escale),
+                                 c.pkf(bn.eshift), bn.C, BN_EPS, c.st));
+  return TD3D_OK;
+}
+
+}  // namespace td3d
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int td3d_abi_version(void) { return TD3D_ABI_VERSION; }
+const char* td3d_last_error(void) { return g_err; }
+
+int td3d_device_check(void) {
+  int dev = 0;
+  TD3D_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TD3D_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_last_error("device %d is sm_%d%d; td3d kernels are built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    return TD3D_ECUDA;
+  }
+  return TD3D_OK;
+}
+
+int td3d_plan_create(const td3d_net_desc* net, int batch, int height, int width, int dtype, int gemm_impl, td3d_plan** out) {
+  TD3D_REQUIRE(net && out, "plan_create: null argument");
+  TD3D_REQUIRE(batch > 0 && batch <= 65535 && height >= 8 && width >= 8, "plan_create: bad batch/resolution %d %dx%d", batch, height, width);
+  TD3D_REQUIRE(dtype == TD3D_F32 || dtype == TD3D_BF16, "plan_create: bad dtype %d", dtype);
+  TD3D_REQUIRE(net->n_blocks > 0 && net->blocks, "plan_create: no blocks");
+  TD3D_REQUIRE(net->stem_ch == 16, "plan_create: stem_ch must be 16");
+  TD3D_REQUIRE(net->num_points == 18, "plan_create: num_points must be 18 (9 keypoints)");
+  TD3D_REQUIRE(net->num_classes >= 1 && net->num_classes <= 32 && net->max_classes >= 1 && net->max_classes <= 32, "plan_create: bad class counts");
+  TD3D_REQUIRE(net->last_ch % 8 == 0 && net->head_ch % 8 == 0, "plan_create: widths must be multiples of 8");
+  td3d_plan* pl = new td3d_plan();
+  pl->net = *net;
+  pl->block_descs.assign(net->blocks, net->blocks + net->n_blocks);
+  pl->net.blocks = pl->block_descs.data();
+  pl->B = batch; pl->H = height; pl->W = width; pl->dtype = dtype; pl->gemm_impl = gemm_impl;
+  pl->esz = dtype == TD3D_BF16 ? 2 : 4;
+  int rc = build(pl);
+  if (rc != TD3D_OK) { delete pl; return rc; }
+  *out = pl;
+  return TD3D_OK;
+}
+
+void td3d_plan_destroy(td3d_plan* plan) { delete plan; }
+
+int td3d_plan_sizes(const td3d_plan* pl, td3d_sizes* out) {
+  TD3D_REQUIRE(pl && out, "plan_sizes: null argument");
+  out->n_param_tensors = (int64_t)pl->params.size();
+  out->param_floats = pl->param_floats;
+  out->n_bn = (int64_t)pl->bns.size();
+  out->bn_floats = pl->bn_floats;
+  out->packed_bytes = (int64_t)pl->packed_bytes;
+  out->workspace_bytes = (int64_t)pl->ws_bytes;
+  out->head_param_offset = pl->w_reg0;
+  out->head_param_stride = pl->head_stride;
+  return TD3D_OK;
+}
+
+int td3d_plan_param_info(const td3d_plan* pl, int64_t index, td3d_param_info* out) {
+  TD3D_REQUIRE(pl && out && index >= 0 && index < (int64_t)pl->params.size(), "param_info: bad index");
+  *out = pl->params[index].info;
+  return TD3D_OK;
+}
+
+int td3d_plan_bn_info(const td3d_plan* pl, int64_t index, td3d_bn_info* out) {
+  TD3D_REQUIRE(pl && out && index >= 0 && index < (int64_t)pl->bns.size(), "bn_info: bad index");
+  memset(out, 0, sizeof(*out));
+  snprintf(out->name, sizeof(out->name), "%s", pl->bns[index].name.c_str());
+  out->offset = pl->bns[index].rm;
+  out->channels = pl->bns[index].C;
+  return TD3D_OK;
+}
+
+int td3d_plan_bind(td3d_plan* pl, float* params, float* grads, float* bn_stats, int64_t* nbt, void* packed, void* workspace) {
+  TD3D_REQUIRE(pl && params && bn_stats && packed && workspace, "plan_bind: null buffer");
+  TD3D_REQUIRE(((uintptr_t)params & 15) == 0 && ((uintptr_t)packed & 255) == 0 && ((uintptr_t)workspace & 255) == 0,
+               "plan_bind: buffers must be 256-byte aligned");
+  pl->P = params; pl->G = grads; pl->BNB = bn_stats; pl->NBT = nbt;
+  pl->PK = (uint8_t*)packed; pl->WS = (uint8_t*)workspace;
+  return TD3D_OK;
+}
+
+int td3d_plan_set_dropout_counter(td3d_plan* pl, const int32_t* counter) {
+  TD3D_REQUIRE(pl, "set_dropout_counter: null plan");
+  pl->dropout_counter = counter;
+  return TD3D_OK;
+}
+
+#define TD3D_BOUND(pl) TD3D_REQUIRE((pl) && (pl)->P && (pl)->WS, "plan is not bound (call td3d_plan_bind)")
+
+int td3d_pack_weights(td3d_plan* pl, void* stream) {
+  TD3D_BOUND(pl);
+  Ctx c = {pl, (cudaStream_t)stream};
+  return pack_impl(c);
+}
+
+int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const float* dropout_keep, uint64_t seed,
+                 int training, float* kp, float* logits, void* stream) {
+  TD3D_BOUND(pl);
+  TD3D_REQUIRE(img && cats && kp && logits, "forward: null argument");
+  Ctx c = {pl, (cudaStream_t)stream};
+  const void* feat = nullptr;
+  TD3D_TRY(forward_backbone(c, img, training, &feat));
+  HeadsArgs h = heads_args(c, feat, cats, dropout_keep, seed, training);
+  TD3D_TRY(launch_heads_fwd(h, pl->dtype, c.st));
+  TD3D_CUDA(cudaMemcpyAsync(kp, h.kp, sizeof(float) * pl->B * pl->net.num_points, cudaMemcpyDeviceToDevice, c.st));
+  TD3D_CUDA(cudaMemcpyAsync(logits, h.logits, sizeof(float) * pl->B * pl->net.num_classes, cudaMemcpyDeviceToDevice, c.st));
+  pl->last_img = img; pl->last_cats = cats; pl->last_keep = dropout_keep; pl->last_seed = seed; pl->last_training = training;
+  return TD3D_OK;
+}
+
+int td3d_forward_export(td3d_plan* pl, const float* img, float* kp_all, float* logits, int select, float* kp_sel,
+                        int64_t* labels, void* stream) {
+  TD3D_BOUND(pl);
+  TD3D_REQUIRE(img && kp_all && logits, "forward_export: null argument");
+  TD3D_REQUIRE(!select || (kp_sel && labels), "forward_export: select needs kp_sel and labels");
+  Ctx c = {pl, (cudaStream_t)stream};
+  const void* feat = nullptr;
+  TD3D_TRY(forward_backbone(c, img, 0, &feat));
+  HeadsArgs h = heads_args(c, feat, nullptr, nullptr, 0, 0);
+  h.logits = logits;
+  TD3D_TRY(launch_heads_all(h, kp_all, pl->dtype, c.st));
+  if (select)
+    TD3D_TRY(launch_select_argmax(kp_all, logits, kp_sel, labels, pl->B, pl->net.num_points, pl->net.num_classes,
+                                  pl->net.max_classes, c.st));
+  pl->last_training = 0;
+  return TD3D_OK;
+}
+
+int td3d_backward_stages(const td3d_plan* pl) { return pl ? n_stages(pl) : 0; }
+
+int td3d_backward(td3d_plan* pl, const float* d_kp, const float* d_logits, int32_t* head_present, int stage_begin,
+                  int stage_end, void* stream) {
+  TD3D_BOUND(pl);
+  TD3D_REQUIRE(pl->G, "backward: no gradient arena bound");
+  TD3D_REQUIRE(d_kp && d_logits && head_present, "backward: null argument");
+  if (stage_end < 0) stage_end = n_stages(pl);
+  Ctx c = {pl, (cudaStream_t)stream};
+  return backward_impl(c, d_kp, d_logits, head_present, stage_begin, stage_end);
+}
+
+int td3d_backward_ready_range(const td3d_plan* pl, int stage, int64_t* begin, int64_t* end) {
+  TD3D_REQUIRE(pl && begin && end, "ready_range: null argument");
+  const int nblk = (int)pl->blocks.size();
+  TD3D_REQUIRE(stage >= 1 && stage <= nblk + 2, "ready_range: stage out of range");
+  // after stages [0,stage) : tail params, then blocks nblk-1 .. nblk-(stage-1)
+  *end = pl->param_floats;
+  if (stage >= nblk + 2) *begin = 0;
+  else if (stage == 1) *begin = pl->first_param_tail;
+  else *begin = pl->blocks[nblk - (stage - 1)].first_param;
+  return TD3D_OK;
+}
+
+int td3d_loss_fwd_bwd(const td3d_loss_desc* desc, const float* kp, const float* gt_kp, const float* logits,
+                      const int64_t* cats, int batch, int num_classes, float* loss_out, float* d_kp, float* d_logits,
+                      void* stream) {
+  TD3D_REQUIRE(desc && kp && gt_kp && loss_out, "loss: null argument");
+  return launch_loss(*desc, kp, gt_kp, logits, cats, batch, num_classes, loss_out, d_kp, d_logits, (cudaStream_t)stream);
+}
+
+int td3d_metrics_accum(const float* kp, const float* gt_kp, const float* logits, const int64_t* cats, int batch,
+                       int num_classes, int max_classes, double* acc, void* stream) {
+  TD3D_REQUIRE(kp && gt_kp && cats && acc, "metrics: null argument");
+  return launch_metrics(kp, gt_kp, logits, cats, batch, num_classes, max_classes, acc, (cudaStream_t)stream);
+}
+
+int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, float* state1, int32_t* steps,
+                    const int32_t* head_present, void* stream) {
+  TD3D_BOUND(pl);
+  TD3D_REQUIRE(desc && state0 && steps && pl->G, "optim_step: null argument");
+  TD3D_REQUIRE(desc->kind >= TD3D_OPT_SGD && desc->kind <= TD3D_OPT_ADADELTA, "optim_step: unknown optimizer %d", desc->kind);
+  TD3D_REQUIRE(!(desc->kind == TD3D_OPT_ADAMW || desc->kind == TD3D_OPT_ADADELTA) || state1, "optim_step: state1 required");
+  OptimArgs a;
+  a.d = *desc;
+  a.p = pl->P; a.g = pl->G; a.s0 = state0; a.s1 = state1; a.n = pl->param_floats;
+  a.head_off = pl->w_reg0; a.head_stride = pl->head_stride; a.n_heads = pl->net.max_classes;
+  a.steps = steps; a.present = head_present;
+  Ctx c = {pl, (cudaStream_t)stream};
+  TD3D_TRY(launch_optim(a, c.st));
+  return pack_impl(c);
+}
+
+// ---- per-kernel entry points ----------------------------------------------------------------
+int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W, int C, int dtype,
+                    void* stream) {
+  return launch_stem_fwd(img, w27x16, y, stats, B, H, W, C, dtype, (cudaStream_t)stream);
+}
+int td3d_k_stem_wgrad(const float* img, const void* g, const void* y, const float* alpha, const float* beta,
+                      const float* gamma, float* dw, int B, int H, int W, int C, int dtype, void* stream) {
+  return launch_stem_wgrad(img, g, y, alpha, beta, gamma, dw, B, H, W, C, dtype, (cudaStream_t)stream);
+}
+int td3d_k_dw_fwd(const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
+                  void* y, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, void* stream) {
+  DwArgs a;
+  a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.y = y; a.stats = stats;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
+  return launch_dw_fwd(a, dtype, (cudaStream_t)stream);
+}
+int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const float* beta, const float* gamma,
+                  const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
+                  void* gx, float* dw, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, void* stream) {
+  DwBwdArgs a;
+  a.g = g; a.y_out = y_out; a.alpha = alpha; a.beta = beta; a.gamma = gamma;
+  a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.gx = gx; a.stats = stats; a.dw = dw;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
+  return launch_dw_bwd(a, dtype, (cudaStream_t)stream);
+}
+int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias, const void* ysaved,
+                   float* stats, int stat_slots, int M, int N, int K, int dtype, int out_f32, int impl, void* stream) {
+  GemmNT g = {};
+  g.a = a; g.w = w; g.y = y; g.addend = addend; g.bias = bias; g.ysaved = ysaved; g.stats = stats; g.slots = stat_slots;
+  g.M = M; g.N = N; g.K = K; g.out_f32 = out_f32;
+  if (impl == TD3D_GEMM_TCGEN05) {
+    TD3D_REQUIRE(dtype == TD3D_BF16, "tcgen05 GEMM is bf16 only");
+    return launch_gemm_nt_tc(g, (cudaStream_t)stream);
+  }
+  return launch_gemm_nt_simt(g, dtype, (cudaStream_t)stream);
+}
+int td3d_k_gemm_tn(const void* a, const void* b, float* c, int M, int N1, int N2, int dtype, int impl, void* stream) {
+  GemmTN g = {a, b, c, M, N1, N2};
+  if (impl == TD3D_GEMM_TCGEN05) {
+    TD3D_REQUIRE(dtype == TD3D_BF16, "tcgen05 GEMM is bf16 only");
+    return launch_gemm_tn_tc(g, (cudaStream_t)stream);
+  }
+  return launch_gemm_tn_simt(g, dtype, (cudaStream_t)stream);
+}
+int td3d_k_apply_xform(const void* y, const float* scale, const float* shift, const float* se, int act, const void* res,
+                       void* out, float* pool_stats, int B, int HW, int C, int dtype, void* stream) {
+  return launch_apply_xform(y, xf_make(scale, shift, se, act), res, out, pool_stats, B, HW, C, dtype, (cudaStream_t)stream);
+}
+int td3d_k_affine2(const void* g, const void* y, const float* alpha, const float* beta, const float* gamma, void* out,
+                   int B, int HW, int C, int dtype, void* stream) {
+  return launch_affine2(g, y, alpha, beta, gamma, out, B, HW, C, dtype, (cudaStream_t)stream);
+}
+int td3d_k_act_bwd_stats(const void* g, const void* y, const float* scale, const float* shift, const float* se, int act,
+                         void* gu, float* stats, int B, int HW, int C, int dtype, void* stream) {
+  return launch_act_bwd_stats(g, nullptr, 1.f, y, xf_make(scale, shift, se, act), gu, stats, B, HW, C, dtype,
+                              (cudaStream_t)stream, nullptr);
+}
+
+}  // extern "C"

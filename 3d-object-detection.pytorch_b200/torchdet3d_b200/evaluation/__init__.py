@@ -1,0 +1,4 @@
+from .metrics import (compute_average_distance, compute_accuracy, compute_metrics_per_cls, MetricAccumulator)
+from .evaluate import Evaluator
+
+__all__ = ["compute_average_distance", "compute_accuracy", "compute_metrics_per_cls", "MetricAccumulator", "Evaluator"]
