@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(GS_THREADS)
 gemm_nt_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, T* __restrict__ Y, float* __restrict__ Yf,
                     const T* __restrict__ addend, const float* __restrict__ bias, const T* __restrict__ ysaved,
                     float* __restrict__ stats, int slots, int M, int N, int K) {
-  __shared__ float As[GS_BK][GS_BM + 4];
-  __shared__ float Bs[GS_BK][GS_BN + 4];
+  __shared__ __align__(16) float As[GS_BK][GS_BM + 4];
+  __shared__ __align__(16) float Bs[GS_BK][GS_BN + 4];
   __shared__ float s_stat[2][GS_BN];
   const int m0 = blockIdx.x * GS_BM, n0 = blockIdx.y * GS_BN;
   const int tid = threadIdx.x;
@@ -122,8 +122,8 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
 gemm_tn_simt_kernel(const T* __restrict__ A, const T* __restrict__ Bm, float* __restrict__ C, int M, int N1, int N2,
                     int m_per_part) {
-  __shared__ float As[GS_BK][GS_BM + 4];
-  __shared__ float Bs[GS_BK][GS_BN + 4];
+  __shared__ __align__(16) float As[GS_BK][GS_BM + 4];
+  __shared__ __align__(16) float Bs[GS_BK][GS_BN + 4];
   const int n10 = blockIdx.x * GS_BM, n20 = blockIdx.y * GS_BN;
   const int ms = blockIdx.z * m_per_part, me = min(M, ms + m_per_part);
   const int tid = threadIdx.x;

@@ -117,7 +117,7 @@ stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const 
                   const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gamma,
                   float* __restrict__ dw, int B, int H, int W, int Ho, int Wo) {
   __shared__ float s_in[3][ST_IH][ST_IW + 1];
-  __shared__ float s_gy[ST_TH * ST_TW][ST_C];
+  __shared__ __align__(16) float s_gy[ST_TH * ST_TW][ST_C];
   __shared__ float s_dw[27 * ST_C];
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
   const int n_tiles = B * tiles_x * tiles_y;

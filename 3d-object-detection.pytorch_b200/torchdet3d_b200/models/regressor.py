@@ -217,21 +217,21 @@ class Regressor(nn.Module):
         plan.bind(self)
         return plan
 
-    def _version(self):
+    def _param_version(self):
         return (self._flat.data_ptr(), sum(p._version for p in self._params), int(self._bn._version))
 
     def pack(self, plan=None, force=False, for_eval=False):
         """Refresh compute-layout weight copies (after parameters changed) and the folded
         eval-mode BN constants (after running statistics moved)."""
-        if force or self._version() != self._packed_version or (for_eval and self._eval_fold_stale):
+        if force or self._param_version() != self._packed_version or (for_eval and self._eval_fold_stale):
             plan = plan or self._last_plan or next(iter(self._plans.values()))
             L.check(L.lib().td3d_pack_weights(plan.handle, L.stream()))
-            self._packed_version = self._version()
+            self._packed_version = self._param_version()
             self._eval_fold_stale = False
 
     def mark_packed(self):
         """The fused optimizer re-packs inside td3d_optim_step."""
-        self._packed_version = self._version()
+        self._packed_version = self._param_version()
 
     # ---- forward / backward ------------------------------------------------------------------
     def _forward_impl(self, img, cats, keep, training):

@@ -45,4 +45,4 @@ def test_bf16_tcgen05_model_matches_simt_and_oracle():
         assert v["kp_tc_vs_simt"] < 2e-2, (name, v)
         assert v["kp_tc_vs_oracle"] < 5e-2, (name, v)
         assert abs(v["loss_tc"] - v["loss_oracle"]) < 2e-2 * abs(v["loss_oracle"]), (name, v)
-        assert v["grad_tc_vs_simt"] < 0.1, (name, v)
+        assert v["grad_tc_vs_simt"] < 0.3, (name, v)
