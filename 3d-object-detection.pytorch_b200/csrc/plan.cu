@@ -61,6 +61,19 @@ struct Param {
   td3d_param_info info;
 };
 
+// Optional per-launch timing (CUDA events on the launching stream) + algorithmic byte counts, by
+// kernel kind. Used by bench.py for the roofline of the dominant kernel; off by default.
+enum ProfKind { PK_STEM_FWD, PK_STEM_WGRAD, PK_GEMM_FWD, PK_GEMM_DGRAD, PK_GEMM_WGRAD, PK_DW_FWD, PK_DW_BWD,
+                PK_BN, PK_XFORM, PK_AFFINE2, PK_ACT_BWD, PK_SE, PK_HEADS, PK_POOL, PK_OPTIM, PK_PACK, PK_COUNT };
+static const char* const kProfNames[PK_COUNT] = {
+    "stem_fwd", "stem_wgrad", "gemm_fwd", "gemm_dgrad", "gemm_wgrad", "dw_fwd", "dw_bwd", "bn_finalize",
+    "apply_xform", "affine2", "act_bwd_stats", "se_fc", "heads", "pool", "optimizer", "pack_weights"};
+struct ProfRec { int kind; double bytes; cudaEvent_t e0, e1; };
+struct Prof {
+  bool enabled = false;
+  std::vector<ProfRec> recs;
+};
+
 }  // namespace td3d
 
 using namespace td3d;
@@ -95,6 +108,7 @@ struct td3d_plan {
   const float* last_img = nullptr; const int64_t* last_cats = nullptr; const float* last_keep = nullptr;
   uint64_t last_seed = 0; int last_training = 0;
   const int32_t* dropout_counter = nullptr;
+  Prof prof;
 };
 
 namespace td3d {
@@ -305,7 +319,63 @@ struct Ctx {
   float* pkf(size_t off) const { return reinterpret_cast<float*>(pl->PK + off); }
   float* P(int64_t off) const { return pl->P + off; }
   float* G(int64_t off) const { return pl->G + off; }
+  void pb(int kind, double bytes) const {
+    if (!pl->prof.enabled) return;
+    ProfRec r; r.kind = kind; r.bytes = bytes;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    pl->prof.recs.push_back(r);
+  }
+  void pe() const {
+    if (!pl->prof.enabled) return;
+    cudaEventRecord(pl->prof.recs.back().e1, st);
+  }
+  double esz() const { return (double)pl->esz; }
 };
+
+// run a launcher under the profiler: K = kind, BYTES = algorithmic bytes this launch must move
+#define TD3D_K(K, BYTES, expr)        \
+  do {                                \
+    c.pb((K), (double)(BYTES));       \
+    int _rc = (expr);                 \
+    c.pe();                           \
+    if (_rc != TD3D_OK) return _rc;   \
+  } while (0)
+
+
+// ---- profiled launch wrappers (algorithmic bytes = what the op must move at minimum) -----------
+static int p_xform(const Ctx& c, const void* y, const XForm& xf, const void* res, void* out, float* pool, int B, int HW,
+                   int C, int dt, cudaStream_t st) {
+  double n = (double)B * HW * C;
+  TD3D_K(out ? PK_XFORM : PK_POOL, n * c.esz() * (1 + (res ? 1 : 0) + (out ? 1 : 0)),
+         launch_apply_xform(y, xf, res, out, pool, B, HW, C, dt, st));
+  return TD3D_OK;
+}
+static int p_affine2(const Ctx& c, const void* g, const void* y, const float* al, const float* be, const float* ga,
+                     void* out, int B, int HW, int C, int dt, cudaStream_t st) {
+  TD3D_K(PK_AFFINE2, 3.0 * B * HW * C * c.esz(), launch_affine2(g, y, al, be, ga, out, B, HW, C, dt, st));
+  return TD3D_OK;
+}
+static int p_actbwd(const Ctx& c, const void* g, const float* gp, float gs, const void* y, const XForm& xf, void* gu,
+                    float* stats, int B, int HW, int C, int dt, cudaStream_t st, const void* addend = nullptr) {
+  double n = (double)B * HW * C;
+  TD3D_K(PK_ACT_BWD, n * c.esz() * (2 + (g ? 1 : 0) + (addend ? 1 : 0)),
+         launch_act_bwd_stats(g, gp, gs, y, xf, gu, stats, B, HW, C, dt, st, addend));
+  return TD3D_OK;
+}
+static int p_dwf(const Ctx& c, const DwArgs& a, int dt, cudaStream_t st) {
+  int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
+  double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
+  TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd(a, dt, st));
+  return TD3D_OK;
+}
+static int p_dwb(const Ctx& c, const DwBwdArgs& a, int dt, cudaStream_t st) {
+  int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
+  double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
+  // fused ideal: read g, y_out, x once; write gx once
+  TD3D_K(PK_DW_BWD, (2 * out + 2 * in) * c.esz(), launch_dw_bwd(a, dt, st));
+  return TD3D_OK;
+}
 
 static bool use_tc(const td3d_plan* pl, int M, int N, int K) {
   if (pl->dtype != TD3D_BF16) return false;
@@ -313,14 +383,22 @@ static bool use_tc(const td3d_plan* pl, int M, int N, int K) {
   return tc_gemm_supported(M, N, K);
 }
 
-static int gemm_nt(const Ctx& c, GemmNT g) {
-  if (use_tc(c.pl, g.M, g.N, g.K)) return launch_gemm_nt_tc(g, c.st);
-  return launch_gemm_nt_simt(g, c.pl->dtype, c.st);
+static int gemm_nt(const Ctx& c, GemmNT g, int kind = PK_GEMM_FWD) {
+  double e = c.esz();
+  double bytes = ((double)g.M * g.K + (double)g.N * g.K) * e + (double)g.M * g.N * (g.out_f32 ? 4.0 : e) +
+                 (double)g.M * g.N * e * ((g.addend ? 1 : 0) + (g.ysaved ? 1 : 0));
+  if (use_tc(c.pl, g.M, g.N, g.K)) { TD3D_K(kind, bytes, launch_gemm_nt_tc(g, c.st)); }
+  else { TD3D_K(kind, bytes, launch_gemm_nt_simt(g, c.pl->dtype, c.st)); }
+  return TD3D_OK;
 }
 static int gemm_tn(const Ctx& c, GemmTN g) {
-  if (c.pl->dtype == TD3D_BF16 && c.pl->gemm_impl != TD3D_GEMM_SIMT && g.N1 % 8 == 0 && g.N2 % 8 == 0)
-    return launch_gemm_tn_tc(g, c.st);
-  return launch_gemm_tn_simt(g, c.pl->dtype, c.st);
+  double bytes = ((double)g.M * g.N1 + (double)g.M * g.N2) * c.esz() + 4.0 * g.N1 * g.N2;
+  if (c.pl->dtype == TD3D_BF16 && c.pl->gemm_impl != TD3D_GEMM_SIMT && g.N1 % 8 == 0 && g.N2 % 8 == 0) {
+    TD3D_K(PK_GEMM_WGRAD, bytes, launch_gemm_tn_tc(g, c.st));
+  } else {
+    TD3D_K(PK_GEMM_WGRAD, bytes, launch_gemm_tn_simt(g, c.pl->dtype, c.st));
+  }
+  return TD3D_OK;
 }
 
 // BatchNorm after a conv: training -> finalize batch statistics (and update running stats);
@@ -335,7 +413,7 @@ static int bn_forward(const Ctx& c, int idx, double count, int training, const f
     a.nbt = c.pl->NBT ? c.pl->NBT + idx : nullptr;
     a.scale = c.wsf(bn.scale); a.shift = c.wsf(bn.shift); a.mean = c.wsf(bn.mean); a.invstd = c.wsf(bn.invstd);
     a.C = bn.C; a.momentum = BN_MOMENTUM; a.eps = BN_EPS;
-    TD3D_TRY(launch_bn_finalize_fwd(a, c.st));
+    TD3D_K(PK_BN, 8.0 * c.pl->B * bn.C, launch_bn_finalize_fwd(a, c.st));
     *scale = a.scale; *shift = a.shift;
   } else {
     *scale = c.pkf(bn.escale); *shift = c.pkf(bn.eshift);
@@ -356,9 +434,9 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   const float *sc, *sh;
   // stem
   Bn& b0 = pl->bns[pl->bn_stem];
-  TD3D_TRY(launch_stem_fwd(img, c.pkf(pl->p_stem), c.ws(pl->y0), c.wsf(b0.fstats), B, pl->H, pl->W, n.stem_ch, dt, c.st));
+  TD3D_K(PK_STEM_FWD, (double)B * 3 * pl->H * pl->W * 4 + (double)B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_fwd(img, c.pkf(pl->p_stem), c.ws(pl->y0), c.wsf(b0.fstats), B, pl->H, pl->W, n.stem_ch, dt, c.st));
   TD3D_TRY(bn_forward(c, pl->bn_stem, (double)B * pl->H1 * pl->W1, training, &sc, &sh));
-  TD3D_TRY(launch_apply_xform(c.ws(pl->y0), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->x0), nullptr,
+  TD3D_TRY(p_xform(c, c.ws(pl->y0), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->x0), nullptr,
                               B, pl->H1 * pl->W1, n.stem_ch, dt, c.st));
   const void* cur = c.ws(pl->x0);
   for (auto& b : pl->blocks) {
@@ -380,7 +458,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     }
     dw.w_taps = c.pkf(b.pdw); dw.y = c.ws(b.y2); dw.stats = c.wsf(pl->bns[b.bn2].fstats);
     dw.B = B; dw.H = b.Hin; dw.W = b.Win; dw.C = E; dw.k = b.d.kernel; dw.stride = b.d.stride;
-    TD3D_TRY(launch_dw_fwd(dw, dt, c.st));
+    TD3D_TRY(p_dwf(c, dw, dt, c.st));
     TD3D_TRY(bn_forward(c, b.bn2, (double)Mo, training, &sc, &sh));
     if (b.d.use_se) {
       SeArgs s;
@@ -389,16 +467,16 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
       s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
       if (b.expand) {      // BN -> SE -> act (mobilenetv3.py:153-156): squeeze from the dw epilogue sums
         s.pool_stats = c.wsf(pl->bns[b.bn2].fstats); s.scale = sc; s.shift = sh;
-        TD3D_TRY(launch_se_fwd(s, c.st));
-        TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, s.gate, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+        TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, s.gate, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
       } else {             // BN -> act -> SE (mobilenetv3.py:137-140)
-        TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h), c.wsf(b.hstats), B, HWo, E, dt, c.st));
+        TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h), c.wsf(b.hstats), B, HWo, E, dt, c.st));
         s.pool_stats = c.wsf(b.hstats); s.scale = nullptr; s.shift = nullptr;
-        TD3D_TRY(launch_se_fwd(s, c.st));
-        TD3D_TRY(launch_apply_xform(c.ws(b.h), xf_make(nullptr, nullptr, s.gate, TD3D_ACT_NONE), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+        TD3D_TRY(p_xform(c, c.ws(b.h), xf_make(nullptr, nullptr, s.gate, TD3D_ACT_NONE), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
       }
     } else {
-      TD3D_TRY(launch_apply_xform(c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+      TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
     }
     GemmNT g = {};
     g.a = c.ws(b.h2); g.w = c.pk(b.pw3); g.y = c.ws(b.y3);
@@ -406,7 +484,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     g.M = Mo; g.N = b.d.out_ch; g.K = E;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, b.bn3, (double)Mo, training, &sc, &sh));
-    TD3D_TRY(launch_apply_xform(c.ws(b.y3), xf_make(sc, sh, nullptr, TD3D_ACT_NONE), b.residual ? cur : nullptr,
+    TD3D_TRY(p_xform(c, c.ws(b.y3), xf_make(sc, sh, nullptr, TD3D_ACT_NONE), b.residual ? cur : nullptr,
                                 c.ws(b.out), nullptr, B, HWo, b.d.out_ch, dt, c.st));
     cur = c.ws(b.out);
   }
@@ -420,9 +498,9 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     g.M = Ml; g.N = n.last_ch; g.K = Cl;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, pl->bn_last, (double)Ml, training, &sc, &sh));
-    TD3D_TRY(launch_apply_xform(c.ws(pl->yc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, nullptr,
+    TD3D_TRY(p_xform(c, c.ws(pl->yc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, nullptr,
                                 c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
-    TD3D_TRY(launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
+    TD3D_K(PK_POOL, 8.0 * B * n.last_ch, launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
   }
   // classifier: Linear -> BatchNorm1d -> h_swish (mobilenetv3.py:191-195)
   {
@@ -432,7 +510,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     g.M = B; g.N = n.head_ch; g.K = n.last_ch;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, pl->bn_fc, (double)B, training, &sc, &sh));
-    TD3D_TRY(launch_apply_xform(c.ws(pl->yfc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->feat), nullptr,
+    TD3D_TRY(p_xform(c, c.ws(pl->yfc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->feat), nullptr,
                                 B, 1, n.head_ch, dt, c.st));
   }
   *feat_out = c.ws(pl->feat);
@@ -464,7 +542,8 @@ static int bn_backward(const Ctx& c, int idx, int HW, const float* se, const flo
   a.alpha = c.wsf(pl->alpha); a.beta = c.wsf(pl->beta); a.gammac = c.wsf(pl->gammac);
   a.dgamma = c.G(bn.gamma); a.dbeta = c.G(bn.beta);
   a.B = pl->B; a.HW = HW; a.C = bn.C;
-  return launch_bn_bwd_finalize(a, c.st);
+  TD3D_K(PK_BN, 8.0 * pl->B * bn.C, launch_bn_bwd_finalize(a, c.st));
+  return TD3D_OK;
 }
 
 __global__ void colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
@@ -509,17 +588,17 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     hb.g_pre = c.wsf(pl->g_pre_heads); hb.g_feat = c.wsf(pl->g_feat);
     hb.dw_reg = c.G(pl->w_reg0); hb.dw_cls = c.G(pl->w_cls); hb.db_cls = c.G(pl->b_cls);
     hb.present = present;
-    TD3D_TRY(launch_heads_bwd(hb, dt, c.st));
+    TD3D_K(PK_HEADS, 8.0 * B * n.head_ch, launch_heads_bwd(hb, dt, c.st));
     // classifier: feat = h_swish(BN1d(yfc))
     Bn& bfc = pl->bns[pl->bn_fc];
     XForm xfc = xf_make(c.wsf(bfc.scale), c.wsf(bfc.shift), nullptr, TD3D_ACT_HSWISH);
-    TD3D_TRY(launch_act_bwd_stats(nullptr, c.wsf(pl->g_feat), 1.f, c.ws(pl->yfc), xfc, c.ws(pl->g_wide_a), c.wsf(bfc.bstats),
+    TD3D_TRY(p_actbwd(c, nullptr, c.wsf(pl->g_feat), 1.f, c.ws(pl->yfc), xfc, c.ws(pl->g_wide_a), c.wsf(bfc.bstats),
                                   B, 1, n.head_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_fc, 1, nullptr, nullptr, nullptr));
     colsum_kernel<<<ceil_div(n.head_ch, 128), 128, 0, c.st>>>(c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                                                               c.wsf(bfc.bstats), c.wsf(bfc.fstats), c.G(pl->b_fc), B, n.head_ch);
     TD3D_LAUNCH_CHECK();
-    TD3D_TRY(launch_affine2(c.ws(pl->g_wide_a), c.ws(pl->yfc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+    TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_a), c.ws(pl->yfc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                             c.ws(pl->g_wide_a), B, 1, n.head_ch, dt, c.st));
     {
       GemmTN t = {c.ws(pl->g_wide_a), c.ws(pl->pooled), c.G(pl->w_fc), B, n.head_ch, n.last_ch};
@@ -527,15 +606,15 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       GemmNT g = {};
       g.a = c.ws(pl->g_wide_a); g.w = c.pk(pl->p_fct); g.y = c.wsf(pl->g_pool_f); g.out_f32 = 1;
       g.M = B; g.N = n.last_ch; g.K = n.head_ch;
-      TD3D_TRY(gemm_nt(c, g));
+      TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
     // avg-pool backward + h_swish + BN of the final conv
     Bn& bl = pl->bns[pl->bn_last];
     XForm xl = xf_make(c.wsf(bl.scale), c.wsf(bl.shift), nullptr, TD3D_ACT_HSWISH);
-    TD3D_TRY(launch_act_bwd_stats(nullptr, c.wsf(pl->g_pool_f), 1.f / (float)HWl, c.ws(pl->yc), xl, c.ws(pl->g_wide_a),
+    TD3D_TRY(p_actbwd(c, nullptr, c.wsf(pl->g_pool_f), 1.f / (float)HWl, c.ws(pl->yc), xl, c.ws(pl->g_wide_a),
                                   c.wsf(bl.bstats), B, HWl, n.last_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_last, HWl, nullptr, nullptr, nullptr));
-    TD3D_TRY(launch_affine2(c.ws(pl->g_wide_a), c.ws(pl->yc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+    TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_a), c.ws(pl->yc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                             c.ws(pl->g_wide_a), B, HWl, n.last_ch, dt, c.st));
     {
       Block& lb = pl->blocks.back();
@@ -545,7 +624,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       g.a = c.ws(pl->g_wide_a); g.w = c.pk(pl->p_lastt); g.y = c.ws(pl->g_narrow[nblk & 1]);
       g.ysaved = c.ws(lb.y3); g.stats = c.wsf(pl->bns[lb.bn3].bstats); g.slots = B;
       g.M = Ml; g.N = Cl; g.K = n.last_ch;
-      TD3D_TRY(gemm_nt(c, g));
+      TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
   }
   // blocks, last to first. Gradient w.r.t. the output of block i lives in g_narrow[(i+1)&1].
@@ -561,7 +640,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     const void* x_in = i == 0 ? c.ws(pl->x0) : c.ws(pl->blocks[i - 1].out);
     // BN3 (linear): g_y3 = alpha*g_out + beta*y3 + gamma
     TD3D_TRY(bn_backward(c, b.bn3, HWo, nullptr, nullptr, nullptr));
-    TD3D_TRY(launch_affine2(g_out, c.ws(b.y3), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac), c.ws(pl->g_y3), B,
+    TD3D_TRY(p_affine2(c, g_out, c.ws(b.y3), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac), c.ws(pl->g_y3), B,
                             HWo, b.d.out_ch, dt, c.st));
     {
       GemmTN t = {c.ws(pl->g_y3), c.ws(b.h2), c.G(b.w3), Mo, b.d.out_ch, E};
@@ -569,7 +648,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       GemmNT g = {};
       g.a = c.ws(pl->g_y3); g.w = c.pk(b.pw3t); g.y = c.ws(pl->g_wide_a);
       g.M = Mo; g.N = E; g.K = b.d.out_ch;
-      TD3D_TRY(gemm_nt(c, g));
+      TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
     Bn& bn2 = pl->bns[b.bn2];
     const float* sc2 = c.wsf(bn2.scale);
@@ -577,7 +656,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     void* gw = c.ws(pl->g_wide_a);
     if (b.expand) {
       const float* gate = b.d.use_se ? c.wsf(b.gate) : nullptr;
-      TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, gate, act), gw, c.wsf(bn2.bstats), B, HWo,
+      TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, gate, act), gw, c.wsf(bn2.bstats), B, HWo,
                                     E, dt, c.st));
       if (b.d.use_se) {
         SeBwdArgs s;
@@ -587,7 +666,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
         s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
         s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
         s.B = B; s.C = E; s.Ch = b.d.se_hidden;
-        TD3D_TRY(launch_se_bwd(s, c.st));
+        TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, launch_se_bwd(s, c.st));
         TD3D_TRY(bn_backward(c, b.bn2, HWo, gate, c.wsf(pl->se_gpool), c.wsf(bn2.fstats)));
       } else {
         TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
@@ -595,7 +674,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     } else {
       if (b.d.use_se) {
         // x = H * gate with H = act(BN(y2)):  g_H = gate*g_x + g_pool/HW
-        TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.h), xf_make(nullptr, nullptr, c.wsf(b.gate), TD3D_ACT_NONE), gw,
+        TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.h), xf_make(nullptr, nullptr, c.wsf(b.gate), TD3D_ACT_NONE), gw,
                                       c.wsf(b.hbstats), B, HWo, E, dt, c.st));
         SeBwdArgs s;
         s.bwd_stats = c.wsf(b.hbstats); s.scale = nullptr; s.shift = nullptr; s.inv_hw = 1.f / (float)HWo;
@@ -604,13 +683,13 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
         s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
         s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
         s.B = B; s.C = E; s.Ch = b.d.se_hidden;
-        TD3D_TRY(launch_se_bwd(s, c.st));
+        TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, launch_se_bwd(s, c.st));
         scale_kernel<<<ceil_div(B * E, 256), 256, 0, c.st>>>(c.wsf(pl->se_gpool), 1.f / (float)HWo, c.wsf(pl->se_gpool_scaled), B * E);
         TD3D_LAUNCH_CHECK();
         TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->zeros_c), 0, sizeof(float) * E, c.st));
-        TD3D_TRY(launch_affine2(gw, c.ws(b.h), c.wsf(b.gate), c.wsf(pl->zeros_c), c.wsf(pl->se_gpool_scaled), gw, B, HWo, E, dt, c.st));
+        TD3D_TRY(p_affine2(c, gw, c.ws(b.h), c.wsf(b.gate), c.wsf(pl->zeros_c), c.wsf(pl->se_gpool_scaled), gw, B, HWo, E, dt, c.st));
       }
-      TD3D_TRY(launch_act_bwd_stats(gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
+      TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
                                     dt, c.st));
       TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
     }
@@ -626,9 +705,9 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       Bn& bn1 = pl->bns[b.bn1];
       d.x = c.ws(b.y1); d.xf = xf_make(c.wsf(bn1.scale), c.wsf(bn1.shift), nullptr, act);
       d.gx = c.ws(pl->g_wide_b); d.stats = c.wsf(bn1.bstats);
-      TD3D_TRY(launch_dw_bwd(d, dt, c.st));
+      TD3D_TRY(p_dwb(c, d, dt, c.st));
       TD3D_TRY(bn_backward(c, b.bn1, HWi, nullptr, nullptr, nullptr));
-      TD3D_TRY(launch_affine2(c.ws(pl->g_wide_b), c.ws(b.y1), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+      TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_b), c.ws(b.y1), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                               c.ws(pl->g_wide_b), B, HWi, E, dt, c.st));
       GemmTN t = {c.ws(pl->g_wide_b), x_in, c.G(b.w1), Mi, E, b.d.in_ch};
       TD3D_TRY(gemm_tn(c, t));
@@ -637,18 +716,18 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       g.addend = b.residual ? g_out : nullptr;
       if (i > 0) { g.ysaved = prev_y; g.stats = prev_bstats; g.slots = B; }
       g.M = Mi; g.N = b.d.in_ch; g.K = E;
-      TD3D_TRY(gemm_nt(c, g));
+      TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     } else {
       d.x = x_in; d.xf = xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE);
       d.gx = g_in; d.stats = nullptr;
-      TD3D_TRY(launch_dw_bwd(d, dt, c.st));
+      TD3D_TRY(p_dwb(c, d, dt, c.st));
       if (i > 0) {
         // previous block output is linear in y3: g_u = g (+ residual), statistics for its BN3
-        TD3D_TRY(launch_act_bwd_stats(g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
+        TD3D_TRY(p_actbwd(c, g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
                                       prev_bstats, B, HWi, b.d.in_ch, dt, c.st, b.residual ? g_out : nullptr));
       } else if (b.residual) {
         // folded into the stem stage below (needs act'); add the residual gradient now
-        TD3D_TRY(launch_act_bwd_stats(g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
+        TD3D_TRY(p_actbwd(c, g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
                                       nullptr, B, HWi, b.d.in_ch, dt, c.st, g_out));
       }
     }
@@ -658,10 +737,10 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     Bn& b0 = pl->bns[pl->bn_stem];
     const int HW1 = pl->H1 * pl->W1;
     void* g0 = c.ws(pl->g_narrow[0]);
-    TD3D_TRY(launch_act_bwd_stats(g0, nullptr, 1.f, c.ws(pl->y0), xf_make(c.wsf(b0.scale), c.wsf(b0.shift), nullptr, TD3D_ACT_HSWISH),
+    TD3D_TRY(p_actbwd(c, g0, nullptr, 1.f, c.ws(pl->y0), xf_make(c.wsf(b0.scale), c.wsf(b0.shift), nullptr, TD3D_ACT_HSWISH),
                                   g0, c.wsf(b0.bstats), B, HW1, n.stem_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_stem, HW1, nullptr, nullptr, nullptr));
-    TD3D_TRY(launch_stem_wgrad(pl->last_img, g0, c.ws(pl->y0), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+    TD3D_K(PK_STEM_WGRAD, (double)B * 3 * pl->H * pl->W * 4 + 2.0 * B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_wgrad(pl->last_img, g0, c.ws(pl->y0), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                                c.G(pl->w_stem), B, pl->H, pl->W, n.stem_ch, dt, c.st));
   }
   return TD3D_OK;
@@ -781,6 +860,29 @@ int td3d_plan_set_dropout_counter(td3d_plan* pl, const int32_t* counter) {
   return TD3D_OK;
 }
 
+int td3d_plan_profile(td3d_plan* pl, int enable) {
+  TD3D_REQUIRE(pl, "plan_profile: null plan");
+  for (auto& r : pl->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  pl->prof.recs.clear();
+  pl->prof.enabled = enable != 0;
+  return TD3D_OK;
+}
+
+int td3d_plan_profile_read(td3d_plan* pl, int kind, char* name, int name_cap, double* ms, double* bytes, int64_t* launches) {
+  TD3D_REQUIRE(pl && ms && bytes && launches, "profile_read: null argument");
+  if (kind < 0 || kind >= PK_COUNT) return 1;   // end of table
+  if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", kProfNames[kind]);
+  *ms = 0; *bytes = 0; *launches = 0;
+  for (auto& r : pl->prof.recs) {
+    if (r.kind != kind) continue;
+    TD3D_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    TD3D_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    *ms += t; *bytes += r.bytes; *launches += 1;
+  }
+  return TD3D_OK;
+}
+
 #define TD3D_BOUND(pl) TD3D_REQUIRE((pl) && (pl)->P && (pl)->WS, "plan is not bound (call td3d_plan_bind)")
 
 int td3d_pack_weights(td3d_plan* pl, void* stream) {
@@ -797,7 +899,7 @@ int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const flo
   const void* feat = nullptr;
   TD3D_TRY(forward_backbone(c, img, training, &feat));
   HeadsArgs h = heads_args(c, feat, cats, dropout_keep, seed, training);
-  TD3D_TRY(launch_heads_fwd(h, pl->dtype, c.st));
+  TD3D_K(PK_HEADS, 4.0 * pl->B * pl->net.head_ch, launch_heads_fwd(h, pl->dtype, c.st));
   TD3D_CUDA(cudaMemcpyAsync(kp, h.kp, sizeof(float) * pl->B * pl->net.num_points, cudaMemcpyDeviceToDevice, c.st));
   TD3D_CUDA(cudaMemcpyAsync(logits, h.logits, sizeof(float) * pl->B * pl->net.num_classes, cudaMemcpyDeviceToDevice, c.st));
   pl->last_img = img; pl->last_cats = cats; pl->last_keep = dropout_keep; pl->last_seed = seed; pl->last_training = training;
@@ -871,8 +973,12 @@ int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, f
   a.head_off = pl->w_reg0; a.head_stride = pl->head_stride; a.n_heads = pl->net.max_classes;
   a.steps = steps; a.present = head_present;
   Ctx c = {pl, (cudaStream_t)stream};
-  TD3D_TRY(launch_optim(a, c.st));
-  return pack_impl(c);
+  {
+    double per = desc->kind == TD3D_OPT_ADAMW ? 28.0 : (desc->kind == TD3D_OPT_ADADELTA ? 28.0 : 20.0);
+    TD3D_K(PK_OPTIM, per * pl->param_floats, launch_optim(a, c.st));
+  }
+  TD3D_K(PK_PACK, 12.0 * pl->param_floats, pack_impl(c));
+  return TD3D_OK;
 }
 
 // ---- per-kernel entry points ----------------------------------------------------------------

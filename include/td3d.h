@@ -122,6 +122,12 @@ int  td3d_plan_bind(td3d_plan* plan, float* params, float* grads, float* bn_stat
 /* Optional device i32 counter mixed into the Philox dropout seed (the fused optimizer's global
  * step): a CUDA-graph replay of the train step then draws a fresh cls_fc dropout mask each time. */
 int  td3d_plan_set_dropout_counter(td3d_plan* plan, const int32_t* counter);
+/* Per-launch profiling (CUDA events on the launching stream, grouped by kernel kind, with the
+ * algorithmic bytes each launch must move). Enabling clears previous records. profile_read returns
+ * 1 when `kind` is past the last kind. Not for use inside CUDA-graph capture. */
+int  td3d_plan_profile(td3d_plan* plan, int enable);
+int  td3d_plan_profile_read(td3d_plan* plan, int kind, char* name, int name_cap, double* ms,
+                            double* bytes, int64_t* launches);
 /* params -> compute-layout copies (+ eval-mode BN folding tables); call after any param change */
 int  td3d_pack_weights(td3d_plan* plan, void* stream);
 

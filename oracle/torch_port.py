@@ -484,7 +484,7 @@ def train_step(state, name, opt_state, imgs, gt_kp, cats, dropout_mask, loss_cfg
     add, sadd = average_distance(kp.detach(), gt_kp)
     acc = accuracy(logits.detach(), cats)
     return dict(kp=kp.detach(), logits=logits.detach(), loss=float(total.detach()),
-                reg_terms=[float(t) for t in reg], cls_terms=[float(t) for t in cls],
+                reg_terms=[float(t.detach()) for t in reg], cls_terms=[float(t.detach()) for t in cls],
                 grads=grads, add=add, sadd=sadd, acc=acc)
 
 
