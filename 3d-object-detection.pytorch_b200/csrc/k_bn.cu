@@ -9,20 +9,31 @@
 
 namespace td3d {
 
-__global__ void bn_finalize_fwd_kernel(BnFwdArgs a) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
+static const int BN_WARPS = 16;   // block = 16 warps x 32 channels; warps stride over the slots
+
+// block: 32 consecutive channels (lane) x BN_WARPS slot-lanes (warp). Coalesced slot reads, double sums.
+__global__ void __launch_bounds__(32 * BN_WARPS) bn_finalize_fwd_kernel(BnFwdArgs a) {
+  __shared__ double s_sum[2][BN_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s1 = 0.0, s2 = 0.0;
-  for (int s = 0; s < a.slots; ++s) {
-    s1 += (double)a.stats[((size_t)s * 2 + 0) * a.C + c];
-    s2 += (double)a.stats[((size_t)s * 2 + 1) * a.C + c];
+  if (c < a.C) {
+    for (int s = w; s < a.slots; s += BN_WARPS) {
+      s1 += (double)a.stats[((size_t)s * 2 + 0) * a.C + c];
+      s2 += (double)a.stats[((size_t)s * 2 + 1) * a.C + c];
+    }
   }
+  s_sum[0][w][lane] = s1;
+  s_sum[1][w][lane] = s2;
+  __syncthreads();
+  if (w != 0 || c >= a.C) return;
+  s1 = 0.0; s2 = 0.0;
+  for (int i = 0; i < BN_WARPS; ++i) { s1 += s_sum[0][i][lane]; s2 += s_sum[1][i][lane]; }
   double mean = s1 / a.count;
   double var = s2 / a.count - mean * mean;
   if (var < 0.0) var = 0.0;
   double invstd = 1.0 / sqrt(var + (double)a.eps);
-  float sc = (float)((double)a.gamma[c] * invstd);
-  a.scale[c] = sc;
+  a.scale[c] = (float)((double)a.gamma[c] * invstd);
   a.shift[c] = (float)((double)a.beta[c] - mean * (double)a.gamma[c] * invstd);
   a.mean[c] = (float)mean;
   a.invstd[c] = (float)invstd;
@@ -35,7 +46,7 @@ __global__ void bn_finalize_fwd_kernel(BnFwdArgs a) {
 }
 
 int launch_bn_finalize_fwd(const BnFwdArgs& a, cudaStream_t st) {
-  bn_finalize_fwd_kernel<<<ceil_div(a.C, 128), 128, 0, st>>>(a);
+  bn_finalize_fwd_kernel<<<ceil_div(a.C, 32), 32 * BN_WARPS, 0, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -64,31 +75,43 @@ int launch_bn_eval_fold(const float* gamma, const float* beta, const float* rm, 
 //   g_z = se*g_u + g_pool/HW
 //   g_y = a*(g_z - mean_M(g_z) - x_hat*mean_M(g_z*x_hat))
 //       = alpha[b,c]*g_u + beta[c]*y + gammac[b,c]
-__global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  const double mu = a.mean[c], is = a.invstd[c];
+__global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArgs a) {
+  __shared__ double s_sum[2][BN_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool on = c < a.C;
+  const double mu = on ? a.mean[c] : 0.0, is = on ? a.invstd[c] : 0.0;
   const double M = (double)a.B * (double)a.HW;
-  double S1 = 0.0, S2 = 0.0;
   const bool se_mode = a.se != nullptr;
-  for (int s = 0; s < a.slots; ++s) {
-    double p1 = a.stats[((size_t)s * 2 + 0) * a.C + c];
-    double p2 = a.stats[((size_t)s * 2 + 1) * a.C + c];
-    double gate = 1.0, gp = 0.0, p0 = 0.0;
-    if (se_mode) {  // slots == B by construction
-      gate = a.se[(size_t)s * a.C + c];
-      gp = a.g_pool[(size_t)s * a.C + c];
-      p0 = a.fwd_pool[((size_t)s * 2 + 0) * a.C + c];
+  double S1 = 0.0, S2 = 0.0;
+  if (on) {
+    for (int s = w; s < a.slots; s += BN_WARPS) {
+      double p1 = a.stats[((size_t)s * 2 + 0) * a.C + c];
+      double p2 = a.stats[((size_t)s * 2 + 1) * a.C + c];
+      double gate = 1.0, gp = 0.0, p0 = 0.0;
+      if (se_mode) {  // slots == B by construction
+        gate = a.se[(size_t)s * a.C + c];
+        gp = a.g_pool[(size_t)s * a.C + c];
+        p0 = a.fwd_pool[((size_t)s * 2 + 0) * a.C + c];
+      }
+      S1 += gate * p1 + gp;
+      S2 += gate * (p2 - mu * p1) * is + (gp / a.HW) * (p0 - a.HW * mu) * is;
     }
-    S1 += gate * p1 + gp;
-    S2 += gate * (p2 - mu * p1) * is + (gp / a.HW) * (p0 - a.HW * mu) * is;
   }
+  s_sum[0][w][lane] = S1;
+  s_sum[1][w][lane] = S2;
+  __syncthreads();
+  if (!on) return;
+  S1 = 0.0; S2 = 0.0;
+  for (int i = 0; i < BN_WARPS; ++i) { S1 += s_sum[0][i][lane]; S2 += s_sum[1][i][lane]; }
   const double c1 = S1 / M, c2 = S2 / M;
   const double aa = (double)a.gamma[c] * is;
-  a.beta[c] = (float)(-aa * c2 * is);
-  a.dgamma[c] = (float)S2;
-  a.dbeta[c] = (float)S1;
-  for (int b = 0; b < a.B; ++b) {
+  if (w == 0) {
+    a.beta[c] = (float)(-aa * c2 * is);
+    a.dgamma[c] = (float)S2;
+    a.dbeta[c] = (float)S1;
+  }
+  for (int b = w; b < a.B; b += BN_WARPS) {
     double gate = 1.0, gp = 0.0;
     if (se_mode) {
       gate = a.se[(size_t)b * a.C + c];
@@ -101,7 +124,7 @@ __global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
 
 int launch_bn_bwd_finalize(const BnBwdArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(!a.se || a.slots == a.B, "bn_bwd_finalize: SE mode needs slots == B");
-  bn_bwd_finalize_kernel<<<ceil_div(a.C, 64), 64, 0, st>>>(a);
+  bn_bwd_finalize_kernel<<<ceil_div(a.C, 32), 32 * BN_WARPS, 0, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

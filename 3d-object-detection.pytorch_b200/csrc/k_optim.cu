@@ -109,6 +109,43 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restri
   }
 }
 
+// ---- table-driven weight packing: ONE launch refreshes every compute-layout copy ------------------
+__global__ void __launch_bounds__(256) pack_table_kernel(const __grid_constant__ PackTable t) {
+  const PackSeg sg = t.seg[blockIdx.y];
+  const int64_t n = (int64_t)sg.rows * sg.cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = sg.src[i];
+    int64_t o = i;
+    if (sg.transpose) {
+      const int r = (int)(i / sg.cols), c = (int)(i % sg.cols);
+      o = (int64_t)c * sg.rows + r;
+    }
+    if (sg.out_dtype == TD3D_BF16) reinterpret_cast<bf16*>(sg.dst)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(sg.dst)[o] = v;
+  }
+}
+__global__ void __launch_bounds__(128) bn_fold_table_kernel(const __grid_constant__ BnFoldTable t, float eps) {
+  const BnFoldSeg sg = t.seg[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < sg.C; c += gridDim.x * blockDim.x) {
+    float invstd = 1.f / sqrtf(sg.rv[c] + eps);
+    float sc = sg.gamma[c] * invstd;
+    sg.scale[c] = sc;
+    sg.shift[c] = sg.beta[c] - sg.rm[c] * sc;
+  }
+}
+int launch_pack_table(const PackTable& t, cudaStream_t st) {
+  if (t.n <= 0) return TD3D_OK;
+  pack_table_kernel<<<dim3(32, t.n), 256, 0, st>>>(t);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+int launch_bn_fold_table(const BnFoldTable& t, float eps, cudaStream_t st) {
+  if (t.n <= 0) return TD3D_OK;
+  bn_fold_table_kernel<<<dim3(2, t.n), 128, 0, st>>>(t, eps);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
 int launch_cast(const float* src, void* dst, int64_t n, int dtype, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -1,161 +1,91 @@
 // Squeeze-and-Excite FCs (reference SELayer, torchdet3d/models/mobilenetv3.py:92-107):
 //   zbar = mean_HW(z);  hid = relu(W1 zbar + b1);  gate = h_sigmoid(W2 hid + b2);  x = z * gate
-// The squeeze (per-(b,c) pixel sums) is produced by the depthwise-conv epilogue; the gate is
-// applied by the consumer's load transform. These kernels are the tiny per-sample FCs only.
+// The squeeze (per-(b,c) pixel sums) is produced by the depthwise-conv epilogue and the gate is
+// applied by the consumer's load transform, so only the tiny [B,C]x[C,C/4] products remain.  They
+// are batched over the whole mini-batch as fp32 GEMMs (the exact FFMA kernels of
+// k_gemm_simple.cu) with small elementwise glue kernels -- everything stays fp32.
 #include "td3d_kernels.h"
 
 namespace td3d {
 
-static const int SE_SB = 4;        // samples per block (weight rows are reused across them)
-static const int SE_THREADS = 256;
+__global__ void se_zbar_kernel(SeArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.C) return;
+  int b = i / a.C, c = i % a.C;
+  float z = a.pool_stats[((size_t)b * 2 + 0) * a.C + c] * a.inv_hw;
+  if (a.scale) z = fmaf(z, a.scale[c], a.shift[c]);
+  a.zbar[i] = z;
+}
+__global__ void se_gate_kernel(const float* __restrict__ pre, float* __restrict__ gate, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gate[i] = hsigmoid(pre[i]);
+}
 
-__global__ void __launch_bounds__(SE_THREADS) se_fwd_kernel(SeArgs a) {
-  extern __shared__ float sm[];
-  float* s_z = sm;                     // [SE_SB][C]
-  float* s_h = sm + SE_SB * a.C;       // [SE_SB][Ch]
-  const int b0 = blockIdx.x * SE_SB;
-  const int nb = min(SE_SB, a.B - b0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < nb * a.C; i += blockDim.x) {
-    int s = i / a.C, c = i % a.C;
-    float z = a.pool_stats[((size_t)(b0 + s) * 2 + 0) * a.C + c] * a.inv_hw;
-    if (a.scale) z = fmaf(z, a.scale[c], a.shift[c]);
-    s_z[s * a.C + c] = z;
-    a.zbar[(size_t)(b0 + s) * a.C + c] = z;
-  }
-  __syncthreads();
-  for (int j = warp; j < a.Ch; j += nwarp) {
-    float acc[SE_SB];
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = 0.f;
-    const float* wr = a.w1 + (size_t)j * a.C;
-    for (int c = lane; c < a.C; c += 32) {
-      float w = wr[c];
-#pragma unroll
-      for (int s = 0; s < SE_SB; ++s) acc[s] = fmaf(w, s_z[s * a.C + c], acc[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = warp_sum(acc[s]);
-    if (lane == 0) {
-      for (int s = 0; s < nb; ++s) {
-        float h = fmaxf(acc[s] + a.b1[j], 0.f);
-        s_h[s * a.Ch + j] = h;
-        a.hid[(size_t)(b0 + s) * a.Ch + j] = h;
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = warp; c < a.C; c += nwarp) {
-    float acc[SE_SB];
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = 0.f;
-    const float* wr = a.w2 + (size_t)c * a.Ch;
-    for (int j = lane; j < a.Ch; j += 32) {
-      float w = wr[j];
-#pragma unroll
-      for (int s = 0; s < SE_SB; ++s) acc[s] = fmaf(w, s_h[s * a.Ch + j], acc[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = warp_sum(acc[s]);
-    if (lane == 0) {
-      for (int s = 0; s < nb; ++s) {
-        float p = acc[s] + a.b2[c];
-        a.pre[(size_t)(b0 + s) * a.C + c] = p;
-        a.gate[(size_t)(b0 + s) * a.C + c] = hsigmoid(p);
-      }
-    }
-  }
+static GemmNT nt(const float* a, const float* w, float* y, const float* bias, int M, int N, int K, int relu) {
+  GemmNT g = {};
+  g.a = a; g.w = w; g.y = y; g.bias = bias; g.M = M; g.N = N; g.K = K; g.relu = relu;
+  return g;
 }
 
 int launch_se_fwd(const SeArgs& a, cudaStream_t st) {
-  size_t smem = sizeof(float) * SE_SB * (a.C + a.Ch);
-  se_fwd_kernel<<<ceil_div(a.B, SE_SB), SE_THREADS, smem, st>>>(a);
+  const int n = a.B * a.C;
+  se_zbar_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  TD3D_TRY(launch_gemm_nt_simt(nt(a.zbar, a.w1, a.hid, a.b1, a.B, a.Ch, a.C, 1), TD3D_F32, st));
+  TD3D_TRY(launch_gemm_nt_simt(nt(a.hid, a.w2, a.pre, a.b2, a.B, a.C, a.Ch, 0), TD3D_F32, st));
+  se_gate_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.pre, a.gate, n);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
-// per-sample chain: g_gate -> g_pre -> g_hid -> g_zbar (=g_pool)
-__global__ void __launch_bounds__(SE_THREADS) se_bwd_chain_kernel(SeBwdArgs a) {
-  extern __shared__ float sm[];
-  float* s_gp = sm;                    // [SE_SB][C]  g_pre
-  float* s_gh = sm + SE_SB * a.C;      // [SE_SB][Ch] g_hid
-  const int b0 = blockIdx.x * SE_SB;
-  const int nb = min(SE_SB, a.B - b0);
-  for (int i = threadIdx.x; i < nb * a.C; i += blockDim.x) {
-    int s = i / a.C, c = i % a.C;
-    size_t bc = (size_t)(b0 + s) * a.C + c;
-    float p1 = a.bwd_stats[((size_t)(b0 + s) * 2 + 0) * a.C + c];
-    float p2 = a.bwd_stats[((size_t)(b0 + s) * 2 + 1) * a.C + c];
-    float gs = a.scale ? fmaf(a.scale[c], p2, a.shift[c] * p1) : p2;   // sum_HW g_u * z
-    float gp = gs * hsigmoid_bwd(a.pre[bc]);
-    s_gp[s * a.C + c] = gp;
-    a.g_pre[bc] = gp;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < a.Ch; j += blockDim.x) {
-    float acc[SE_SB];
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = 0.f;
-    for (int c = 0; c < a.C; ++c) {
-      float w = a.w2[(size_t)c * a.Ch + j];
-#pragma unroll
-      for (int s = 0; s < SE_SB; ++s) acc[s] = fmaf(w, s_gp[s * a.C + c], acc[s]);
-    }
-    for (int s = 0; s < nb; ++s) {
-      size_t bj = (size_t)(b0 + s) * a.Ch + j;
-      float gh = a.hid[bj] > 0.f ? acc[s] : 0.f;
-      s_gh[s * a.Ch + j] = gh;
-      a.g_hid[bj] = gh;
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    float acc[SE_SB];
-#pragma unroll
-    for (int s = 0; s < SE_SB; ++s) acc[s] = 0.f;
-    for (int j = 0; j < a.Ch; ++j) {
-      float w = a.w1[(size_t)j * a.C + c];
-#pragma unroll
-      for (int s = 0; s < SE_SB; ++s) acc[s] = fmaf(w, s_gh[s * a.Ch + j], acc[s]);
-    }
-    for (int s = 0; s < nb; ++s) a.g_pool[(size_t)(b0 + s) * a.C + c] = acc[s];
-  }
-}
-
-// weight gradients: dW2[c,j] = sum_b g_pre[b,c]*hid[b,j]; dW1[j,c] = sum_b g_hid[b,j]*zbar[b,c]
-__global__ void se_bwd_wgrad_kernel(SeBwdArgs a) {
-  const int n2 = a.C * a.Ch;
+// g_pre[b,c] = (sum_HW g_u * z)[b,c] * h_sigmoid'(pre)
+__global__ void se_gpre_kernel(SeBwdArgs a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n2) {                               // dW2 [C,Ch], j fastest
-    int c = i / a.Ch, j = i % a.Ch;
-    float acc = 0.f;
-    for (int b = 0; b < a.B; ++b) acc = fmaf(a.g_pre[(size_t)b * a.C + c], a.hid[(size_t)b * a.Ch + j], acc);
-    a.dw2[i] = acc;
-  } else if (i < 2 * n2) {                    // dW1 [Ch,C], c fastest
-    int k = i - n2;
-    int j = k / a.C, c = k % a.C;
-    float acc = 0.f;
-    for (int b = 0; b < a.B; ++b) acc = fmaf(a.g_hid[(size_t)b * a.Ch + j], a.zbar[(size_t)b * a.C + c], acc);
-    a.dw1[k] = acc;
-  } else if (i < 2 * n2 + a.C) {              // db2
-    int c = i - 2 * n2;
-    float acc = 0.f;
-    for (int b = 0; b < a.B; ++b) acc += a.g_pre[(size_t)b * a.C + c];
-    a.db2[c] = acc;
-  } else if (i < 2 * n2 + a.C + a.Ch) {       // db1
-    int j = i - 2 * n2 - a.C;
-    float acc = 0.f;
-    for (int b = 0; b < a.B; ++b) acc += a.g_hid[(size_t)b * a.Ch + j];
-    a.db1[j] = acc;
+  if (i >= a.B * a.C) return;
+  int b = i / a.C, c = i % a.C;
+  float p1 = a.bwd_stats[((size_t)b * 2 + 0) * a.C + c];
+  float p2 = a.bwd_stats[((size_t)b * 2 + 1) * a.C + c];
+  float gs = a.scale ? fmaf(a.scale[c], p2, a.shift[c] * p1) : p2;
+  a.g_pre[i] = gs * hsigmoid_bwd(a.pre[i]);
+}
+__global__ void se_relu_mask_kernel(const float* __restrict__ hid, float* __restrict__ g, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(hid[i] > 0.f)) g[i] = 0.f;
+}
+// out[c] = sum_b x[b,c]
+__global__ void se_colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C) {
+  __shared__ float s[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < C)
+    for (int b = w; b < B; b += 8) acc += x[(size_t)b * C + c];
+  s[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) acc += s[i][lane];
+    out[c] = acc;
   }
 }
 
 int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
-  size_t smem = sizeof(float) * SE_SB * (a.C + a.Ch);
-  se_bwd_chain_kernel<<<ceil_div(a.B, SE_SB), SE_THREADS, smem, st>>>(a);
+  const int n = a.B * a.C, nh = a.B * a.Ch;
+  se_gpre_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a);
   TD3D_LAUNCH_CHECK();
-  int n = 2 * a.C * a.Ch + a.C + a.Ch;
-  se_bwd_wgrad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a);
+  // g_hid = (g_pre W2) * [hid > 0]   (W operand = W2^T [Ch, C])
+  TD3D_TRY(launch_gemm_nt_simt(nt(a.g_pre, a.w2t, a.g_hid, nullptr, a.B, a.Ch, a.C, 0), TD3D_F32, st));
+  se_relu_mask_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(a.hid, a.g_hid, nh);
+  TD3D_LAUNCH_CHECK();
+  // g_zbar = g_hid W1            (W operand = W1^T [C, Ch])
+  TD3D_TRY(launch_gemm_nt_simt(nt(a.g_hid, a.w1t, a.g_pool, nullptr, a.B, a.C, a.Ch, 0), TD3D_F32, st));
+  // weight gradients (the gradient arena is zeroed at the start of backward; TN accumulates)
+  GemmTN t2 = {a.g_pre, a.hid, a.dw2, a.B, a.C, a.Ch};
+  TD3D_TRY(launch_gemm_tn_simt(t2, TD3D_F32, st));
+  GemmTN t1 = {a.g_hid, a.zbar, a.dw1, a.B, a.Ch, a.C};
+  TD3D_TRY(launch_gemm_tn_simt(t1, TD3D_F32, st));
+  se_colsum_kernel<<<ceil_div(a.C, 32), 256, 0, st>>>(a.g_pre, a.db2, a.B, a.C);
+  TD3D_LAUNCH_CHECK();
+  se_colsum_kernel<<<ceil_div(a.Ch, 32), 256, 0, st>>>(a.g_hid, a.db1, a.B, a.Ch);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -51,6 +51,7 @@ struct Block {
   int64_t w1 = -1, wdw = -1, w3 = -1;   // param offsets
   int64_t se_w1 = -1, se_b1 = -1, se_w2 = -1, se_b2 = -1;
   size_t pw1 = 0, pw1t = 0, pdw = 0, pw3 = 0, pw3t = 0;   // packed offsets
+  size_t pse_w1t = 0, pse_w2t = 0;                        // fp32 transposed SE weights
   size_t y1 = 0, y2 = 0, h = 0, h2 = 0, y3 = 0, out = 0;  // workspace activations (T)
   size_t hstats = 0, hbstats = 0;       // dw-first + SE: pool sums of H and their backward twin
   size_t zbar = 0, hid = 0, pre = 0, gate = 0;
@@ -109,6 +110,8 @@ struct td3d_plan {
   uint64_t last_seed = 0; int last_training = 0;
   const int32_t* dropout_counter = nullptr;
   Prof prof;
+  td3d::PackTable pack_table;
+  td3d::BnFoldTable fold_table;
 };
 
 namespace td3d {
@@ -226,6 +229,10 @@ static int build(td3d_plan* pl) {
     b.pdw = pk.take(sizeof(float) * b.d.kernel * b.d.kernel * b.d.exp_ch);
     b.pw3 = pk.take(e * b.d.out_ch * b.d.exp_ch);
     b.pw3t = pk.take(e * b.d.out_ch * b.d.exp_ch);
+    if (b.d.use_se) {
+      b.pse_w1t = pk.take(sizeof(float) * b.d.exp_ch * b.d.se_hidden);
+      b.pse_w2t = pk.take(sizeof(float) * b.d.exp_ch * b.d.se_hidden);
+    }
   }
   pl->p_last = pk.take(e * n.last_ch * cin);
   pl->p_lastt = pk.take(e * n.last_ch * cin);
@@ -546,17 +553,24 @@ static int bn_backward(const Ctx& c, int idx, int HW, const float* se, const flo
   return TD3D_OK;
 }
 
-__global__ void colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
-                              const float* __restrict__ gammac, const float* __restrict__ bstats,
-                              const float* __restrict__ fstats, float* __restrict__ out, int B, int C) {
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gammac,
+              const float* __restrict__ bstats, const float* __restrict__ fstats, float* __restrict__ out, int B, int C) {
   // sum_b (alpha[b,c]*g_u + beta[c]*y + gammac[b,c]) from the per-sample sums (HW = 1)
-  int cc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cc >= C) return;
+  __shared__ double s[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cc = blockIdx.x * 32 + lane;
   double acc = 0.0;
-  for (int b = 0; b < B; ++b)
-    acc += (double)alpha[(size_t)b * C + cc] * bstats[((size_t)b * 2) * C + cc] +
-           (double)beta[cc] * fstats[((size_t)b * 2) * C + cc] + (double)gammac[(size_t)b * C + cc];
-  out[cc] = (float)acc;
+  if (cc < C)
+    for (int b = w; b < B; b += 8)
+      acc += (double)alpha[(size_t)b * C + cc] * bstats[((size_t)b * 2) * C + cc] +
+             (double)beta[cc] * fstats[((size_t)b * 2) * C + cc] + (double)gammac[(size_t)b * C + cc];
+  s[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && cc < C) {
+    for (int i = 1; i < 8; ++i) acc += s[i][lane];
+    out[cc] = (float)acc;
+  }
 }
 
 __global__ void scale_kernel(const float* __restrict__ src, float s, float* __restrict__ dst, int n) {
@@ -595,7 +609,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     TD3D_TRY(p_actbwd(c, nullptr, c.wsf(pl->g_feat), 1.f, c.ws(pl->yfc), xfc, c.ws(pl->g_wide_a), c.wsf(bfc.bstats),
                                   B, 1, n.head_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_fc, 1, nullptr, nullptr, nullptr));
-    colsum_kernel<<<ceil_div(n.head_ch, 128), 128, 0, c.st>>>(c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+    colsum_kernel<<<ceil_div(n.head_ch, 32), 256, 0, c.st>>>(c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                                                               c.wsf(bfc.bstats), c.wsf(bfc.fstats), c.G(pl->b_fc), B, n.head_ch);
     TD3D_LAUNCH_CHECK();
     TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_a), c.ws(pl->yfc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
@@ -661,7 +675,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       if (b.d.use_se) {
         SeBwdArgs s;
         s.bwd_stats = c.wsf(bn2.bstats); s.scale = sc2; s.shift = sh2; s.inv_hw = 1.f / (float)HWo;
-        s.w1 = c.P(b.se_w1); s.w2 = c.P(b.se_w2);
+        s.w1t = c.pkf(b.pse_w1t); s.w2t = c.pkf(b.pse_w2t);
         s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
         s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
         s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
@@ -678,7 +692,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
                                       c.wsf(b.hbstats), B, HWo, E, dt, c.st));
         SeBwdArgs s;
         s.bwd_stats = c.wsf(b.hbstats); s.scale = nullptr; s.shift = nullptr; s.inv_hw = 1.f / (float)HWo;
-        s.w1 = c.P(b.se_w1); s.w2 = c.P(b.se_w2);
+        s.w1t = c.pkf(b.pse_w1t); s.w2t = c.pkf(b.pse_w2t);
         s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
         s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
         s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
@@ -746,29 +760,56 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
   return TD3D_OK;
 }
 
-static int pack_impl(const Ctx& c) {
-  td3d_plan* pl = c.pl;
+static int add_seg(PackTable& t, const float* src, void* dst, int rows, int cols, int transpose, int out_dtype) {
+  TD3D_REQUIRE(t.n < 160, "pack table overflow");
+  PackSeg& sg = t.seg[t.n++];
+  sg.src = src; sg.dst = dst; sg.rows = rows; sg.cols = cols; sg.transpose = transpose; sg.out_dtype = out_dtype;
+  return TD3D_OK;
+}
+
+// (re)build the pack / BN-fold tables for the currently bound buffers
+static int build_tables(td3d_plan* pl) {
+  Ctx c = {pl, 0};
   const td3d_net_desc& n = pl->net;
   const int dt = pl->dtype;
-  TD3D_TRY(launch_transpose_cast(c.P(pl->w_stem), c.pk(pl->p_stem), n.stem_ch, 27, TD3D_F32, c.st));
+  PackTable& t = pl->pack_table;
+  t.n = 0;
+  TD3D_TRY(add_seg(t, c.P(pl->w_stem), c.pk(pl->p_stem), n.stem_ch, 27, 1, TD3D_F32));
   for (auto& b : pl->blocks) {
     const int E = b.d.exp_ch, kk = b.d.kernel * b.d.kernel;
     if (b.expand) {
-      TD3D_TRY(launch_cast(c.P(b.w1), c.pk(b.pw1), (int64_t)E * b.d.in_ch, dt, c.st));
-      TD3D_TRY(launch_transpose_cast(c.P(b.w1), c.pk(b.pw1t), E, b.d.in_ch, dt, c.st));
+      TD3D_TRY(add_seg(t, c.P(b.w1), c.pk(b.pw1), E, b.d.in_ch, 0, dt));
+      TD3D_TRY(add_seg(t, c.P(b.w1), c.pk(b.pw1t), E, b.d.in_ch, 1, dt));
     }
-    TD3D_TRY(launch_transpose_cast(c.P(b.wdw), c.pk(b.pdw), E, kk, TD3D_F32, c.st));
-    TD3D_TRY(launch_cast(c.P(b.w3), c.pk(b.pw3), (int64_t)E * b.d.out_ch, dt, c.st));
-    TD3D_TRY(launch_transpose_cast(c.P(b.w3), c.pk(b.pw3t), b.d.out_ch, E, dt, c.st));
+    TD3D_TRY(add_seg(t, c.P(b.wdw), c.pk(b.pdw), E, kk, 1, TD3D_F32));
+    TD3D_TRY(add_seg(t, c.P(b.w3), c.pk(b.pw3), b.d.out_ch, E, 0, dt));
+    TD3D_TRY(add_seg(t, c.P(b.w3), c.pk(b.pw3t), b.d.out_ch, E, 1, dt));
+    if (b.d.use_se) {
+      TD3D_TRY(add_seg(t, c.P(b.se_w1), c.pk(b.pse_w1t), b.d.se_hidden, E, 1, TD3D_F32));
+      TD3D_TRY(add_seg(t, c.P(b.se_w2), c.pk(b.pse_w2t), E, b.d.se_hidden, 1, TD3D_F32));
+    }
   }
   const int Cl = pl->blocks.back().d.out_ch;
-  TD3D_TRY(launch_cast(c.P(pl->w_last), c.pk(pl->p_last), (int64_t)n.last_ch * Cl, dt, c.st));
-  TD3D_TRY(launch_transpose_cast(c.P(pl->w_last), c.pk(pl->p_lastt), n.last_ch, Cl, dt, c.st));
-  TD3D_TRY(launch_cast(c.P(pl->w_fc), c.pk(pl->p_fc), (int64_t)n.head_ch * n.last_ch, dt, c.st));
-  TD3D_TRY(launch_transpose_cast(c.P(pl->w_fc), c.pk(pl->p_fct), n.head_ch, n.last_ch, dt, c.st));
-  for (auto& bn : pl->bns)
-    TD3D_TRY(launch_bn_eval_fold(c.P(bn.gamma), c.P(bn.beta), pl->BNB + bn.rm, pl->BNB + bn.rm + bn.C, c.pkf(bn.escale),
-                                 c.pkf(bn.eshift), bn.C, BN_EPS, c.st));
+  TD3D_TRY(add_seg(t, c.P(pl->w_last), c.pk(pl->p_last), n.last_ch, Cl, 0, dt));
+  TD3D_TRY(add_seg(t, c.P(pl->w_last), c.pk(pl->p_lastt), n.last_ch, Cl, 1, dt));
+  TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fc), n.head_ch, n.last_ch, 0, dt));
+  TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fct), n.head_ch, n.last_ch, 1, dt));
+  BnFoldTable& f = pl->fold_table;
+  f.n = 0;
+  TD3D_REQUIRE(pl->bns.size() <= 128, "too many BatchNorm layers for the fold table");
+  for (auto& bn : pl->bns) {
+    BnFoldSeg& sg = f.seg[f.n++];
+    sg.gamma = c.P(bn.gamma); sg.beta = c.P(bn.beta);
+    sg.rm = pl->BNB + bn.rm; sg.rv = pl->BNB + bn.rm + bn.C;
+    sg.scale = c.pkf(bn.escale); sg.shift = c.pkf(bn.eshift); sg.C = bn.C;
+  }
+  return TD3D_OK;
+}
+
+// weights only (every optimizer step) / weights + eval-mode BN fold (explicit td3d_pack_weights)
+static int pack_impl(const Ctx& c, bool with_bn_fold) {
+  TD3D_TRY(launch_pack_table(c.pl->pack_table, c.st));
+  if (with_bn_fold) TD3D_TRY(launch_bn_fold_table(c.pl->fold_table, BN_EPS, c.st));
   return TD3D_OK;
 }
 
@@ -851,7 +892,7 @@ int td3d_plan_bind(td3d_plan* pl, float* params, float* grads, float* bn_stats, 
                "plan_bind: buffers must be 256-byte aligned");
   pl->P = params; pl->G = grads; pl->BNB = bn_stats; pl->NBT = nbt;
   pl->PK = (uint8_t*)packed; pl->WS = (uint8_t*)workspace;
-  return TD3D_OK;
+  return build_tables(pl);
 }
 
 int td3d_plan_set_dropout_counter(td3d_plan* pl, const int32_t* counter) {
@@ -888,7 +929,7 @@ int td3d_plan_profile_read(td3d_plan* pl, int kind, char* name, int name_cap, do
 int td3d_pack_weights(td3d_plan* pl, void* stream) {
   TD3D_BOUND(pl);
   Ctx c = {pl, (cudaStream_t)stream};
-  return pack_impl(c);
+  return pack_impl(c, true);
 }
 
 int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const float* dropout_keep, uint64_t seed,
@@ -977,7 +1018,7 @@ int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, f
     double per = desc->kind == TD3D_OPT_ADAMW ? 28.0 : (desc->kind == TD3D_OPT_ADADELTA ? 28.0 : 20.0);
     TD3D_K(PK_OPTIM, per * pl->param_floats, launch_optim(a, c.st));
   }
-  TD3D_K(PK_PACK, 12.0 * pl->param_floats, pack_impl(c));
+  TD3D_K(PK_PACK, 12.0 * pl->param_floats, pack_impl(c, false));
   return TD3D_OK;
 }
 

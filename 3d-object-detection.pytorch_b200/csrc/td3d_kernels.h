@@ -49,7 +49,7 @@ struct SeBwdArgs {
   const float* bwd_stats;    // [B][2][C]: P1 = sum gu, P2 = sum gu*y
   const float* scale; const float* shift;   // gs = scale*P2 + shift*P1 (null: gs = P2)
   float inv_hw;
-  const float* w1; const float* w2;
+  const float* w1t; const float* w2t;                  // transposed copies: W1^T [C,Ch], W2^T [Ch,C]
   const float* zbar; const float* hid; const float* pre;
   float* g_pre; float* g_hid; float* g_pool;           // [B,C] [B,Ch] [B,C]
   float* dw1; float* db1; float* dw2; float* db2;      // grads arena
@@ -83,6 +83,8 @@ struct DwBwdArgs {
   int B, H, W, C, k, stride;
 };
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
+int launch_dw_fwd_simple(const DwArgs& a, int dtype, cudaStream_t st);
+int launch_dw_bwd_simple(const DwBwdArgs& a, int dtype, cudaStream_t st);
 
 // ---- k_gemm_simple.cu / k_gemm_tc.cu ----
 struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m,n])
@@ -93,6 +95,7 @@ struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m
   float* stats; int slots;   // [slots][2][N] or null
   int M, N, K;
   int out_f32;               // write Y as float regardless of dtype
+  int relu;                  // SIMT kernel only: y = max(y, 0) before the store
 };
 int launch_gemm_nt_simt(const GemmNT& g, int dtype, cudaStream_t st);
 int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st);       // bf16 only
@@ -142,6 +145,12 @@ struct OptimArgs {
   int32_t* steps; const int32_t* present;
 };
 int launch_optim(const OptimArgs& a, cudaStream_t st);
+struct PackSeg { const float* src; void* dst; int rows, cols; int transpose; int out_dtype; };
+struct PackTable { int n; PackSeg seg[160]; };
+struct BnFoldSeg { const float *gamma, *beta, *rm, *rv; float *scale, *shift; int C; };
+struct BnFoldTable { int n; BnFoldSeg seg[128]; };
+int launch_pack_table(const PackTable& t, cudaStream_t st);
+int launch_bn_fold_table(const BnFoldTable& t, float eps, cudaStream_t st);
 int launch_cast(const float* src, void* dst, int64_t n, int dtype, cudaStream_t st);
 int launch_transpose_cast(const float* src, void* dst, int rows, int cols, int dtype, cudaStream_t st);  // dst[c][r] = src[r][c]
 int launch_cast_f32(const void* src, float* dst, int64_t n, int dtype, cudaStream_t st);
