@@ -1,4 +1,4 @@
-# first bench + launch list (run under gpurun)
+# tests + bench + launch list (run under gpurun)
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
