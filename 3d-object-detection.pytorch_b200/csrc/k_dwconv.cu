@@ -383,10 +383,17 @@ dw_bwd_weight_tiled_kernel(const T* __restrict__ g, const T* __restrict__ yo, co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static bool use_simple() {
+// TD3D_DW_IMPL selects the depthwise generation for A/B debugging: 2 = k_dw2.cu (default),
+// 1 = the 8x8-tile kernels of this file, 0 = the direct kernels of k_dwconv_simple.cu.
+static int dw_impl() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TD3D_DW_SIMPLE"); v = (e && atoi(e)) ? 1 : 0; }
-  return v == 1;
+  if (v < 0) {
+    const char* e = getenv("TD3D_DW_IMPL");
+    v = e ? atoi(e) : 2;
+    const char* s = getenv("TD3D_DW_SIMPLE");
+    if (s && atoi(s)) v = 0;
+  }
+  return v;
 }
 
 template <typename KernelT>
@@ -461,7 +468,8 @@ static int dw_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
 
 int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw fwd: C=%d must be a multiple of 8", a.C);
-  if (use_simple()) return launch_dw_fwd_simple(a, dtype, st);
+  if (dw_impl() == 0) return launch_dw_fwd_simple(a, dtype, st);
+  if (dw_impl() == 2) return launch_dw_fwd_v2(a, dtype, st);
   DW_DISPATCH(dw_fwd_t, a);
   set_last_error("dw fwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   return TD3D_EINVAL;
@@ -469,7 +477,8 @@ int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
 
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw bwd: C=%d must be a multiple of 8", a.C);
-  if (use_simple()) return launch_dw_bwd_simple(a, dtype, st);
+  if (dw_impl() == 0) return launch_dw_bwd_simple(a, dtype, st);
+  if (dw_impl() == 2) return launch_dw_bwd_v2(a, dtype, st);
   DW_DISPATCH(dw_bwd_t, a);
   set_last_error("dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   return TD3D_EINVAL;

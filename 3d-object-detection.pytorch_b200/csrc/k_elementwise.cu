@@ -183,12 +183,16 @@ __global__ void pool_finalize_kernel(const float* __restrict__ stats, float scal
   out[i] = from_f<T>(stats[((size_t)b * 2) * C + c] * scale);
 }
 
+// Pixels per block: long per-thread pixel loops amortise the per-block reduction (shared + global
+// atomics per channel), but the grid must still fill the machine (>= ~4 blocks per SM).
 static void ew_grid(int B, int HW, int C, dim3* grid, int* pix_per_block) {
   int CV = C >> 3;
   if (CV > EW_THREADS) CV = EW_THREADS;
   int PL = EW_THREADS / CV;
   if (PL < 1) PL = 1;
-  int ppb = PL * EW_ITERS;
+  int iters = 64;
+  while (iters > EW_ITERS && (long)ceil_div(HW, PL * iters) * B < 148 * 2) iters >>= 1;
+  int ppb = PL * iters;
   if (ppb > HW) ppb = HW;
   *pix_per_block = ppb;
   *grid = dim3((unsigned)ceil_div(HW, ppb), (unsigned)B);

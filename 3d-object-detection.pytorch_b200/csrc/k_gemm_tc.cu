@@ -159,26 +159,34 @@ struct TcNtParams {
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
+  int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
+                        // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
+  int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
+                        // 4 no shared atomics, 8 no global reductions, 16 no TMEM load
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcNtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[2], s_tempty[2];
+  __shared__ __align__(8) uint64_t s_wfull;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_stat[2][256];
+  __shared__ float s_stat[4][2][256];     // per epilogue warp: no atomics while a tile is reduced
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms must be 1024B aligned)
-  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (uint32_t)(p.a_stage_bytes + p.b_stage_bytes);
+  const uint32_t k_blocks_u = (uint32_t)((p.K + p.block_k - 1) / p.block_k);
+  const uint32_t wres = (smem_u32(smem_raw) + 1023u) & ~1023u;      // resident W: [n_tiles][k_blocks][b_stage]
+  const uint32_t ring = wres + (p.w_resident ? (uint32_t)p.n_tiles * k_blocks_u * (uint32_t)p.b_stage_bytes : 0u);
+  const uint32_t stage_bytes = (uint32_t)(p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&s_tfull[s]), 1); mbar_init(smem_u32(&s_tempty[s]), 4); }
+    mbar_init(smem_u32(&s_wfull), 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_stat[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stat[0][0][0])[i] = 0.f;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
   tc_fence_before();
@@ -192,6 +200,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.w_resident && blockIdx.x < num_tiles) {
+        const uint32_t wf = smem_u32(&s_wfull);
+        mbar_expect_tx(wf, (uint32_t)(p.n_tiles * k_blocks * p.block_n * p.swizzle_bytes));
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int kb = 0; kb < k_blocks; ++kb)
+            tma_load_2d(wres + (uint32_t)((nt * k_blocks + kb) * p.b_stage_bytes), &map_w, wf, kb * p.block_k, nt * p.block_n);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles) * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
@@ -199,9 +214,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&s_full[stage]);
           const uint32_t a_dst = ring + stage * stage_bytes, b_dst = a_dst + p.a_stage_bytes;
-          mbar_expect_tx(full, (uint32_t)p.tx_bytes);
+          mbar_expect_tx(full, (uint32_t)(p.w_resident ? TC_BLOCK_M * p.swizzle_bytes : p.tx_bytes));
           tma_load_2d(a_dst, &map_a, full, kb * p.block_k, m0);
-          tma_load_2d(b_dst, &map_w, full, kb * p.block_k, n0);
+          if (!p.w_resident) tma_load_2d(b_dst, &map_w, full, kb * p.block_k, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -214,14 +229,17 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
+      if (p.w_resident && blockIdx.x < num_tiles) mbar_wait(smem_u32(&s_wfull), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_ACC_STRIDE);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_full[stage]), phase);
           tc_fence_after();
-          const uint32_t a_src = ring + stage * stage_bytes, b_src = a_src + p.a_stage_bytes;
+          const uint32_t a_src = ring + stage * stage_bytes;
+          const uint32_t b_src = p.w_resident ? wres + (uint32_t)((n_tile * k_blocks + kb) * p.b_stage_bytes) : a_src + p.a_stage_bytes;
           const int k_left = p.K - kb * p.block_k;
           const int k_steps = ((k_left < p.block_k ? k_left : p.block_k) + 15) >> 4;   // UMMA_K = 16 (bf16)
           for (int ks = 0; ks < k_steps; ++ks) {
@@ -251,7 +269,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool row_ok = m < p.M;
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_ACC_STRIDE + ch * 32), r);
+        if (!(p.dbg & 16)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_ACC_STRIDE + ch * 32), r);
         const int nb = n0 + ch * 32;
         float v[32], w2[32];
 #pragma unroll
@@ -276,9 +294,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int i = 0; i < 8; ++i) x[i] += ad[i];
             }
             if (p.yf) {
-              store8(p.yf + off, x);
+              if (!(p.dbg & 1)) store8(p.yf + off, x);
             } else {
-              store8(p.y + off, x);
+              if (!(p.dbg & 1)) store8(p.y + off, x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
             }
@@ -294,11 +312,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int i = 0; i < 8; ++i) { v[g * 8 + i] = 0.f; w2[g * 8 + i] = 0.f; }
           }
         }
-        if (p.stats) {
+        if (p.stats && !(p.dbg & 2)) {
           float t1 = warp_transpose_sum32_tc(v);
           float t2 = warp_transpose_sum32_tc(w2);
-          atomicAdd(&s_stat[0][ch * 32 + lane], t1);
-          atomicAdd(&s_stat[1][ch * 32 + lane], t2);
+          if (!(p.dbg & 4)) {
+            s_stat[q][0][ch * 32 + lane] = t1;      // one warp per TMEM lane quarter owns row q
+            s_stat[q][1][ch * 32 + lane] = t2;
+          } else if (t1 + t2 == 123.456f) {
+            s_stat[q][0][lane] = t1;
+          }
         }
       }
       tc_fence_before();
@@ -309,8 +331,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int slot = m_tile % p.slots;
         for (int j = et; j < 2 * p.block_n; j += 128) {
           const int which = j / p.block_n, nn = j % p.block_n;
-          if (n0 + nn < p.N) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], s_stat[which][nn]);
-          s_stat[which][nn] = 0.f;
+          const float tot = (s_stat[0][which][nn] + s_stat[1][which][nn]) + (s_stat[2][which][nn] + s_stat[3][which][nn]);
+          if (n0 + nn < p.N && !(p.dbg & 8)) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -514,8 +536,11 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.a_stage_bytes = TC_BLOCK_M * sw;
   p.b_stage_bytes = ceil_div(bn * sw, 1024) * 1024;
   p.tx_bytes = TC_BLOCK_M * sw + bn * sw;
-  int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  int budget = 200 * 1024;
+  const int k_blocks = ceil_div(g.K, p.block_k);
+  const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
+  p.w_resident = (wres_bytes <= 96 * 1024 && !env_int("TD3D_TC_NO_WRES", 0)) ? 1 : 0;
+  int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
+  int budget = 200 * 1024 - (p.w_resident ? wres_bytes : 0);
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
@@ -524,13 +549,14 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
+  p.dbg = env_int("TD3D_TC_DBG", 0);
   CUtensorMap map_a, map_w;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
-  size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
     attr_set = true;
   }
   int grid = p.m_tiles * p.n_tiles;

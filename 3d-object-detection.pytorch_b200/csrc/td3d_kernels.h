@@ -83,6 +83,8 @@ struct DwBwdArgs {
   int B, H, W, C, k, stride;
 };
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
+int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu (default)
+int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st);
 int launch_dw_fwd_simple(const DwArgs& a, int dtype, cudaStream_t st);
 int launch_dw_bwd_simple(const DwBwdArgs& a, int dtype, cudaStream_t st);
 

@@ -1,0 +1,31 @@
+"""Micro-benchmark of the tcgen05 NT GEMM on the hot streaming shapes (run on the B200 box).
+TD3D_TC_DBG experiments isolate which part of the epilogue bounds the kernel."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3d-object-detection.pytorch_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from torchdet3d_b200 import _lib as L
+import _k as K
+L.require_b200()
+dev = "cuda"
+SHAPES = [(256 * 112 * 112, 64, 16), (256 * 112 * 112, 16, 16), (256 * 56 * 56, 24, 64), (256 * 56 * 56, 72, 24), (256 * 14 * 14, 480, 80), (256 * 14 * 14, 112, 672)]
+def run(M, N, Kd, slots, dbg):
+    os.environ["TD3D_TC_DBG"] = str(dbg)
+    a = torch.randn(M, Kd, device=dev).bfloat16(); w = torch.randn(N, Kd, device=dev).bfloat16()
+    y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(slots, 2, N, device=dev) if slots else None
+    def call():
+        L.check(L.lib().td3d_k_gemm_nt(L.ptr(a), L.ptr(w), L.ptr(y), None, None, None, L.ptr(st), slots, M, N, Kd, L.BF16, 0, L.GEMM_TCGEN05, L.stream()))
+    for _ in range(3): call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): call()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    gb = (M * Kd + M * N) * 2 / 1e9
+    return us, gb / (us * 1e-6) / 1e3
+for M, N, Kd in SHAPES:
+    for slots, dbg in [(256, 0), (0, 0), (256, 1), (256, 2), (256, 4), (256, 8), (256, 16), (256, 1 | 2), (256, 1 | 2 | 16)]:
+        us, tbs = run(M, N, Kd, slots, dbg)
+        print(f"M={M} N={N} K={Kd} slots={slots} dbg={dbg:2d}: {us:8.1f} us  {tbs:6.2f} TB/s", flush=True)
