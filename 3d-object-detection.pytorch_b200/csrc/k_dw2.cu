@@ -2,20 +2,26 @@
 // Reference op: nn.Conv2d(hidden, hidden, k, s, (k-1)//2, groups=hidden) inside InvertedResidual,
 // torchdet3d/models/mobilenetv3.py:136,152, and its autograd backward.
 //
-// Why a second generation: the depthwise tensors are the widest of the network, and at B200's HBM
-// rate (~23 B/clk/SM) a 3x3 depthwise layer has a budget of only ~22 issued instructions per element,
-// a 5x5 layer is FMA-bound outright.  So these kernels are built to be instruction-lean:
-//   * host-chosen CTA tiles (pick_tile) as large as shared memory allows, several samples per CTA
-//     for 7x7 / 14x14 maps, so halo re-staging and per-CTA fixed costs are amortised;
-//   * the producer's lazily applied transform (BatchNorm fold + SE gate + activation, or the
-//     BatchNorm-backward affine of the gradient) is evaluated ONCE per staged element, fp32 in smem;
+// The depthwise tensors are the widest of the network, and at B200's HBM rate (~23 B/clk/SM) a 3x3
+// depthwise layer has a budget of only ~22 issued instructions per element; a 5x5 layer is FMA-bound
+// outright.  ncu on the first tiled generations showed half of all issued instructions going to
+// per-CTA set-up (index divisions, constants, weights) and the load latency exposed once per small
+// CTA, so these kernels are
+//   * PERSISTENT: ~2 CTAs per SM, each walking a contiguous range of (sample block, tile) items of
+//     one channel group; thread mapping, item geometry, weights and per-channel constants are set up
+//     once per CTA;
+//   * PREFETCHED: the raw (bf16/fp32) tile of item i+1 is fetched with cp.async into a private
+//     staging area while item i is computed; the producer's lazily applied transform (BatchNorm fold
+//     + SE gate + activation, or the BatchNorm-backward affine of the gradient) is then evaluated
+//     ONCE per staged element into an fp32 shared-memory tile;
 //   * a thread owns 4 channels x (2x4 | 1x4) outputs and walks the window row by row with 128-bit
 //     conflict-free shared loads; multiply-adds are packed fp32x2 (FFMA2, sm_100);
-//   * statistics (BatchNorm sums / SE squeeze) leave the CTA as one global atomic per channel.
+//   * statistics (BatchNorm sums / SE squeeze) stay in registers across the tiles of a sample block
+//     and leave the CTA as one global atomic per channel.
 //
 //   forward   y  = dw(act(se*(scale*x+shift)))                      + sum y,  sum y^2   per (b,c)
 //   bwd-data  gx = act'(u(x)) * dw^T(alpha*g + beta*y + gamma)      + sum gx, sum gx*x  per (b,c)
-//   bwd-wgt   dW[c,ky,kx] += sum gy * x_t(shifted)   persistent CTAs, taps accumulate in registers
+//   bwd-wgt   dW[c,ky,kx] += sum gy * x_t(shifted)   taps accumulate in registers across all items
 #include "td3d_kernels.h"
 
 #include <stdlib.h>
@@ -27,21 +33,32 @@ namespace td3d {
 namespace {
 
 constexpr int D2_THREADS = 256;
-constexpr int D2_MAXCG = 32;        // channels per CTA (16 or 32)
-constexpr int D2_MAXNB = 8;         // samples per CTA
-constexpr int D2_U = 4;             // staging loads in flight per thread
+constexpr int D2_MAXNB = 8;         // samples per CTA tile
+constexpr int D2_NIT = 8;           // staged 8-channel vectors per thread and tile (upper bound)
+constexpr uint32_t D2_DEAD = 0xffffffffu;
 
 struct D2Tile {
-  int cg, ps, nv8;            // channels per CTA, smem pixel stride (floats), 8-channel vectors per pixel
-  int tyt, txt, nb;           // thread-tiles per CTA (y, x), samples per CTA
+  int cg;                     // channels per CTA (16 or 32; template parameter of the kernels)
+  int tyt, txt, nb;           // thread-tiles per CTA (y, x), samples per CTA tile
   int th, tw;                 // owned tile extent (pixels of the owned grid)
   int ih, iw;                 // staged (halo) tile extent
   int tiles_y, tiles_x, b_blocks, n_groups;
+  int nit;                    // staged vectors per thread: ceil(nb*ih*iw*(cg/8) / 256)
+  int nit2;                   // same for the second (owned-extent) tile of the weight gradient
+  int items_per_cta;
 };
 
-struct D2Consts {
-  float sc[D2_MAXCG], sh[D2_MAXCG], be[D2_MAXCG];
-  float se[D2_MAXNB][D2_MAXCG], al[D2_MAXNB][D2_MAXCG], ga[D2_MAXNB][D2_MAXCG];
+template <int CG> struct D2C {
+  static constexpr int PS = CG + 4;          // smem pixel stride (floats): +1 float4 spreads the banks of adjacent
+                                             // pixels (staging stores) and adjacent thread-tiles (compute loads)
+  static constexpr int NV8 = CG / 8;
+  static constexpr int NQ = CG / 4;
+  static constexpr int NSP = D2_THREADS / NQ;
+};
+
+template <int CG> struct D2Consts {
+  float sc[CG], sh[CG], be[CG];
+  float se[D2_MAXNB][CG], al[D2_MAXNB][CG], ga[D2_MAXNB][CG];
 };
 
 // ---- small vector helpers ---------------------------------------------------------------------
@@ -55,6 +72,11 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& a, const float4&
   const float2 hi = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(acc.z, acc.w));
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+__device__ __forceinline__ void add4(float4& acc, const float4& a) {
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(acc.x, acc.y));
+  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 __device__ __forceinline__ void fmav(float4& acc, const float4& a, const float4& b) { fma4(acc, a, b); }
 __device__ __forceinline__ void fmav(float2& acc, const float2& a, const float2& b) { acc = __ffma2_rn(a, b, acc); }
 template <int V> struct VecOf { typedef float4 type; };
@@ -66,13 +88,19 @@ __device__ __forceinline__ void zerov(float2& v) { v = make_float2(0.f, 0.f); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float comp(const float2& v, int i) { return i == 0 ? v.x : v.y; }
 
-__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void st4(bf16* p, const float4& v) {
+// store 4 channels in the activation dtype; returns the values as stored (rounded) for the statistics
+__device__ __forceinline__ float4 st4r(float* p, const float4& v) {
+  *reinterpret_cast<float4*>(p) = v;
+  return v;
+}
+__device__ __forceinline__ float4 st4r(bf16* p, const float4& v) {
   uint2 raw;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
   h[0] = __floats2bfloat162_rn(v.x, v.y);
   h[1] = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = raw;
+  return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                     __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const bf16* p) {
@@ -80,16 +108,21 @@ __device__ __forceinline__ float4 ld4(const bf16* p) {
   return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
                      __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
 }
-template <typename T> __device__ __forceinline__ float4 rnd4(const float4& v) {
-  return make_float4(to_f(from_f<T>(v.x)), to_f(from_f<T>(v.y)), to_f(from_f<T>(v.z)), to_f(from_f<T>(v.w)));
-}
 
-// raw 8-channel vector as loaded from global memory
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// one staged 8-channel vector in the thread's private raw area: [u][tid] x sizeof(T)*8 bytes
 template <typename T> struct Raw8;
 template <> struct Raw8<bf16> {
-  uint4 r;
-  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
-  __device__ __forceinline__ void unpack(float v[8]) const {
+  static constexpr int BYTES = 16;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const bf16* src) { cp_async16(dst, src); }
+  static __device__ __forceinline__ void read(const uint8_t* p, float v[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
     v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
     v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
     v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
@@ -97,35 +130,46 @@ template <> struct Raw8<bf16> {
   }
 };
 template <> struct Raw8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = __ldg(reinterpret_cast<const float4*>(p));
-    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  static constexpr int BYTES = 32;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const float* src) {
+    cp_async16(dst, src);
+    cp_async16(dst + 16, src + 4);
   }
-  __device__ __forceinline__ void unpack(float v[8]) const {
+  static __device__ __forceinline__ void read(const uint8_t* p, float v[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 16);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 };
 
+// h_swish(u) = u * relu6(u+3)/6 = u * sat(u/6 + 1/2): one FFMA.SAT + one FMUL
 __device__ __forceinline__ float act_f(float u, int act) {
   if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
-  if (act == TD3D_ACT_HSWISH) return u * (fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f));
+  if (act == TD3D_ACT_HSWISH) return u * __saturatef(fmaf(u, 1.f / 6.f, 0.5f));
   return u;
+}
+__device__ __forceinline__ float act_d(float u, int act) {
+  if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
+  return 1.f;
 }
 
 // ---- per-CTA constants ------------------------------------------------------------------------
-__device__ __forceinline__ void d2_load_consts(D2Consts& k, const XForm& xf, const float* __restrict__ alpha,
-                                               const float* __restrict__ beta, const float* __restrict__ gamma,
-                                               int b0, int nb, int B, int c0, int C) {
-  for (int i = threadIdx.x; i < D2_MAXCG; i += D2_THREADS) {
+template <int CG>
+__device__ __forceinline__ void d2_load_chan_consts(D2Consts<CG>& k, const XForm& xf, const float* __restrict__ beta, int c0,
+                                                    int C) {
+  for (int i = threadIdx.x; i < CG; i += D2_THREADS) {
     const int c = c0 + i;
     const bool on = c < C;
     k.sc[i] = (on && xf.scale) ? xf.scale[c] : 1.f;
     k.sh[i] = (on && xf.scale) ? xf.shift[c] : 0.f;
     k.be[i] = (on && beta) ? beta[c] : 0.f;
   }
-  for (int i = threadIdx.x; i < nb * D2_MAXCG; i += D2_THREADS) {
-    const int n = i / D2_MAXCG, cc = i % D2_MAXCG;
+}
+template <int CG>
+__device__ __forceinline__ void d2_load_sample_consts(D2Consts<CG>& k, const XForm& xf, const float* __restrict__ alpha,
+                                                      const float* __restrict__ gamma, int b0, int nb, int B, int c0, int C) {
+  for (int i = threadIdx.x; i < nb * CG; i += D2_THREADS) {
+    const int n = i / CG, cc = i % CG;
     const int c = c0 + cc, b = b0 + n;
     const bool on = c < C && b < B;
     k.se[n][cc] = (on && xf.se) ? xf.se[(size_t)b * C + c] : 1.f;
@@ -134,66 +178,80 @@ __device__ __forceinline__ void d2_load_consts(D2Consts& k, const XForm& xf, con
   }
 }
 
-// ---- staging ----------------------------------------------------------------------------------
-// Walks the (sample, row, col) items of a [nb][rows][cols] tile for one fixed 8-channel vector per
-// thread, D2_U items at a time (loads first, then transform + store), without divisions in the loop.
-struct D2Walk {
-  int nbi, r, c, dr, dc, rows, cols, nb;
-  __device__ __forceinline__ void init(int rows_, int cols_, int nb_, int nv8) {
-    rows = rows_; cols = cols_; nb = nb_;
-    const int dpix = D2_THREADS / nv8;
-    const int pix = threadIdx.x / nv8;
-    c = pix % cols;
-    const int rr = pix / cols;
-    r = rr % rows; nbi = rr / rows;
-    dc = dpix % cols; dr = dpix / cols;
+// weights [K*K][C] fp32 -> s_w[K*K][CG] (optionally flipped: tap (ky,kx) <- (K-1-ky, K-1-kx))
+template <int K, int CG>
+__device__ __forceinline__ void d2_load_w(float* s_w, const float* __restrict__ w, int c0, int C, bool flip) {
+  for (int i = threadIdx.x; i < K * K * CG; i += D2_THREADS) {
+    const int tap = i / CG, c = c0 + i % CG;
+    const int src = flip ? (K * K - 1 - tap) : tap;
+    s_w[i] = c < C ? w[(size_t)src * C + c] : 0.f;
   }
-  __device__ __forceinline__ bool live() const { return nbi < nb; }
-  __device__ __forceinline__ void next() {
-    c += dc; r += dr;
-    if (c >= cols) { c -= cols; ++r; }
-    while (r >= rows) { r -= rows; ++nbi; }
-  }
-};
+}
 
-// tile[nbi][r][c][ch] = act(se*(scale*x+shift)) for sample b0+nbi, pixel (y0+r, x0+c); zero outside
-template <typename T>
-__device__ __forceinline__ void d2_stage_x(float* __restrict__ tile, const T* __restrict__ x, const D2Consts& k, int act,
-                                           bool has_se, int ps, int nv8, int b0, int B, int H, int W, int C, int c0, int y0,
-                                           int x0, int rows, int cols, int nb) {
-  const int v8 = threadIdx.x % nv8;
-  const int ch = c0 + v8 * 8;
-  const bool ch_ok = ch < C;
-  float sc[8], sh[8];
+// ---- staging ----------------------------------------------------------------------------------
+// A thread stages one fixed 8-channel vector (v8) of pixels pix0, pix0 + 256/NV8, ... of a
+// [nb][rows][cols] tile.  The tile-relative geometry of its items never changes, so it is decoded
+// once per CTA into rc[u] = r | c << 8 | nbi << 16.
+template <int CG>
+__device__ __forceinline__ void d2_items(uint32_t (&rc)[D2_NIT], int rows, int cols, int nb) {
+  const int dpix = D2_THREADS / D2C<CG>::NV8;
+  const int pix0 = threadIdx.x / D2C<CG>::NV8;
+#pragma unroll
+  for (int u = 0; u < D2_NIT; ++u) {
+    const int pix = pix0 + u * dpix;
+    const int c = pix % cols, rr = pix / cols;
+    const int r = rr % rows, n = rr / rows;
+    rc[u] = n < nb ? (uint32_t)(r | (c << 8) | (n << 16)) : D2_DEAD;
+  }
+}
+
+// issue the cp.async fetches of one tile (origin (y0,x0) of sample block b0 in an [B,Hs,Ws,C] tensor);
+// returns the bit mask of the items that lie inside the tensor
+template <typename T, int CG>
+__device__ __forceinline__ uint32_t d2_fetch(uint32_t raw_s, const T* __restrict__ src, const T* __restrict__ src2,
+                                             uint32_t raw2_s, const uint32_t (&rc)[D2_NIT], int nit, int b0, int B, int Hs,
+                                             int Ws, int C, int ch, int y0, int x0) {
+  uint32_t mask = 0;
+  if (ch < C) {
+#pragma unroll
+    for (int u = 0; u < D2_NIT; ++u) {
+      if (u < nit && rc[u] != D2_DEAD) {
+        const int gy = y0 + (int)(rc[u] & 0xffu), gx = x0 + (int)((rc[u] >> 8) & 0xffu), b = b0 + (int)(rc[u] >> 16);
+        if ((unsigned)gy < (unsigned)Hs && (unsigned)gx < (unsigned)Ws && b < B) {
+          const uint32_t off = ((uint32_t)(b * Hs + gy) * (uint32_t)Ws + (uint32_t)gx) * (uint32_t)C + (uint32_t)ch;
+          const uint32_t slot = (uint32_t)(u * D2_THREADS + threadIdx.x) * Raw8<T>::BYTES;
+          Raw8<T>::fetch(raw_s + slot, src + off);
+          if (src2) Raw8<T>::fetch(raw2_s + slot, src2 + off);
+          mask |= 1u << u;
+        }
+      }
+    }
+  }
+  cp_async_commit();
+  return mask;
+}
+
+// raw -> tile[nbi][r][c][ch] = act(se*(scale*x+shift)); zero outside the tensor
+template <typename T, int CG>
+__device__ __forceinline__ void d2_xform_x(float* __restrict__ tile, const uint8_t* __restrict__ raw, uint32_t mask,
+                                           const uint32_t (&rc)[D2_NIT], int nit, int rows, int cols,
+                                           const D2Consts<CG>& k, int act, bool has_se) {
+  const int v8 = threadIdx.x % D2C<CG>::NV8;
+  float sc[8], sh[8];                // re-read per tile: not live across the compute phase
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc[i] = k.sc[v8 * 8 + i]; sh[i] = k.sh[v8 * 8 + i]; }
-  D2Walk w;
-  w.init(rows, cols, nb, nv8);
-  while (w.live()) {
-    Raw8<T> raw[D2_U];
-    float* dst[D2_U];
-    int sn[D2_U];
-    bool ok[D2_U], lv[D2_U];
 #pragma unroll
-    for (int u = 0; u < D2_U; ++u) {
-      lv[u] = w.live();
-      const int gy = y0 + w.r, gx = x0 + w.c, b = b0 + w.nbi;
-      ok[u] = lv[u] && ch_ok && gy >= 0 && gy < H && gx >= 0 && gx < W && b < B;
-      dst[u] = tile + ((size_t)(w.nbi * rows + w.r) * cols + w.c) * ps + v8 * 8;
-      sn[u] = w.nbi;
-      if (ok[u]) raw[u].load(x + (((size_t)b * H + gy) * W + gx) * C + ch);
-      if (lv[u]) w.next();
-    }
-#pragma unroll
-    for (int u = 0; u < D2_U; ++u) {
-      if (!lv[u]) continue;
+  for (int u = 0; u < D2_NIT; ++u) {
+    if (u < nit && rc[u] != D2_DEAD) {
+      const int r = rc[u] & 0xffu, c = (rc[u] >> 8) & 0xffu, n = rc[u] >> 16;
+      float* dst = tile + ((n * rows + r) * cols + c) * D2C<CG>::PS + v8 * 8;
       float v[8];
-      if (ok[u]) {
-        raw[u].unpack(v);
+      if ((mask >> u) & 1u) {
+        Raw8<T>::read(raw + (size_t)(u * D2_THREADS + threadIdx.x) * Raw8<T>::BYTES, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
         if (has_se) {
-          const float4 e0 = lds4(&k.se[sn[u]][v8 * 8]), e1 = lds4(&k.se[sn[u]][v8 * 8 + 4]);
+          const float4 e0 = lds4(&k.se[n][v8 * 8]), e1 = lds4(&k.se[n][v8 * 8 + 4]);
           v[0] *= e0.x; v[1] *= e0.y; v[2] *= e0.z; v[3] *= e0.w;
           v[4] *= e1.x; v[5] *= e1.y; v[6] *= e1.z; v[7] *= e1.w;
         }
@@ -203,55 +261,34 @@ __device__ __forceinline__ void d2_stage_x(float* __restrict__ tile, const T* __
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
-      sts4(dst[u], v[0], v[1], v[2], v[3]);
-      sts4(dst[u] + 4, v[4], v[5], v[6], v[7]);
+      sts4(dst, v[0], v[1], v[2], v[3]);
+      sts4(dst + 4, v[4], v[5], v[6], v[7]);
     }
   }
 }
 
-// tile[nbi][r][c][ch] = alpha*g + beta*y + gamma for output pixel (y0+r, x0+c); zero outside
-template <typename T>
-__device__ __forceinline__ void d2_stage_gy(float* __restrict__ tile, const T* __restrict__ g, const T* __restrict__ yo,
-                                            const D2Consts& k, int ps, int nv8, int b0, int B, int Ho, int Wo, int C, int c0,
-                                            int y0, int x0, int rows, int cols, int nb) {
-  const int v8 = threadIdx.x % nv8;
-  const int ch = c0 + v8 * 8;
-  const bool ch_ok = ch < C;
+// raw (g, y) -> tile = alpha*g + beta*y + gamma; zero outside the tensor
+template <typename T, int CG>
+__device__ __forceinline__ void d2_xform_gy(float* __restrict__ tile, const uint8_t* __restrict__ raw_g,
+                                            const uint8_t* __restrict__ raw_y, uint32_t mask, const uint32_t (&rc)[D2_NIT],
+                                            int nit, int rows, int cols, const D2Consts<CG>& k) {
+  const int v8 = threadIdx.x % D2C<CG>::NV8;
   float be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) be[i] = k.be[v8 * 8 + i];
-  D2Walk w;
-  w.init(rows, cols, nb, nv8);
-  constexpr int U = D2_U / 2;
-  while (w.live()) {
-    Raw8<T> rg[U], ry[U];
-    float* dst[U];
-    int sn[U];
-    bool ok[U], lv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      lv[u] = w.live();
-      const int gy = y0 + w.r, gx = x0 + w.c, b = b0 + w.nbi;
-      ok[u] = lv[u] && ch_ok && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo && b < B;
-      dst[u] = tile + ((size_t)(w.nbi * rows + w.r) * cols + w.c) * ps + v8 * 8;
-      sn[u] = w.nbi;
-      if (ok[u]) {
-        const size_t off = (((size_t)b * Ho + gy) * Wo + gx) * C + ch;
-        rg[u].load(g + off);
-        ry[u].load(yo + off);
-      }
-      if (lv[u]) w.next();
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!lv[u]) continue;
+  for (int u = 0; u < D2_NIT; ++u) {
+    if (u < nit && rc[u] != D2_DEAD) {
+      const int r = rc[u] & 0xffu, c = (rc[u] >> 8) & 0xffu, n = rc[u] >> 16;
+      float* dst = tile + ((n * rows + r) * cols + c) * D2C<CG>::PS + v8 * 8;
       float v[8];
-      if (ok[u]) {
+      if ((mask >> u) & 1u) {
         float yv[8];
-        rg[u].unpack(v);
-        ry[u].unpack(yv);
-        const float4 a0 = lds4(&k.al[sn[u]][v8 * 8]), a1 = lds4(&k.al[sn[u]][v8 * 8 + 4]);
-        const float4 g0 = lds4(&k.ga[sn[u]][v8 * 8]), g1 = lds4(&k.ga[sn[u]][v8 * 8 + 4]);
+        const size_t slot = (size_t)(u * D2_THREADS + threadIdx.x) * Raw8<T>::BYTES;
+        Raw8<T>::read(raw_g + slot, v);
+        Raw8<T>::read(raw_y + slot, yv);
+        const float4 a0 = lds4(&k.al[n][v8 * 8]), a1 = lds4(&k.al[n][v8 * 8 + 4]);
+        const float4 g0 = lds4(&k.ga[n][v8 * 8]), g1 = lds4(&k.ga[n][v8 * 8 + 4]);
         v[0] = fmaf(a0.x, v[0], fmaf(be[0], yv[0], g0.x)); v[1] = fmaf(a0.y, v[1], fmaf(be[1], yv[1], g0.y));
         v[2] = fmaf(a0.z, v[2], fmaf(be[2], yv[2], g0.z)); v[3] = fmaf(a0.w, v[3], fmaf(be[3], yv[3], g0.w));
         v[4] = fmaf(a1.x, v[4], fmaf(be[4], yv[4], g1.x)); v[5] = fmaf(a1.y, v[5], fmaf(be[5], yv[5], g1.y));
@@ -260,44 +297,28 @@ __device__ __forceinline__ void d2_stage_gy(float* __restrict__ tile, const T* _
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
-      sts4(dst[u], v[0], v[1], v[2], v[3]);
-      sts4(dst[u] + 4, v[4], v[5], v[6], v[7]);
+      sts4(dst, v[0], v[1], v[2], v[3]);
+      sts4(dst + 4, v[4], v[5], v[6], v[7]);
     }
   }
 }
 
-// weights [K*K][C] fp32 -> s_w[K*K][D2_MAXCG] (optionally flipped: tap (ky,kx) <- (K-1-ky, K-1-kx))
-template <int K>
-__device__ __forceinline__ void d2_load_w(float* s_w, const float* __restrict__ w, int c0, int C, bool flip) {
-  for (int i = threadIdx.x; i < K * K * D2_MAXCG; i += D2_THREADS) {
-    const int tap = i / D2_MAXCG, c = c0 + i % D2_MAXCG;
-    const int src = flip ? (K * K - 1 - tap) : tap;
-    s_w[i] = c < C ? w[(size_t)src * C + c] : 0.f;
-  }
-}
-
 // out[oy][ox] = sum_{ky,kx} tile[(oy*S+ky)][(ox*S+kx)] * w[ky][kx] for a thread's OY x OX outputs
-template <int K, int S, int OY, int OX>
-__device__ __forceinline__ void d2_conv(float4 (&acc)[OY][OX], const float* base, int row_stride, int ps,
-                                        const float* s_wq) {
-  constexpr int NR = (OY - 1) * S + K, NC = (OX - 1) * S + K;
-  float4 wreg[K == 3 ? 9 : 1];
-  if (K == 3) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) wreg[i] = lds4(s_wq + i * D2_MAXCG);
-  }
+template <int K, int S, int OY, int OX, int CG>
+__device__ __forceinline__ void d2_conv(float4 (&acc)[OY][OX], const float* base, int row_stride, const float* s_wq) {
+  constexpr int NR = (OY - 1) * S + K, NC = (OX - 1) * S + K, PS = D2C<CG>::PS;
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     float4 row[NC];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) row[j] = lds4(base + r * row_stride + j * ps);
+    for (int j = 0; j < NC; ++j) row[j] = lds4(base + r * row_stride + j * PS);
 #pragma unroll
     for (int oy = 0; oy < OY; ++oy) {
       const int ky = r - oy * S;
       if (ky < 0 || ky >= K) continue;
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const float4 wv = K == 3 ? wreg[ky * K + kx] : lds4(s_wq + (ky * K + kx) * D2_MAXCG);
+        const float4 wv = lds4(s_wq + (ky * K + kx) * CG);
 #pragma unroll
         for (int ox = 0; ox < OX; ++ox) fma4(acc[oy][ox], row[ox * S + kx], wv);
       }
@@ -305,25 +326,26 @@ __device__ __forceinline__ void d2_conv(float4 (&acc)[OY][OX], const float* base
   }
 }
 
-// per-(sample, channel) sums: thread partials -> smem [sp][2][cg] -> column sums -> one global atomic
-__device__ __forceinline__ void d2_reduce_stats(float* part, const float4& s1, const float4& s2, int sp, int q, int cg,
-                                                int per_sample, int nb, float* __restrict__ stats, int b0, int B, int c0,
-                                                int C) {
-  __syncthreads();                                   // everybody is done reading the tile
-  float* mine = part + (size_t)sp * 2 * cg + q * 4;
-  st4(mine, s1);
-  st4(mine + cg, s2);
+// per-(sample, channel) sums: thread partials -> smem [sp][2][CG] -> column sums -> one global atomic
+template <int CG>
+__device__ __forceinline__ void d2_flush_stats(float* part, float4& s1, float4& s2, int sp, int q, int per_sample, int nb,
+                                               float* __restrict__ stats, int b0, int B, int c0, int C) {
+  float* mine = part + (size_t)sp * 2 * CG + q * 4;
+  *reinterpret_cast<float4*>(mine) = s1;
+  *reinterpret_cast<float4*>(mine + CG) = s2;
   __syncthreads();
-  for (int t = threadIdx.x; t < nb * 2 * cg; t += D2_THREADS) {
-    const int n = t / (2 * cg), j = t % (2 * cg);
+  for (int t = threadIdx.x; t < nb * 2 * CG; t += D2_THREADS) {
+    const int n = t / (2 * CG), j = t % (2 * CG);
     float s = 0.f;
-    for (int i = 0; i < per_sample; ++i) s += part[(size_t)(n * per_sample + i) * 2 * cg + j];
-    const int which = j / cg, c = c0 + j % cg, b = b0 + n;
+    for (int i = 0; i < per_sample; ++i) s += part[(size_t)(n * per_sample + i) * 2 * CG + j];
+    const int which = j / CG, c = c0 + j % CG, b = b0 + n;
     if (c < C && b < B) atomicAdd(&stats[((size_t)b * 2 + which) * C + c], s);
   }
+  s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  s2 = s1;
 }
 
-struct D2Map {       // thread -> (channel quad, sample, thread-tile)
+struct D2Map {       // thread -> (channel vector, sample, thread-tile)
   int q, sp, nbi, ty, tx;
   bool active;
   __device__ __forceinline__ void init(const D2Tile& t, int nqv) {
@@ -336,286 +358,356 @@ struct D2Map {       // thread -> (channel quad, sample, thread-tile)
   }
 };
 
-__device__ __forceinline__ void d2_block(const D2Tile& t, int& b0, int& ty0, int& tx0) {
-  const int bx = blockIdx.x;
-  tx0 = (bx % t.tiles_x) * t.tw;
-  ty0 = ((bx / t.tiles_x) % t.tiles_y) * t.th;
-  b0 = (bx / (t.tiles_x * t.tiles_y)) * t.nb;
-}
+struct D2Item {      // walks the CTA's contiguous item range: item = (bb * tiles_y + tyi) * tiles_x + txi
+  int bb, tyi, txi;
+  __device__ __forceinline__ void init(const D2Tile& t, int item) {
+    txi = item % t.tiles_x;
+    tyi = (item / t.tiles_x) % t.tiles_y;
+    bb = item / (t.tiles_x * t.tiles_y);
+  }
+  __device__ __forceinline__ void next(const D2Tile& t) {
+    if (++txi == t.tiles_x) { txi = 0; if (++tyi == t.tiles_y) { tyi = 0; ++bb; } }
+  }
+};
 
 template <int S> struct D2Geo { static constexpr int OY = S == 1 ? 2 : 1, OX = 4; };
+
+// dynamic smem: [fp32 tile(s)] [stats partials / weight-gradient partials] [raw area(s)]
+struct D2Smem { uint32_t tile_floats, tile2_floats, part_floats, raw_bytes, raw2_bytes; };
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <typename T, int K, int S>
-__global__ void __launch_bounds__(D2_THREADS, K == 3 ? 3 : 2)
+template <typename T, int K, int S, int CG>
+__global__ void __launch_bounds__(D2_THREADS, 2)
 d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T* __restrict__ y,
-              float* __restrict__ stats, int B, int H, int W, int Ho, int Wo, int C, D2Tile t) {
-  constexpr int P = (K - 1) / 2, OY = D2Geo<S>::OY, OX = D2Geo<S>::OX;
-  extern __shared__ __align__(16) float d2_smem[];
-  __shared__ D2Consts kc;
-  __shared__ __align__(16) float s_w[K * K * D2_MAXCG];
-  float* tile = d2_smem;
-  int b0, ty0, tx0;
-  d2_block(t, b0, ty0, tx0);
-  const int c0 = blockIdx.y * t.cg;
-  d2_load_consts(kc, xf, nullptr, nullptr, nullptr, b0, t.nb, B, c0, C);
-  d2_load_w<K>(s_w, w, c0, C, false);
-  __syncthreads();
-  d2_stage_x<T>(tile, x, kc, xf.act, xf.se != nullptr, t.ps, t.nv8, b0, B, H, W, C, c0, ty0 * S - P, tx0 * S - P, t.ih,
-                t.iw, t.nb);
-  __syncthreads();
+              float* __restrict__ stats, int B, int H, int W, int Ho, int Wo, int C, D2Tile t, D2Smem sm) {
+  constexpr int P = (K - 1) / 2, OY = D2Geo<S>::OY, OX = D2Geo<S>::OX, PS = D2C<CG>::PS;
+  extern __shared__ __align__(16) uint8_t d2_smem[];
+  __shared__ D2Consts<CG> kc;
+  __shared__ __align__(16) float s_w[K * K * CG];
+  float* tile = reinterpret_cast<float*>(d2_smem);
+  float* part = tile + sm.tile_floats;
+  uint8_t* raw = reinterpret_cast<uint8_t*>(part + sm.part_floats);
+  const uint32_t raw_s = s_u32(raw);
+  const int c0 = blockIdx.y * CG;
+  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
+  const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
+  d2_load_chan_consts<CG>(kc, xf, nullptr, c0, C);
+  d2_load_w<K, CG>(s_w, w, c0, C, false);
+  uint32_t rc[D2_NIT];
+  d2_items<CG>(rc, t.ih, t.iw, t.nb);
   D2Map m;
-  m.init(t, t.cg / 4);
-  float4 acc[OY][OX];
-#pragma unroll
-  for (int i = 0; i < OY; ++i)
-#pragma unroll
-    for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  m.init(t, D2C<CG>::NQ);
+  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  __syncthreads();
+  const bool has_se = xf.se != nullptr;
+  D2Item cur, nxt;
+  cur.init(t, it0);
+  uint32_t mask = d2_fetch<T, CG>(raw_s, x, nullptr, 0u, rc, t.nit, cur.bb * t.nb, B, H, W, C, ch, cur.tyi * t.th * S - P,
+                                  cur.txi * t.tw * S - P);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  if (m.active) {
-    const float* base = tile + ((size_t)(m.nbi * t.ih + m.ty * OY * S) * t.iw + m.tx * OX * S) * t.ps + m.q * 4;
-    d2_conv<K, S, OY, OX>(acc, base, t.iw * t.ps, t.ps, s_w + m.q * 4);
-    const int b = b0 + m.nbi, c = c0 + m.q * 4;
-    if (b < B && c < C) {
+  int cur_bb = -1;
+  const int c = c0 + m.q * 4;
+  const float* s_wq = s_w + m.q * 4;
+  const int row_stride = t.iw * PS;
+  const float* base = tile + ((m.nbi * t.ih + m.ty * OY * S) * t.iw + m.tx * OX * S) * PS + m.q * 4;
+  for (int item = it0; item < it1; ++item) {
+    const int b0 = cur.bb * t.nb, ty0 = cur.tyi * t.th, tx0 = cur.txi * t.tw;
+    if (cur.bb != cur_bb) {
+      if (has_se || (stats && cur_bb >= 0)) __syncthreads();     // previous tile fully consumed (kc.se, part)
+      if (stats && cur_bb >= 0)
+        d2_flush_stats<CG>(part, s1, s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
+      if (has_se) d2_load_sample_consts<CG>(kc, xf, nullptr, nullptr, b0, t.nb, B, c0, C);
+      cur_bb = cur.bb;
+    }
+    cp_async_wait_all();
+    __syncthreads();                                  // previous compute done with the tile; constants visible
+    d2_xform_x<T, CG>(tile, raw, mask, rc, t.nit, t.ih, t.iw, kc, xf.act, has_se);
+    __syncthreads();
+    nxt = cur;
+    nxt.next(t);
+    if (item + 1 < it1)
+      mask = d2_fetch<T, CG>(raw_s, x, nullptr, 0u, rc, t.nit, nxt.bb * t.nb, B, H, W, C, ch, nxt.tyi * t.th * S - P,
+                             nxt.txi * t.tw * S - P);
+    if (m.active) {
+      float4 acc[OY][OX];
 #pragma unroll
-      for (int oy = 0; oy < OY; ++oy) {
-        const int yy = ty0 + m.ty * OY + oy;
-        if (yy >= Ho) continue;
+      for (int i = 0; i < OY; ++i)
 #pragma unroll
-        for (int ox = 0; ox < OX; ++ox) {
-          const int xx = tx0 + m.tx * OX + ox;
-          if (xx >= Wo) continue;
-          st4(y + (((size_t)b * Ho + yy) * Wo + xx) * C + c, acc[oy][ox]);
-          const float4 r = rnd4<T>(acc[oy][ox]);
-          s1.x += r.x; s1.y += r.y; s1.z += r.z; s1.w += r.w;
-          fma4(s2, r, r);
+        for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      d2_conv<K, S, OY, OX, CG>(acc, base, row_stride, s_wq);
+      const int b = b0 + m.nbi, yy0 = ty0 + m.ty * OY, xx0 = tx0 + m.tx * OX;
+      if (b < B && c < C) {
+        T* yb = y + (((size_t)b * Ho + yy0) * Wo + xx0) * C + c;
+#pragma unroll
+        for (int oy = 0; oy < OY; ++oy) {
+          if (yy0 + oy >= Ho) continue;
+#pragma unroll
+          for (int ox = 0; ox < OX; ++ox) {
+            if (xx0 + ox >= Wo) continue;
+            const float4 r = st4r(yb + (oy * Wo + ox) * C, acc[oy][ox]);
+            add4(s1, r);
+            fma4(s2, r, r);
+          }
         }
       }
     }
+    cur = nxt;
   }
-  if (stats) d2_reduce_stats(tile, s1, s2, m.sp, m.q, t.cg, t.tyt * t.txt, t.nb, stats, b0, B, c0, C);
+  if (stats && cur_bb >= 0) {
+    __syncthreads();
+    d2_flush_stats<CG>(part, s1, s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward data, stride 1: correlation of the staged gy tile with the flipped filter
+// backward data.  Stride 1: correlation of the staged gy tile with the flipped filter.  Stride 2:
+// the owned grid is the coarse (= output) grid; a thread produces the 2x2 input pixels under each
+// of its 2x2 coarse positions; tap (ky,kx) feeds exactly one of the four input parities with a
+// compile-time gy offset: no divergence, no wasted multiply.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_d(float u, int act) {
-  if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-  if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
-  return 1.f;
-}
-
 struct D2Fin {       // epilogue of the data gradient: gx = acc * act'(u(x)), statistics of the stored value
   float4 sc, sh, se, s1, s2;
   int act;
   template <typename T>
-  __device__ __forceinline__ void apply(float4 acc, const T* __restrict__ x, T* __restrict__ gx, size_t off) {
-    const float4 xv = ld4(x + off);
+  __device__ __forceinline__ void apply(float4 acc, const T* __restrict__ xp, T* __restrict__ gp) {
+    const float4 xv = ld4(xp);
     acc.x *= act_d(se.x * fmaf(xv.x, sc.x, sh.x), act);
     acc.y *= act_d(se.y * fmaf(xv.y, sc.y, sh.y), act);
     acc.z *= act_d(se.z * fmaf(xv.z, sc.z, sh.z), act);
     acc.w *= act_d(se.w * fmaf(xv.w, sc.w, sh.w), act);
-    st4(gx + off, acc);
-    const float4 r = rnd4<T>(acc);
-    s1.x += r.x; s1.y += r.y; s1.z += r.z; s1.w += r.w;
+    const float4 r = st4r(gp, acc);
+    add4(s1, r);
     fma4(s2, r, xv);
   }
 };
 
-template <typename T, int K>
-__global__ void __launch_bounds__(D2_THREADS, K == 3 ? 3 : 2)
-d2_bwd_data_s1_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
-                      const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
-                      const float* __restrict__ w, T* __restrict__ gx, float* __restrict__ stats, int B, int H, int W, int C,
-                      D2Tile t) {
-  constexpr int P = (K - 1) / 2, OY = 2, OX = 4;
-  extern __shared__ __align__(16) float d2_smem[];
-  __shared__ D2Consts kc;
-  __shared__ __align__(16) float s_w[K * K * D2_MAXCG];
-  float* tile = d2_smem;
-  int b0, ty0, tx0;
-  d2_block(t, b0, ty0, tx0);
-  const int c0 = blockIdx.y * t.cg;
-  d2_load_consts(kc, xf, alpha, beta, gamma, b0, t.nb, B, c0, C);
-  d2_load_w<K>(s_w, w, c0, C, true);
-  __syncthreads();
-  d2_stage_gy<T>(tile, g, yo, kc, t.ps, t.nv8, b0, B, H, W, C, c0, ty0 - P, tx0 - P, t.ih, t.iw, t.nb);
-  __syncthreads();
-  D2Map m;
-  m.init(t, t.cg / 4);
-  D2Fin fin;
-  fin.s1 = make_float4(0.f, 0.f, 0.f, 0.f); fin.s2 = fin.s1; fin.act = xf.act;
-  if (m.active) {
-    float4 acc[OY][OX];
-#pragma unroll
-    for (int i = 0; i < OY; ++i)
-#pragma unroll
-      for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* base = tile + ((size_t)(m.nbi * t.ih + m.ty * OY) * t.iw + m.tx * OX) * t.ps + m.q * 4;
-    d2_conv<K, 1, OY, OX>(acc, base, t.iw * t.ps, t.ps, s_w + m.q * 4);
-    const int b = b0 + m.nbi, c = c0 + m.q * 4;
-    if (b < B && c < C) {
-      fin.sc = lds4(&kc.sc[m.q * 4]); fin.sh = lds4(&kc.sh[m.q * 4]); fin.se = lds4(&kc.se[m.nbi][m.q * 4]);
-#pragma unroll
-      for (int oy = 0; oy < OY; ++oy) {
-        const int yy = ty0 + m.ty * OY + oy;
-        if (yy >= H) continue;
-#pragma unroll
-        for (int ox = 0; ox < OX; ++ox) {
-          const int xx = tx0 + m.tx * OX + ox;
-          if (xx >= W) continue;
-          fin.apply<T>(acc[oy][ox], x, gx, (((size_t)b * H + yy) * W + xx) * C + c);
-        }
-      }
-    }
-  }
-  if (stats) d2_reduce_stats(tile, fin.s1, fin.s2, m.sp, m.q, t.cg, t.tyt * t.txt, t.nb, stats, b0, B, c0, C);
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward data, stride 2.  The owned grid is the coarse (= output) grid; a thread produces the
-// 2x2 input pixels under each of its two coarse positions.  Tap (ky,kx) feeds exactly one of the
-// four input parities with a compile-time gy offset: no divergence, no wasted multiply.
-// ------------------------------------------------------------------------------------------------
-template <typename T, int K>
+template <typename T, int K, int S, int CG>
 __global__ void __launch_bounds__(D2_THREADS, 2)
-d2_bwd_data_s2_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
-                      const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
-                      const float* __restrict__ w, T* __restrict__ gx, float* __restrict__ stats, int B, int H, int W, int Ho,
-                      int Wo, int C, D2Tile t) {
-  constexpr int P = (K - 1) / 2, OXC = 2, OYC = 2;
-  extern __shared__ __align__(16) float d2_smem[];
-  __shared__ D2Consts kc;
-  __shared__ __align__(16) float s_w[K * K * D2_MAXCG];
-  float* tile = d2_smem;
-  int b0, ty0, tx0;
-  d2_block(t, b0, ty0, tx0);
-  const int c0 = blockIdx.y * t.cg;
-  d2_load_consts(kc, xf, alpha, beta, gamma, b0, t.nb, B, c0, C);
-  d2_load_w<K>(s_w, w, c0, C, false);
-  __syncthreads();
-  d2_stage_gy<T>(tile, g, yo, kc, t.ps, t.nv8, b0, B, Ho, Wo, C, c0, ty0 - 1, tx0 - 1, t.ih, t.iw, t.nb);
-  __syncthreads();
+d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
+                   const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
+                   const float* __restrict__ w, T* __restrict__ gx, float* __restrict__ stats, int B, int H, int W, int Ho,
+                   int Wo, int C, D2Tile t, D2Smem sm) {
+  constexpr int P = (K - 1) / 2, PS = D2C<CG>::PS;
+  constexpr int HALO = S == 1 ? P : 1;              // staged halo (pixels of the gy grid) on each side
+  extern __shared__ __align__(16) uint8_t d2_smem[];
+  __shared__ D2Consts<CG> kc;
+  __shared__ __align__(16) float s_w[K * K * CG];
+  float* tile = reinterpret_cast<float*>(d2_smem);
+  float* part = tile + sm.tile_floats;
+  uint8_t* raw_g = reinterpret_cast<uint8_t*>(part + sm.part_floats);
+  uint8_t* raw_y = raw_g + sm.raw_bytes;
+  const uint32_t rawg_s = s_u32(raw_g), rawy_s = s_u32(raw_y);
+  const int c0 = blockIdx.y * CG;
+  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
+  const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
+  d2_load_chan_consts<CG>(kc, xf, beta, c0, C);
+  d2_load_w<K, CG>(s_w, w, c0, C, S == 1);
+  uint32_t rc[D2_NIT];
+  d2_items<CG>(rc, t.ih, t.iw, t.nb);
   D2Map m;
-  m.init(t, t.cg / 4);
+  m.init(t, D2C<CG>::NQ);
+  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  __syncthreads();
+  D2Item cur, nxt;
+  cur.init(t, it0);
+  uint32_t mask = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rc, t.nit, cur.bb * t.nb, B, Ho, Wo, C, ch, cur.tyi * t.th - HALO,
+                                  cur.txi * t.tw - HALO);
   D2Fin fin;
   fin.s1 = make_float4(0.f, 0.f, 0.f, 0.f); fin.s2 = fin.s1; fin.act = xf.act;
-  if (m.active) {
-    const int b = b0 + m.nbi, c = c0 + m.q * 4;
-    fin.sc = lds4(&kc.sc[m.q * 4]); fin.sh = lds4(&kc.sh[m.q * 4]); fin.se = lds4(&kc.se[m.nbi][m.q * 4]);
-#pragma unroll 1
-    for (int rr = 0; rr < OYC; ++rr) {
-    const int cy = m.ty * OYC + rr;                // coarse row inside the tile
-    // window: coarse rows cy-1..cy+1 (tile rows cy..cy+2), coarse cols tx*2-1 .. tx*2+2 (tile cols tx*2 .. tx*2+3)
-    float4 win[3][OXC + 2];
-    const float* base = tile + ((size_t)(m.nbi * t.ih + cy) * t.iw + m.tx * OXC) * t.ps + m.q * 4;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int j = 0; j < OXC + 2; ++j) win[r][j] = lds4(base + (r * t.iw + j) * t.ps);
-    float4 acc[OXC][2][2];
-#pragma unroll
-    for (int i = 0; i < OXC; ++i)
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 2; ++bb) acc[i][a][bb] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      const int a = (ky + P) & 1;                  // input-row parity fed by this tap
-      const int dy = (a + P - ky) / 2;             // exact (a + P - ky is even); in [-1, 1]
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const int bb = (kx + P) & 1;
-        const int dx = (bb + P - kx) / 2;
-        const float4 wv = lds4(s_w + (ky * K + kx) * D2_MAXCG + m.q * 4);
-#pragma unroll
-        for (int i = 0; i < OXC; ++i) fma4(acc[i][a][bb], win[1 + dy][i + 1 + dx], wv);
-      }
+  fin.sc = lds4(&kc.sc[m.q * 4]); fin.sh = lds4(&kc.sh[m.q * 4]);
+  int cur_bb = -1;
+  const int c = c0 + m.q * 4;
+  const float* s_wq = s_w + m.q * 4;
+  const int row_stride = t.iw * PS;
+  for (int item = it0; item < it1; ++item) {
+    const int b0 = cur.bb * t.nb, ty0 = cur.tyi * t.th, tx0 = cur.txi * t.tw;
+    if (cur.bb != cur_bb) {
+      __syncthreads();                                // previous tile fully consumed (kc.al/ga/se, part)
+      if (stats && cur_bb >= 0)
+        d2_flush_stats<CG>(part, fin.s1, fin.s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
+      d2_load_sample_consts<CG>(kc, xf, alpha, gamma, b0, t.nb, B, c0, C);
+      cur_bb = cur.bb;
     }
-    if (b < B && c < C) {
+    cp_async_wait_all();
+    __syncthreads();
+    d2_xform_gy<T, CG>(tile, raw_g, raw_y, mask, rc, t.nit, t.ih, t.iw, kc);
+    __syncthreads();
+    nxt = cur;
+    nxt.next(t);
+    if (item + 1 < it1)
+      mask = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rc, t.nit, nxt.bb * t.nb, B, Ho, Wo, C, ch, nxt.tyi * t.th - HALO,
+                             nxt.txi * t.tw - HALO);
+    if (m.active) {
+      const int b = b0 + m.nbi;
+      const bool live = b < B && c < C;
+      fin.se = lds4(&kc.se[m.nbi][m.q * 4]);
+      if (S == 1) {
+        constexpr int OY = 2, OX = 4;
+        float4 acc[OY][OX];
 #pragma unroll
-      for (int i = 0; i < OXC; ++i)
+        for (int i = 0; i < OY; ++i)
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const int hh = 2 * (ty0 + cy) + a;
-          if (hh >= H) continue;
+          for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = tile + ((m.nbi * t.ih + m.ty * OY) * t.iw + m.tx * OX) * PS + m.q * 4;
+        d2_conv<K, 1, OY, OX, CG>(acc, base, row_stride, s_wq);
+        const int yy0 = ty0 + m.ty * OY, xx0 = tx0 + m.tx * OX;
+        if (live) {
+          const size_t o0 = (((size_t)b * H + yy0) * W + xx0) * C + c;
 #pragma unroll
-          for (int bb = 0; bb < 2; ++bb) {
-            const int ww = 2 * (tx0 + m.tx * OXC + i) + bb;
-            if (ww >= W) continue;
-            fin.apply<T>(acc[i][a][bb], x, gx, (((size_t)b * H + hh) * W + ww) * C + c);
+          for (int oy = 0; oy < OY; ++oy) {
+            if (yy0 + oy >= H) continue;
+#pragma unroll
+            for (int ox = 0; ox < OX; ++ox) {
+              if (xx0 + ox >= W) continue;
+              const size_t o = o0 + (size_t)((oy * W + ox) * C);
+              fin.apply<T>(acc[oy][ox], x + o, gx + o);
+            }
           }
         }
+      } else {
+        constexpr int OYC = 2, OXC = 2;
+#pragma unroll 1
+        for (int rr = 0; rr < OYC; ++rr) {
+          const int cy = m.ty * OYC + rr;            // coarse row inside the tile
+          // window: coarse rows cy-1..cy+1 (tile rows cy..cy+2), coarse cols tx*2-1..tx*2+2 (tile cols tx*2..tx*2+3)
+          float4 win[3][OXC + 2];
+          const float* base = tile + ((m.nbi * t.ih + cy) * t.iw + m.tx * OXC) * PS + m.q * 4;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int j = 0; j < OXC + 2; ++j) win[r][j] = lds4(base + r * row_stride + j * PS);
+          float4 acc[OXC][2][2];
+#pragma unroll
+          for (int i = 0; i < OXC; ++i)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int bb = 0; bb < 2; ++bb) acc[i][a][bb] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int ky = 0; ky < K; ++ky) {
+            const int a = (ky + P) & 1;              // input-row parity fed by this tap
+            const int dy = (a + P - ky) / 2;         // exact (a + P - ky is even); in [-1, 1]
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+              const int bb = (kx + P) & 1;
+              const int dx = (bb + P - kx) / 2;
+              const float4 wv = lds4(s_wq + (ky * K + kx) * CG);
+#pragma unroll
+              for (int i = 0; i < OXC; ++i) fma4(acc[i][a][bb], win[1 + dy][i + 1 + dx], wv);
+            }
+          }
+          if (live) {
+            const int hh0 = 2 * (ty0 + cy), ww0 = 2 * (tx0 + m.tx * OXC);
+            const size_t o0 = (((size_t)b * H + hh0) * W + ww0) * C + c;
+#pragma unroll
+            for (int i = 0; i < OXC; ++i)
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                if (hh0 + a >= H) continue;
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                  if (ww0 + 2 * i + bb >= W) continue;
+                  const size_t o = o0 + (size_t)((a * W + 2 * i + bb) * C);
+                  fin.apply<T>(acc[i][a][bb], x + o, gx + o);
+                }
+              }
+          }
+        }
+      }
     }
-    }
+    cur = nxt;
   }
-  if (stats) d2_reduce_stats(tile, fin.s1, fin.s2, m.sp, m.q, t.cg, t.tyt * t.txt, t.nb, stats, b0, B, c0, C);
+  if (stats && cur_bb >= 0) {
+    __syncthreads();
+    d2_flush_stats<CG>(part, fin.s1, fin.s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward weights: persistent CTAs (grid.x) over (sample block, tile) items of one channel group
-// (grid.y).  A thread owns V channels x (OY x OX) outputs; its K*K tap accumulators live in registers
-// across all items and leave the CTA once (shuffle -> smem -> one global atomic per tap and channel).
+// backward weights.  A thread owns V channels x (OY x OX) outputs; its K*K tap accumulators live in
+// registers across all items and leave the CTA once (shuffle -> smem -> one global atomic per tap
+// and channel).  Both operand tiles (x_t with halo, gy) are prefetched like in the other kernels.
 // ------------------------------------------------------------------------------------------------
 template <int K, int S> struct D2WGeo {
   static constexpr int V = K == 3 ? 4 : 2;
   static constexpr int OY = S == 1 ? 2 : 1, OX = 4;
 };
 
-template <typename T, int K, int S>
+template <typename T, int K, int S, int CG>
 __global__ void __launch_bounds__(D2_THREADS, 2)
 d2_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
                      const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
-                     float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int C, D2Tile t, int items_per_cta) {
+                     float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int C, D2Tile t, D2Smem sm) {
   constexpr int P = (K - 1) / 2, V = D2WGeo<K, S>::V, OY = D2WGeo<K, S>::OY, OX = D2WGeo<K, S>::OX;
-  constexpr int NR = (OY - 1) * S + K, NC = (OX - 1) * S + K;
+  constexpr int NR = (OY - 1) * S + K, NC = (OX - 1) * S + K, PS = D2C<CG>::PS;
   typedef typename VecOf<V>::type VT;
-  extern __shared__ __align__(16) float d2_smem[];
-  __shared__ D2Consts kc;
-  float* xt = d2_smem;                                        // [nb][ih][iw][ps]
-  float* gt = xt + (size_t)t.nb * t.ih * t.iw * t.ps;         // [nb][th][tw][ps]
-  const int c0 = blockIdx.y * t.cg;
-  const int nqv = t.cg / V;
+  extern __shared__ __align__(16) uint8_t d2_smem[];
+  __shared__ D2Consts<CG> kc;
+  float* xt = reinterpret_cast<float*>(d2_smem);             // [nb][ih][iw][PS]
+  float* gt = xt + sm.tile_floats;                            // [nb][th][tw][PS]
+  float* part = gt + sm.tile2_floats;                         // [8 warps][K*K][CG]
+  uint8_t* raw_x = reinterpret_cast<uint8_t*>(part + sm.part_floats);
+  uint8_t* raw_g = raw_x + sm.raw_bytes;
+  uint8_t* raw_y = raw_g + sm.raw2_bytes;
+  const uint32_t rawx_s = s_u32(raw_x), rawg_s = s_u32(raw_g), rawy_s = s_u32(raw_y);
+  const int c0 = blockIdx.y * CG;
+  constexpr int NQV = CG / V;
+  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
+  const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
+  d2_load_chan_consts<CG>(kc, xf, beta, c0, C);
+  uint32_t rcx[D2_NIT], rcg[D2_NIT];
+  d2_items<CG>(rcx, t.ih, t.iw, t.nb);
+  d2_items<CG>(rcg, t.th, t.tw, t.nb);
   D2Map m;
-  m.init(t, nqv);
+  m.init(t, NQV);
+  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  __syncthreads();
+  const bool has_se = xf.se != nullptr;
   VT acc[K * K];
 #pragma unroll
   for (int i = 0; i < K * K; ++i) zerov(acc[i]);
-  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
-  const int it0 = blockIdx.x * items_per_cta;
-  const int it1 = min(n_items, it0 + items_per_cta);
+  D2Item cur, nxt;
+  cur.init(t, it0);
+  uint32_t mx = d2_fetch<T, CG>(rawx_s, x, nullptr, 0u, rcx, t.nit, cur.bb * t.nb, B, H, W, C, ch, cur.tyi * t.th * S - P,
+                                cur.txi * t.tw * S - P);
+  uint32_t mg = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rcg, t.nit2, cur.bb * t.nb, B, Ho, Wo, C, ch, cur.tyi * t.th,
+                                cur.txi * t.tw);
   int cur_bb = -1;
+  const float* gb = gt + ((m.nbi * t.th + m.ty * OY) * t.tw + m.tx * OX) * PS + m.q * V;
+  const float* xb = xt + ((m.nbi * t.ih + m.ty * OY * S) * t.iw + m.tx * OX * S) * PS + m.q * V;
+  const int xrow = t.iw * PS, grow = t.tw * PS;
   for (int item = it0; item < it1; ++item) {
-    const int tx0 = (item % t.tiles_x) * t.tw;
-    const int ty0 = ((item / t.tiles_x) % t.tiles_y) * t.th;
-    const int bb = item / (t.tiles_x * t.tiles_y);
-    const int b0 = bb * t.nb;
-    __syncthreads();                                          // previous item's tiles fully consumed
-    if (bb != cur_bb) {
-      d2_load_consts(kc, xf, alpha, beta, gamma, b0, t.nb, B, c0, C);
-      cur_bb = bb;
+    if (cur.bb != cur_bb) {
       __syncthreads();
+      d2_load_sample_consts<CG>(kc, xf, alpha, gamma, cur.bb * t.nb, t.nb, B, c0, C);
+      cur_bb = cur.bb;
     }
-    d2_stage_x<T>(xt, x, kc, xf.act, xf.se != nullptr, t.ps, t.nv8, b0, B, H, W, C, c0, ty0 * S - P, tx0 * S - P, t.ih,
-                  t.iw, t.nb);
-    d2_stage_gy<T>(gt, g, yo, kc, t.ps, t.nv8, b0, B, Ho, Wo, C, c0, ty0, tx0, t.th, t.tw, t.nb);
+    cp_async_wait_all();
     __syncthreads();
+    d2_xform_x<T, CG>(xt, raw_x, mx, rcx, t.nit, t.ih, t.iw, kc, xf.act, has_se);
+    d2_xform_gy<T, CG>(gt, raw_g, raw_y, mg, rcg, t.nit2, t.th, t.tw, kc);
+    __syncthreads();
+    nxt = cur;
+    nxt.next(t);
+    if (item + 1 < it1) {
+      mx = d2_fetch<T, CG>(rawx_s, x, nullptr, 0u, rcx, t.nit, nxt.bb * t.nb, B, H, W, C, ch, nxt.tyi * t.th * S - P,
+                           nxt.txi * t.tw * S - P);
+      mg = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rcg, t.nit2, nxt.bb * t.nb, B, Ho, Wo, C, ch, nxt.tyi * t.th,
+                           nxt.txi * t.tw);
+    }
     if (m.active) {
       VT gv[OY][OX];
-      const float* gb = gt + ((size_t)(m.nbi * t.th + m.ty * OY) * t.tw + m.tx * OX) * t.ps + m.q * V;
 #pragma unroll
       for (int oy = 0; oy < OY; ++oy)
 #pragma unroll
-        for (int ox = 0; ox < OX; ++ox) ldsv(gv[oy][ox], gb + (oy * t.tw + ox) * t.ps);
-      const float* xb = xt + ((size_t)(m.nbi * t.ih + m.ty * OY * S) * t.iw + m.tx * OX * S) * t.ps + m.q * V;
+        for (int ox = 0; ox < OX; ++ox) ldsv(gv[oy][ox], gb + oy * grow + ox * PS);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         VT row[NC];
 #pragma unroll
-        for (int j = 0; j < NC; ++j) ldsv(row[j], xb + (r * t.iw + j) * t.ps);
+        for (int j = 0; j < NC; ++j) ldsv(row[j], xb + r * xrow + j * PS);
 #pragma unroll
         for (int oy = 0; oy < OY; ++oy) {
           const int ky = r - oy * S;
@@ -627,26 +719,26 @@ d2_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ yo, const fl
         }
       }
     }
+    cur = nxt;
   }
   // reduce over the lanes that share a channel vector, then over the warps, then flush
-  __syncthreads();
-  float* part = d2_smem;                                      // [8 warps][K*K][cg]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < K * K; ++i) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float v = comp(acc[i], j);
-      for (int o = nqv; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < nqv) part[((size_t)warp * K * K + i) * t.cg + lane * V + j] = v;
+#pragma unroll
+      for (int o = NQV; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < NQV) part[(warp * K * K + i) * CG + lane * V + j] = v;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * K * t.cg; i += D2_THREADS) {
+  for (int i = threadIdx.x; i < K * K * CG; i += D2_THREADS) {
     float s = 0.f;
 #pragma unroll
-    for (int wp = 0; wp < D2_THREADS / 32; ++wp) s += part[(size_t)wp * K * K * t.cg + i];
-    const int tap = i / t.cg, c = c0 + i % t.cg;
+    for (int wp = 0; wp < D2_THREADS / 32; ++wp) s += part[wp * K * K * CG + i];
+    const int tap = i / CG, c = c0 + i % CG;
     if (c < C) atomicAdd(&dw[(size_t)c * K * K + tap], s);    // reference layout [C,1,K,K]
   }
 }
@@ -654,79 +746,12 @@ d2_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ yo, const fl
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-const int D2_SMEM_CAP_FLOATS = 18 * 1024;   // 72 KB per CTA -> 3 CTAs per SM by shared memory
+const long D2_SMEM_CAP_BYTES = 104 * 1024;    // per CTA -> 2 CTAs per SM
 
 int pick_cg(int C) {
   const int g32 = ceil_div(C, 32) * 32;
   if (C % 32 == 0 || (double)g32 / C <= 1.07) return 32;
   return 16;
-}
-
-// owned grid own_h x own_w; a thread owns oy x ox of it; staged extent of t owned pixels = (t-1)*ss + kk;
-// extra_own: also stages a plain owned-size tile (weight gradient: gy next to x_t)
-D2Tile pick_tile(int B, int C, int own_h, int own_w, int oy, int ox, int ss, int kk, int extra_own, int nqv_div, int K) {
-  D2Tile best = {};
-  double best_cost = 1e300;
-  const int cg = pick_cg(C);
-  const int nsp = D2_THREADS / (cg / nqv_div);
-  // pixel stride padded by one float4: staging stores of adjacent pixels and the compute loads of
-  // adjacent thread-tiles then fall into disjoint bank groups
-  const int ps = cg + 4;
-  for (int tyt = 1; tyt <= nsp; ++tyt) {
-    if ((tyt - 1) * oy >= own_h) break;
-    for (int txt = 1; tyt * txt <= nsp; ++txt) {
-      if ((txt - 1) * ox >= own_w) break;
-      int nb = nsp / (tyt * txt);
-      if (nb > D2_MAXNB) nb = D2_MAXNB;
-      if (nb > B) nb = B;
-      const int th = tyt * oy, tw = txt * ox;
-      const int ih = (th - 1) * ss + kk, iw = (tw - 1) * ss + kk;
-      for (; nb >= 1; --nb) {
-        const long floats = (long)nb * ((long)ih * iw + (long)extra_own * th * tw) * ps;
-        if (floats > D2_SMEM_CAP_FLOATS) continue;
-        const int tiles_y = ceil_div(own_h, th), tiles_x = ceil_div(own_w, tw), bbl = ceil_div(B, nb);
-        // staged pixels that lie inside the image cost a load + transform; the rest only a store
-        const double stage = (double)nb * ((double)ih * iw + (double)extra_own * th * tw);
-        const double comp_c = (double)nsp * oy * ox * (2.0 * K * K + 16.0) / 30.0;
-        const double cost = (double)tiles_y * tiles_x * bbl * (stage + comp_c + 96.0);
-        if (cost < best_cost) {
-          best_cost = cost;
-          best.cg = cg; best.ps = ps; best.nv8 = cg / 8;
-          best.tyt = tyt; best.txt = txt; best.nb = nb; best.th = th; best.tw = tw; best.ih = ih; best.iw = iw;
-          best.tiles_y = tiles_y; best.tiles_x = tiles_x; best.b_blocks = bbl; best.n_groups = ceil_div(C, cg);
-        }
-        break;      // smaller nb only ever costs more for this (tyt, txt)
-      }
-    }
-  }
-  return best;
-}
-
-size_t tile_bytes(const D2Tile& t, int extra_own, size_t min_floats) {
-  size_t f = (size_t)t.nb * ((size_t)t.ih * t.iw + (size_t)extra_own * t.th * t.tw) * t.ps;
-  if (f < min_floats) f = min_floats;
-  return f * sizeof(float);
-}
-
-template <typename KernelT>
-int d2_ensure_smem(KernelT kernel) {
-  TD3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  return TD3D_OK;
-}
-
-template <typename T, int K, int S>
-int d2_fwd_t(const DwArgs& a, cudaStream_t st) {
-  const int Ho = (a.H - 1) / S + 1, Wo = (a.W - 1) / S + 1;
-  const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2Geo<S>::OY, D2Geo<S>::OX, S, K, 0, 4, K);
-  TD3D_REQUIRE(t.cg > 0, "dw fwd: no tile fits (H=%d W=%d C=%d k=%d s=%d)", a.H, a.W, a.C, K, S);
-  static bool once = false;
-  if (!once) { TD3D_TRY(d2_ensure_smem(d2_fwd_kernel<T, K, S>)); once = true; }
-  const size_t smem = tile_bytes(t, 0, (size_t)(D2_THREADS / (t.cg / 4)) * 2 * t.cg);
-  dim3 grid(t.tiles_x * t.tiles_y * t.b_blocks, t.n_groups);
-  d2_fwd_kernel<T, K, S><<<grid, D2_THREADS, smem, st>>>((const T*)a.x, a.xf, a.w_taps, (T*)a.y, a.stats, a.B, a.H, a.W, Ho,
-                                                         Wo, a.C, t);
-  TD3D_LAUNCH_CHECK();
-  return TD3D_OK;
 }
 
 int d2_num_sms() {
@@ -740,51 +765,151 @@ int d2_num_sms() {
   return n;
 }
 
+// owned grid own_h x own_w; a thread owns oy x ox of it; staged extent of t owned pixels = (t-1)*ss + kk.
+// n_src: tensors fetched for the staged tile (1: x, 2: g and y); extra_own: the weight gradient also
+// stages an owned-extent gy tile (2 source tensors) next to x_t.  esz = sizeof(T).
+D2Tile pick_tile(int B, int C, int own_h, int own_w, int oy, int ox, int ss, int kk, int n_src, int extra_own, int vec,
+                 int K, int esz, int part_floats) {
+  D2Tile best = {};
+  double best_cost = 1e300;
+  const int cg = pick_cg(C);
+  const int nv8 = cg / 8, ps = cg + 4;
+  const int nsp = D2_THREADS / (cg / vec);
+  for (int tyt = 1; tyt <= nsp; ++tyt) {
+    if ((tyt - 1) * oy >= own_h) break;
+    for (int txt = 1; tyt * txt <= nsp; ++txt) {
+      if ((txt - 1) * ox >= own_w) break;
+      int nb = nsp / (tyt * txt);
+      if (nb > D2_MAXNB) nb = D2_MAXNB;
+      if (nb > B) nb = B;
+      const int th = tyt * oy, tw = txt * ox;
+      const int ih = (th - 1) * ss + kk, iw = (tw - 1) * ss + kk;
+      if (ih > 255 || iw > 255) continue;
+      for (; nb >= 1; --nb) {
+        const int nit = ceil_div((long)nb * ih * iw * nv8, D2_THREADS);
+        const int nit2 = extra_own ? ceil_div((long)nb * th * tw * nv8, D2_THREADS) : 0;
+        if (nit > D2_NIT || nit2 > D2_NIT) continue;
+        const long bytes = 4L * nb * ((long)ih * iw + (long)extra_own * th * tw) * ps + 4L * part_floats +
+                           (long)D2_THREADS * esz * 8 * ((long)nit * n_src + (long)nit2 * 2);
+        if (bytes > D2_SMEM_CAP_BYTES) continue;
+        const int tiles_y = ceil_div(own_h, th), tiles_x = ceil_div(own_w, tw), bbl = ceil_div(B, nb);
+        const double stage = (double)nb * ((double)ih * iw + (double)extra_own * th * tw);
+        const double comp_c = (double)nsp * oy * ox * (2.0 * K * K + 16.0) / 30.0;
+        const double cost = (double)tiles_y * tiles_x * bbl * (stage + comp_c + 48.0);
+        if (cost < best_cost) {
+          best_cost = cost;
+          best.cg = cg;
+          best.tyt = tyt; best.txt = txt; best.nb = nb; best.th = th; best.tw = tw; best.ih = ih; best.iw = iw;
+          best.tiles_y = tiles_y; best.tiles_x = tiles_x; best.b_blocks = bbl; best.n_groups = ceil_div(C, cg);
+          best.nit = nit; best.nit2 = nit2;
+        }
+        break;      // smaller nb only ever costs more for this (tyt, txt)
+      }
+    }
+  }
+  if (best.cg) {
+    const int n_items = best.b_blocks * best.tiles_y * best.tiles_x;
+    int per = ceil_div(d2_num_sms() * 2, best.n_groups);
+    if (per > n_items) per = n_items;
+    best.items_per_cta = ceil_div(n_items, per);
+  }
+  return best;
+}
+
+D2Smem smem_layout(const D2Tile& t, int extra_own, int esz, int part_floats) {
+  D2Smem s;
+  const int ps = t.cg + 4;
+  s.tile_floats = (uint32_t)(t.nb * t.ih * t.iw * ps);
+  s.tile2_floats = extra_own ? (uint32_t)(t.nb * t.th * t.tw * ps) : 0u;
+  s.part_floats = (uint32_t)part_floats;
+  s.raw_bytes = (uint32_t)(t.nit * D2_THREADS * esz * 8);
+  s.raw2_bytes = (uint32_t)(t.nit2 * D2_THREADS * esz * 8);
+  return s;
+}
+size_t smem_bytes(const D2Smem& s, int n_src) {
+  return 4 * ((size_t)s.tile_floats + s.tile2_floats + s.part_floats) + (size_t)s.raw_bytes * n_src + (size_t)s.raw2_bytes * 2;
+}
+
+template <typename KernelT>
+int d2_ensure_smem(KernelT kernel) {
+  TD3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  return TD3D_OK;
+}
+
+int d2_grid_x(const D2Tile& t) { return ceil_div(t.b_blocks * t.tiles_y * t.tiles_x, t.items_per_cta); }
+
+template <typename T, int K, int S, int CG>
+int d2_fwd_launch(const DwArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { TD3D_TRY(d2_ensure_smem(d2_fwd_kernel<T, K, S, CG>)); once = true; }
+  const int part = D2C<CG>::NSP * 2 * CG;
+  const D2Smem sm = smem_layout(t, 0, sizeof(T), part);
+  dim3 grid(d2_grid_x(t), t.n_groups);
+  d2_fwd_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 1), st>>>((const T*)a.x, a.xf, a.w_taps, (T*)a.y, a.stats, a.B,
+                                                                          a.H, a.W, Ho, Wo, a.C, t, sm);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+template <typename T, int K, int S>
+int d2_fwd_t(const DwArgs& a, cudaStream_t st) {
+  const int Ho = (a.H - 1) / S + 1, Wo = (a.W - 1) / S + 1;
+  const int cg = pick_cg(a.C);
+  const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2Geo<S>::OY, D2Geo<S>::OX, S, K, 1, 0, 4, K, sizeof(T),
+                             (D2_THREADS / (cg / 4)) * 2 * cg);
+  TD3D_REQUIRE(t.cg > 0, "dw fwd: no tile fits (H=%d W=%d C=%d k=%d s=%d)", a.H, a.W, a.C, K, S);
+  if (t.cg == 32) return d2_fwd_launch<T, K, S, 32>(a, t, Ho, Wo, st);
+  return d2_fwd_launch<T, K, S, 16>(a, t, Ho, Wo, st);
+}
+
+template <typename T, int K, int S, int CG>
+int d2_bwd_data_launch(const DwBwdArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_data_kernel<T, K, S, CG>)); once = true; }
+  const int part = D2C<CG>::NSP * 2 * CG;
+  const D2Smem sm = smem_layout(t, 0, sizeof(T), part);
+  dim3 grid(d2_grid_x(t), t.n_groups);
+  d2_bwd_data_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 2), st>>>(
+      (const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma, (const T*)a.x, a.xf, a.w_taps, (T*)a.gx, a.stats, a.B, a.H, a.W,
+      Ho, Wo, a.C, t, sm);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+template <typename T, int K, int S, int CG>
+int d2_bwd_weight_launch(const DwBwdArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_weight_kernel<T, K, S, CG>)); once = true; }
+  const int part = (D2_THREADS / 32) * K * K * CG;
+  const D2Smem sm = smem_layout(t, 1, sizeof(T), part);
+  dim3 grid(d2_grid_x(t), t.n_groups);
+  d2_bwd_weight_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 1), st>>>(
+      (const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma, (const T*)a.x, a.xf, a.dw, a.B, a.H, a.W, Ho, Wo, a.C, t, sm);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
 template <typename T, int K, int S>
 int d2_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
   const int Ho = (a.H - 1) / S + 1, Wo = (a.W - 1) / S + 1;
+  const int cg = pick_cg(a.C);
   if (a.gx) {
-    if (S == 1) {
-      const D2Tile t = pick_tile(a.B, a.C, a.H, a.W, 2, 4, 1, K, 0, 4, K);
-      TD3D_REQUIRE(t.cg > 0, "dw bwd-data: no tile fits");
-      static bool once = false;
-      if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_data_s1_kernel<T, K>)); once = true; }
-      const size_t smem = tile_bytes(t, 0, (size_t)(D2_THREADS / (t.cg / 4)) * 2 * t.cg);
-      dim3 grid(t.tiles_x * t.tiles_y * t.b_blocks, t.n_groups);
-      d2_bwd_data_s1_kernel<T, K><<<grid, D2_THREADS, smem, st>>>((const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma,
-                                                                  (const T*)a.x, a.xf, a.w_taps, (T*)a.gx, a.stats, a.B, a.H,
-                                                                  a.W, a.C, t);
-    } else {
-      // owned grid = coarse grid; a thread owns 2 x 2 coarse positions; staged gy = owned + 1-pixel halo
-      const D2Tile t = pick_tile(a.B, a.C, (a.H + 1) / 2, (a.W + 1) / 2, 2, 2, 1, 3, 0, 4, K);
-      TD3D_REQUIRE(t.cg > 0, "dw bwd-data: no tile fits");
-      static bool once = false;
-      if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_data_s2_kernel<T, K>)); once = true; }
-      const size_t smem = tile_bytes(t, 0, (size_t)(D2_THREADS / (t.cg / 4)) * 2 * t.cg);
-      dim3 grid(t.tiles_x * t.tiles_y * t.b_blocks, t.n_groups);
-      d2_bwd_data_s2_kernel<T, K><<<grid, D2_THREADS, smem, st>>>((const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma,
-                                                                  (const T*)a.x, a.xf, a.w_taps, (T*)a.gx, a.stats, a.B, a.H,
-                                                                  a.W, Ho, Wo, a.C, t);
-    }
-    TD3D_LAUNCH_CHECK();
+    const int part = (D2_THREADS / (cg / 4)) * 2 * cg;
+    // stride 1: owned grid = input grid, thread tile 2x4, halo (K-1)/2.  stride 2: owned grid = coarse
+    // (= output) grid, a thread owns 2x2 coarse positions, staged gy = owned + 1-pixel halo.
+    const D2Tile t = S == 1 ? pick_tile(a.B, a.C, a.H, a.W, 2, 4, 1, K, 2, 0, 4, K, sizeof(T), part)
+                            : pick_tile(a.B, a.C, (a.H + 1) / 2, (a.W + 1) / 2, 2, 2, 1, 3, 2, 0, 4, K, sizeof(T), part);
+    TD3D_REQUIRE(t.cg > 0, "dw bwd-data: no tile fits");
+    if (t.cg == 32) TD3D_TRY((d2_bwd_data_launch<T, K, S, 32>(a, t, Ho, Wo, st)));
+    else TD3D_TRY((d2_bwd_data_launch<T, K, S, 16>(a, t, Ho, Wo, st)));
   }
   if (a.dw) {
     constexpr int V = D2WGeo<K, S>::V;
-    const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2WGeo<K, S>::OY, D2WGeo<K, S>::OX, S, K, 1, V, K);
+    const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2WGeo<K, S>::OY, D2WGeo<K, S>::OX, S, K, 1, 1, V, K, sizeof(T),
+                               (D2_THREADS / 32) * K * K * cg);
     TD3D_REQUIRE(t.cg > 0, "dw bwd-weight: no tile fits");
-    static bool once = false;
-    if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_weight_kernel<T, K, S>)); once = true; }
-    const size_t smem = tile_bytes(t, 1, (size_t)(D2_THREADS / 32) * K * K * t.cg);
-    const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
-    int per = ceil_div(d2_num_sms() * 2, t.n_groups);
-    if (per > n_items) per = n_items;
-    const int items_per_cta = ceil_div(n_items, per);
-    per = ceil_div(n_items, items_per_cta);
-    dim3 grid(per, t.n_groups);
-    d2_bwd_weight_kernel<T, K, S><<<grid, D2_THREADS, smem, st>>>((const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma,
-                                                                  (const T*)a.x, a.xf, a.dw, a.B, a.H, a.W, Ho, Wo, a.C, t,
-                                                                  items_per_cta);
-    TD3D_LAUNCH_CHECK();
+    if (t.cg == 32) TD3D_TRY((d2_bwd_weight_launch<T, K, S, 32>(a, t, Ho, Wo, st)));
+    else TD3D_TRY((d2_bwd_weight_launch<T, K, S, 16>(a, t, Ho, Wo, st)));
   }
   return TD3D_OK;
 }
@@ -806,8 +931,15 @@ int d2_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
     }                                                                                           \
   } while (0)
 
+static bool d2_fits_32bit(const char* what, int B, int H, int W, int C) {
+  if ((double)B * H * W * C < 2147483648.0) return true;
+  set_last_error("%s: tensor of %d x %d x %d x %d elements exceeds the 32-bit offset range", what, B, H, W, C);
+  return false;
+}
+
 int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B > 0, "dw fwd: C=%d must be a multiple of 8", a.C);
+  if (!d2_fits_32bit("dw fwd", a.B, a.H, a.W, a.C)) return TD3D_EINVAL;
   D2_DISPATCH(d2_fwd_t, a);
   set_last_error("dw fwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   return TD3D_EINVAL;
@@ -815,6 +947,7 @@ int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st) {
 
 int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B > 0, "dw bwd: C=%d must be a multiple of 8", a.C);
+  if (!d2_fits_32bit("dw bwd", a.B, a.H, a.W, a.C)) return TD3D_EINVAL;
   D2_DISPATCH(d2_bwd_t, a);
   set_last_error("dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   return TD3D_EINVAL;

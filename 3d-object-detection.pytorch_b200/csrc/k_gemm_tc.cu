@@ -137,14 +137,28 @@ __device__ __forceinline__ float warp_transpose_sum32_tc(float v[32]) {
   return v[0];
 }
 
+// Debug timeline (TD3D_TC_DBG bit 32): CTA 0 records %globaltimer at pipeline events of its first tiles.
+__device__ unsigned long long g_tc_timeline[8 * 64];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(ev, idx)                                                                         \
+  do {                                                                                            \
+    if ((p.dbg & 32) && blockIdx.x == 0 && (idx) < 64) g_tc_timeline[(ev) * 64 + (idx)] = gtimer(); \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // NT kernel
 // ------------------------------------------------------------------------------------------------
-static const int TC_THREADS = 192;          // 6 warps
+static const int TC_THREADS = 192;          // 6 warps (TN kernel)
+static const int TC_EPI_GROUPS = 3;         // NT kernel: independent 4-warp epilogue groups (one warp per TMEM lane quarter)
+static const int TC_NT_THREADS = 64 + TC_EPI_GROUPS * 128;
+static const int TC_MAX_ACC = 8;            // TMEM accumulator stages
 static const int TC_BLOCK_M = 128;
 static const int TC_MAX_STAGES = 12;
 static const int TC_TMEM_COLS = 512;
-static const int TC_ACC_STRIDE = 256;       // TMEM columns between the two accumulator stages
 
 struct TcNtParams {
   int M, N, K;
@@ -159,19 +173,24 @@ struct TcNtParams {
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
+  int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
   int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
                         // 4 no shared atomics, 8 no global reductions, 16 no TMEM load
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Measured on B200 (TD3D_TC_DBG=32 timeline): with a single 4-warp epilogue group every 32-column chunk
+// costs ~1 us of one-warp-per-scheduler latency-bound issue, the MMA/TMA side idles, and the kernel
+// runs at ~1 TB/s.  Hence TC_EPI_GROUPS groups work on different tiles concurrently, each draining its
+// own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
+__global__ void __launch_bounds__(TC_NT_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcNtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[2], s_tempty[2];
+  __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[TC_MAX_ACC], s_tempty[TC_MAX_ACC];
   __shared__ __align__(8) uint64_t s_wfull;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_stat[4][2][256];     // per epilogue warp: no atomics while a tile is reduced
+  __shared__ float s_stat[TC_EPI_GROUPS][4][2][256];     // per epilogue warp: no atomics while a tile is reduced
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms must be 1024B aligned)
@@ -182,11 +201,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&s_tfull[s]), 1); mbar_init(smem_u32(&s_tempty[s]), 4); }
+    for (int s = 0; s < p.n_acc; ++s) { mbar_init(smem_u32(&s_tfull[s]), 1); mbar_init(smem_u32(&s_tempty[s]), 4); }
     mbar_init(smem_u32(&s_wfull), 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stat[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < TC_EPI_GROUPS * 4 * 2 * 256; i += blockDim.x) (&s_stat[0][0][0][0])[i] = 0.f;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
   tc_fence_before();
@@ -208,15 +227,18 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_load_2d(wres + (uint32_t)((nt * k_blocks + kb) * p.b_stage_bytes), &map_w, wf, kb * p.block_k, nt * p.block_n);
       }
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int m0 = (tile / p.n_tiles) * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
+          TC_STAMP(0, ti);
           const uint32_t full = smem_u32(&s_full[stage]);
           const uint32_t a_dst = ring + stage * stage_bytes, b_dst = a_dst + p.a_stage_bytes;
           mbar_expect_tx(full, (uint32_t)(p.w_resident ? TC_BLOCK_M * p.swizzle_bytes : p.tx_bytes));
           tma_load_2d(a_dst, &map_a, full, kb * p.block_k, m0);
           if (!p.w_resident) tma_load_2d(b_dst, &map_w, full, kb * p.block_k, n0);
+          TC_STAMP(1, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -228,15 +250,19 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t layout_type = p.swizzle_bytes == 128 ? 2u : (p.swizzle_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
       int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
       if (p.w_resident && blockIdx.x < num_tiles) mbar_wait(smem_u32(&s_wfull), 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int n_tile = tile % p.n_tiles;
+        const int as = ti % p.n_acc;
+        const uint32_t aphase = (uint32_t)(ti / p.n_acc) & 1u;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
+        TC_STAMP(2, ti);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_ACC_STRIDE);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_full[stage]), phase);
+          TC_STAMP(3, ti);
           tc_fence_after();
           const uint32_t a_src = ring + stage * stage_bytes;
           const uint32_t b_src = p.w_resident ? wres + (uint32_t)((n_tile * k_blocks + kb) * p.b_stage_bytes) : a_src + p.a_stage_bytes;
@@ -249,27 +275,31 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           umma_commit(smem_u32(&s_empty[stage]));                 // frees the smem slot when MMAs retire
           if (kb == k_blocks - 1) umma_commit(smem_u32(&s_tfull[as]));
+          TC_STAMP(4, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
-    int as = 0; uint32_t aphase = 0;
+    const int eg = (warp - 2) >> 2;         // epilogue group
+    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    float (*gstat)[2][256] = s_stat[eg];
+    for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; tile < num_tiles; tile += TC_EPI_GROUPS * gridDim.x, ti += TC_EPI_GROUPS) {
+      const int as = ti % p.n_acc;
+      const uint32_t aphase = (uint32_t)(ti / p.n_acc) & 1u;
       const int m_tile = tile / p.n_tiles;
       const int m0 = m_tile * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
       mbar_wait(smem_u32(&s_tfull[as]), aphase);
+      if (q == 2 && lane == 0) TC_STAMP(5, ti);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t r[32];
-        if (!(p.dbg & 16)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_ACC_STRIDE + ch * 32), r);
+        if (!(p.dbg & 16)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride + ch * 32), r);
         const int nb = n0 + ch * 32;
         float v[32], w2[32];
 #pragma unroll
@@ -316,27 +346,28 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           float t1 = warp_transpose_sum32_tc(v);
           float t2 = warp_transpose_sum32_tc(w2);
           if (!(p.dbg & 4)) {
-            s_stat[q][0][ch * 32 + lane] = t1;      // one warp per TMEM lane quarter owns row q
-            s_stat[q][1][ch * 32 + lane] = t2;
+            gstat[q][0][ch * 32 + lane] = t1;      // one warp per TMEM lane quarter owns row q
+            gstat[q][1][ch * 32 + lane] = t2;
           } else if (t1 + t2 == 123.456f) {
-            s_stat[q][0][lane] = t1;
+            gstat[q][0][lane] = t1;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (q == 2 && lane == 0) TC_STAMP(6, ti);
       if (lane == 0) mbar_arrive(smem_u32(&s_tempty[as]));
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
         const int slot = m_tile % p.slots;
         for (int j = et; j < 2 * p.block_n; j += 128) {
           const int which = j / p.block_n, nn = j % p.block_n;
-          const float tot = (s_stat[0][which][nn] + s_stat[1][which][nn]) + (s_stat[2][which][nn] + s_stat[3][which][nn]);
+          const float tot = (gstat[0][which][nn] + gstat[1][which][nn]) + (gstat[2][which][nn] + gstat[3][which][nn]);
           if (n0 + nn < p.N && !(p.dbg & 8)) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (q == 2 && lane == 0) TC_STAMP(7, ti);
     }
   }
   tc_fence_before();
@@ -502,6 +533,12 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+int tc_timeline_read(unsigned long long* out, int n) {
+  if (n > 8 * 64) n = 8 * 64;
+  TD3D_CUDA(cudaMemcpyFromSymbol(out, g_tc_timeline, sizeof(unsigned long long) * n));
+  return TD3D_OK;
+}
+
 bool tc_gemm_supported(int M, int N, int K) { return M > 0 && N >= 8 && K >= 8 && (N % 8) == 0 && (K % 8) == 0; }
 
 static int g_num_sms = 0;
@@ -540,7 +577,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
   p.w_resident = (wres_bytes <= 96 * 1024 && !env_int("TD3D_TC_NO_WRES", 0)) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
-  int budget = 200 * 1024 - (p.w_resident ? wres_bytes : 0);
+  int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0);
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
@@ -550,18 +587,22 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
   p.dbg = env_int("TD3D_TC_DBG", 0);
+  p.acc_stride = 32;
+  while (p.acc_stride < bn) p.acc_stride <<= 1;
+  p.n_acc = TC_TMEM_COLS / p.acc_stride;
+  if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
   CUtensorMap map_a, map_w;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
   size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     attr_set = true;
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_nt_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_w, p);
+  gemm_nt_tc_kernel<<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, p);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

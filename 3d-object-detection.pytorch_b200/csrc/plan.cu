@@ -1066,6 +1066,7 @@ int td3d_k_gemm_tn(const void* a, const void* b, float* c, int M, int N1, int N2
   }
   return launch_gemm_tn_simt(g, dtype, (cudaStream_t)stream);
 }
+int td3d_debug_tc_timeline(uint64_t* out, int n) { return tc_timeline_read((unsigned long long*)out, n); }
 int td3d_k_apply_xform(const void* y, const float* scale, const float* shift, const float* se, int act, const void* res,
                        void* out, float* pool_stats, int B, int HW, int C, int dtype, void* stream) {
   return launch_apply_xform(y, xf_make(scale, shift, se, act), res, out, pool_stats, B, HW, C, dtype, (cudaStream_t)stream);

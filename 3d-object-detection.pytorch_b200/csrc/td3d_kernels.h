@@ -107,6 +107,7 @@ struct GemmTN {              // C[N1,N2] (f32) = A[M,N1]^T * B[M,N2]
 int launch_gemm_tn_simt(const GemmTN& g, int dtype, cudaStream_t st);
 int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st);       // bf16 only
 bool tc_gemm_supported(int M, int N, int K);
+int tc_timeline_read(unsigned long long* out, int n);   // debug: pipeline event times of CTA 0 (TD3D_TC_DBG & 32)
 
 // ---- k_heads.cu ----
 struct HeadsArgs {

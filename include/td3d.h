@@ -202,6 +202,10 @@ int td3d_k_act_bwd_stats(const void* g, const void* y, const float* scale, const
                          const float* se, int act, void* gu, float* stats, int B, int HW, int C,
                          int dtype, void* stream);
 
+/* Debug aid: with env TD3D_TC_DBG=32 CTA 0 of the tcgen05 NT GEMM records %globaltimer (ns) at 8 pipeline
+ * events of its first 64 tiles; this copies the [8][64] table to the host. */
+int td3d_debug_tc_timeline(uint64_t* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,3 +29,24 @@ for M, N, Kd in SHAPES:
     for slots, dbg in [(256, 0), (0, 0), (256, 1), (256, 2), (256, 4), (256, 8), (256, 16), (256, 1 | 2), (256, 1 | 2 | 16)]:
         us, tbs = run(M, N, Kd, slots, dbg)
         print(f"M={M} N={N} K={Kd} slots={slots} dbg={dbg:2d}: {us:8.1f} us  {tbs:6.2f} TB/s", flush=True)
+
+# ---- pipeline timeline of CTA 0 (ns since first event) ----
+import ctypes as C
+import numpy as np
+for M, N, Kd in [(256 * 112 * 112, 64, 16), (256 * 112 * 112, 16, 16)]:
+    for slots in (0, 256):
+        os.environ["TD3D_TC_DBG"] = "32"
+        a = torch.randn(M, Kd, device=dev).bfloat16(); w = torch.randn(N, Kd, device=dev).bfloat16()
+        y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        st = torch.zeros(slots, 2, N, device=dev) if slots else None
+        L.check(L.lib().td3d_k_gemm_nt(L.ptr(a), L.ptr(w), L.ptr(y), None, None, None, L.ptr(st), slots, M, N, Kd, L.BF16, 0, L.GEMM_TCGEN05, L.stream()))
+        torch.cuda.synchronize()
+        buf = (C.c_uint64 * 512)()
+        L.check(L.lib().td3d_debug_tc_timeline(buf, 512))
+        t = np.array(buf, dtype=np.int64).reshape(8, 64)
+        t0 = t[t > 0].min()
+        names = ["prod:empty_ok", "prod:tma_issued", "mma:tempty_ok", "mma:full_ok", "mma:issued", "epi:tfull_ok", "epi:chunks_done", "epi:flush_done"]
+        print(f"--- timeline N={N} K={Kd} slots={slots} (ns, tiles 0..23 of CTA 0)")
+        for e in range(8):
+            print(f"{names[e]:16s}", " ".join(f"{int(v - t0):6d}" for v in t[e, :24]))
+os.environ["TD3D_TC_DBG"] = "0"

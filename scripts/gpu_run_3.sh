@@ -1,9 +1,9 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python scripts/gemm_bench.py 2>&1 | grep -E "dbg= 0|dbg=19|dbg= 2" > gpurun_out/gemm_bench.log
+python scripts/gemm_bench.py 2>&1 | grep -E "dbg= 0|dbg=19|timeline|epi:|mma:issued" | cut -c1-200 > gpurun_out/gemm_bench.log
 cat gpurun_out/gemm_bench.log
-timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -40 > gpurun_out/t_all.log
+timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -40 > gpurun_out/t_all.log
 grep -E "passed|failed" gpurun_out/t_all.log
 timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -n 5 gpurun_out/bench.err
