@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   const bool on = c < a.C;
   const double mu = on ? a.mean[c] : 0.0, is = on ? a.invstd[c] : 0.0;
   const double M = (double)a.B * (double)a.HW;
+  const double inv_hw = 1.0 / (double)a.HW;         // no divisions inside the slot / sample loops
   const bool se_mode = a.se != nullptr;
   double S1 = 0.0, S2 = 0.0;
   if (on) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
         p0 = a.fwd_pool[((size_t)s * 2 + 0) * a.C + c];
       }
       S1 += gate * p1 + gp;
-      S2 += gate * (p2 - mu * p1) * is + (gp / a.HW) * (p0 - a.HW * mu) * is;
+      S2 += (gate * (p2 - mu * p1) + gp * (p0 * inv_hw - mu)) * is;
     }
   }
   s_sum[0][w][lane] = S1;
@@ -111,14 +112,16 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
     a.dgamma[c] = (float)S2;
     a.dbeta[c] = (float)S1;
   }
+  // per-sample constants in fp32 from fp64 per-channel terms (B*C cheap FMAs instead of B*C divisions)
+  const float aa_f = (float)aa, g0_f = (float)(aa * (c2 * mu * is - c1)), ahw_f = (float)(aa * inv_hw);
   for (int b = w; b < a.B; b += BN_WARPS) {
-    double gate = 1.0, gp = 0.0;
+    float gate = 1.f, gp = 0.f;
     if (se_mode) {
       gate = a.se[(size_t)b * a.C + c];
       gp = a.g_pool[(size_t)b * a.C + c];
     }
-    a.alpha[(size_t)b * a.C + c] = (float)(aa * gate);
-    a.gammac[(size_t)b * a.C + c] = (float)(aa * (gp / a.HW - c1 + c2 * mu * is));
+    a.alpha[(size_t)b * a.C + c] = aa_f * gate;
+    a.gammac[(size_t)b * a.C + c] = fmaf(ahw_f, gp, g0_f);
   }
 }
 

@@ -49,6 +49,12 @@ struct D2Tile {
 };
 
 template <int CG> struct D2C {
+  // Staging thread map: a thread stages one 8-channel vector v8 of pixels pix0, pix0 + DPIX, ...
+  // CG = 32: v8 fastest (4 lanes = one pixel's 64 contiguous bytes).  CG = 16: v8 slowest, lanes are
+  // consecutive pixels, otherwise the two 8-float stores of 4 pixels x 2 vectors collide in the banks.
+  static constexpr int DPIX = D2_THREADS / (CG / 8);
+  static __device__ __forceinline__ int v8() { return CG == 16 ? (int)threadIdx.x / DPIX : (int)threadIdx.x % (CG / 8); }
+  static __device__ __forceinline__ int pix0() { return CG == 16 ? (int)threadIdx.x % DPIX : (int)threadIdx.x / (CG / 8); }
   static constexpr int PS = CG + 4;          // smem pixel stride (floats): +1 float4 spreads the banks of adjacent
                                              // pixels (staging stores) and adjacent thread-tiles (compute loads)
   static constexpr int NV8 = CG / 8;
@@ -108,6 +114,22 @@ __device__ __forceinline__ float4 ld4(const bf16* p) {
   return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
                      __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
 }
+
+// 4 channels as loaded from global memory, kept packed until the epilogue needs them
+template <typename T> struct Raw4;
+template <> struct Raw4<bf16> {
+  uint2 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ float4 get() const {
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+  }
+};
+template <> struct Raw4<float> {
+  float4 r;
+  __device__ __forceinline__ void load(const float* p) { r = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ float4 get() const { return r; }
+};
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -194,8 +216,8 @@ __device__ __forceinline__ void d2_load_w(float* s_w, const float* __restrict__ 
 // once per CTA into rc[u] = r | c << 8 | nbi << 16.
 template <int CG>
 __device__ __forceinline__ void d2_items(uint32_t (&rc)[D2_NIT], int rows, int cols, int nb) {
-  const int dpix = D2_THREADS / D2C<CG>::NV8;
-  const int pix0 = threadIdx.x / D2C<CG>::NV8;
+  const int dpix = D2C<CG>::DPIX;
+  const int pix0 = D2C<CG>::pix0();
 #pragma unroll
   for (int u = 0; u < D2_NIT; ++u) {
     const int pix = pix0 + u * dpix;
@@ -236,7 +258,7 @@ template <typename T, int CG>
 __device__ __forceinline__ void d2_xform_x(float* __restrict__ tile, const uint8_t* __restrict__ raw, uint32_t mask,
                                            const uint32_t (&rc)[D2_NIT], int nit, int rows, int cols,
                                            const D2Consts<CG>& k, int act, bool has_se) {
-  const int v8 = threadIdx.x % D2C<CG>::NV8;
+  const int v8 = D2C<CG>::v8();
   float sc[8], sh[8];                // re-read per tile: not live across the compute phase
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc[i] = k.sc[v8 * 8 + i]; sh[i] = k.sh[v8 * 8 + i]; }
@@ -272,7 +294,7 @@ template <typename T, int CG>
 __device__ __forceinline__ void d2_xform_gy(float* __restrict__ tile, const uint8_t* __restrict__ raw_g,
                                             const uint8_t* __restrict__ raw_y, uint32_t mask, const uint32_t (&rc)[D2_NIT],
                                             int nit, int rows, int cols, const D2Consts<CG>& k) {
-  const int v8 = threadIdx.x % D2C<CG>::NV8;
+  const int v8 = D2C<CG>::v8();
   float be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) be[i] = k.be[v8 * 8 + i];
@@ -399,7 +421,7 @@ d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T*
   d2_items<CG>(rc, t.ih, t.iw, t.nb);
   D2Map m;
   m.init(t, D2C<CG>::NQ);
-  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  const int v8 = D2C<CG>::v8(), ch = c0 + v8 * 8;
   __syncthreads();
   const bool has_se = xf.se != nullptr;
   D2Item cur, nxt;
@@ -471,8 +493,7 @@ struct D2Fin {       // epilogue of the data gradient: gx = acc * act'(u(x)), st
   float4 sc, sh, se, s1, s2;
   int act;
   template <typename T>
-  __device__ __forceinline__ void apply(float4 acc, const T* __restrict__ xp, T* __restrict__ gp) {
-    const float4 xv = ld4(xp);
+  __device__ __forceinline__ void apply(float4 acc, const float4& xv, T* __restrict__ gp) {
     acc.x *= act_d(se.x * fmaf(xv.x, sc.x, sh.x), act);
     acc.y *= act_d(se.y * fmaf(xv.y, sc.y, sh.y), act);
     acc.z *= act_d(se.z * fmaf(xv.z, sc.z, sh.z), act);
@@ -508,7 +529,7 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
   d2_items<CG>(rc, t.ih, t.iw, t.nb);
   D2Map m;
   m.init(t, D2C<CG>::NQ);
-  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  const int v8 = D2C<CG>::v8(), ch = c0 + v8 * 8;
   __syncthreads();
   D2Item cur, nxt;
   cur.init(t, it0);
@@ -551,10 +572,18 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
 #pragma unroll
           for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* base = tile + ((m.nbi * t.ih + m.ty * OY) * t.iw + m.tx * OX) * PS + m.q * 4;
-        d2_conv<K, 1, OY, OX, CG>(acc, base, row_stride, s_wq);
         const int yy0 = ty0 + m.ty * OY, xx0 = tx0 + m.tx * OX;
+        const size_t o0 = (((size_t)b * H + yy0) * W + xx0) * C + c;
+        Raw4<T> xr[OY][OX];                          // forward input of the owned pixels: issued now, used after the taps
         if (live) {
-          const size_t o0 = (((size_t)b * H + yy0) * W + xx0) * C + c;
+#pragma unroll
+          for (int oy = 0; oy < OY; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < OX; ++ox)
+              if (yy0 + oy < H && xx0 + ox < W) xr[oy][ox].load(x + o0 + (size_t)((oy * W + ox) * C));
+        }
+        d2_conv<K, 1, OY, OX, CG>(acc, base, row_stride, s_wq);
+        if (live) {
 #pragma unroll
           for (int oy = 0; oy < OY; ++oy) {
             if (yy0 + oy >= H) continue;
@@ -562,7 +591,7 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
             for (int ox = 0; ox < OX; ++ox) {
               if (xx0 + ox >= W) continue;
               const size_t o = o0 + (size_t)((oy * W + ox) * C);
-              fin.apply<T>(acc[oy][ox], x + o, gx + o);
+              fin.apply<T>(acc[oy][ox], xr[oy][ox].get(), gx + o);
             }
           }
         }
@@ -572,6 +601,18 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
         for (int rr = 0; rr < OYC; ++rr) {
           const int cy = m.ty * OYC + rr;            // coarse row inside the tile
           // window: coarse rows cy-1..cy+1 (tile rows cy..cy+2), coarse cols tx*2-1..tx*2+2 (tile cols tx*2..tx*2+3)
+          const int hh0 = 2 * (ty0 + cy), ww0 = 2 * (tx0 + m.tx * OXC);
+          const size_t o0 = (((size_t)b * H + hh0) * W + ww0) * C + c;
+          Raw4<T> xr[OXC][2][2];
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < OXC; ++i)
+#pragma unroll
+              for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb)
+                  if (hh0 + a < H && ww0 + 2 * i + bb < W) xr[i][a][bb].load(x + o0 + (size_t)((a * W + 2 * i + bb) * C));
+          }
           float4 win[3][OXC + 2];
           const float* base = tile + ((m.nbi * t.ih + cy) * t.iw + m.tx * OXC) * PS + m.q * 4;
 #pragma unroll
@@ -599,8 +640,6 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
             }
           }
           if (live) {
-            const int hh0 = 2 * (ty0 + cy), ww0 = 2 * (tx0 + m.tx * OXC);
-            const size_t o0 = (((size_t)b * H + hh0) * W + ww0) * C + c;
 #pragma unroll
             for (int i = 0; i < OXC; ++i)
 #pragma unroll
@@ -610,7 +649,7 @@ d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const floa
                 for (int bb = 0; bb < 2; ++bb) {
                   if (ww0 + 2 * i + bb >= W) continue;
                   const size_t o = o0 + (size_t)((a * W + 2 * i + bb) * C);
-                  fin.apply<T>(acc[i][a][bb], x + o, gx + o);
+                  fin.apply<T>(acc[i][a][bb], xr[i][a][bb].get(), gx + o);
                 }
               }
           }
@@ -662,7 +701,7 @@ d2_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ yo, const fl
   d2_items<CG>(rcg, t.th, t.tw, t.nb);
   D2Map m;
   m.init(t, NQV);
-  const int v8 = threadIdx.x % D2C<CG>::NV8, ch = c0 + v8 * 8;
+  const int v8 = D2C<CG>::v8(), ch = c0 + v8 * 8;
   __syncthreads();
   const bool has_se = xf.se != nullptr;
   VT acc[K * K];

@@ -13,6 +13,30 @@ namespace td3d {
 
 static const int EW_THREADS = 256;
 static const int EW_ITERS = 8;
+static const int EW_U = 4;             // pixels per thread whose loads are in flight together
+
+// 8 channels as loaded (kept packed until used: a batch of EW_U pixels x up to 3 tensors stays in registers)
+template <typename T> struct RawV8;
+template <> struct RawV8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+};
+template <> struct RawV8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
 
 // out = act(se*(scale*y+shift)) (+res);  pool (optional): stats[b][0][c] += sum_pixels out
 template <typename T>
@@ -39,21 +63,36 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
     if (xf.se) loadf8(xf.se + (size_t)b * C + c, se);
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
-    for (int p = p0 + pl; p < p1; p += PL) {
-      const size_t off = ((size_t)b * HW + p) * C + c;
-      float v[8];
-      load8(y + off, v);
+    for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
+      RawV8<T> rv[EW_U], rr[EW_U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = act_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), xf.act);
-      if (res) {
-        float r[8];
-        load8(res + off, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
+      for (int u = 0; u < EW_U; ++u) {
+        const int p = pb + u * PL;
+        if (p < p1) {
+          const size_t off = ((size_t)b * HW + p) * C + c;
+          rv[u].load(y + off);
+          if (res) rr[u].load(res + off);
+        }
       }
-      if (out) store8(out + off, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
+      for (int u = 0; u < EW_U; ++u) {
+        const int p = pb + u * PL;
+        if (p >= p1) continue;
+        const size_t off = ((size_t)b * HW + p) * C + c;
+        float v[8];
+        rv[u].get(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), xf.act);
+        if (res) {
+          float r[8];
+          rr[u].get(r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += r[i];
+        }
+        if (out) store8(out + off, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
+      }
     }
     if (stats) {
 #pragma unroll
@@ -129,33 +168,50 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
     }
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
-    for (int p = p0 + pl; p < p1; p += PL) {
-      const size_t off = ((size_t)b * HW + p) * C + c;
-      float gv[8], yv[8];
-      load8(y + off, yv);
-      if (g_pooled) {
+    // batches of EW_U pixels: all loads of a batch are issued before the first use (memory-level parallelism)
+    for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
+      RawV8<T> rg[EW_U], ry[EW_U], ra[EW_U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gv[i] = gp[i];
-      } else {
-        load8(g + off, gv);
-      }
-      if (addend) {
-        float ad[8];
-        load8(addend + off, ad);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gv[i] += ad[i];
+      for (int u = 0; u < EW_U; ++u) {
+        const int p = pb + u * PL;
+        if (p < p1) {
+          const size_t off = ((size_t)b * HW + p) * C + c;
+          ry[u].load(y + off);
+          if (!g_pooled) rg[u].load(g + off);
+          if (addend) ra[u].load(addend + off);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float u = se[i] * fmaf(yv[i], sc[i], sh[i]);
-        gv[i] *= act_bwd(u, xf.act);
-      }
-      store8(gu + off, gv);
+      for (int u = 0; u < EW_U; ++u) {
+        const int p = pb + u * PL;
+        if (p >= p1) continue;
+        const size_t off = ((size_t)b * HW + p) * C + c;
+        float gv[8], yv[8];
+        ry[u].get(yv);
+        if (g_pooled) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float r = to_f(from_f<T>(gv[i]));      // statistics of the stored (rounded) gradient
-        a1[i] += r;
-        a2[i] = fmaf(r, yv[i], a2[i]);
+          for (int i = 0; i < 8; ++i) gv[i] = gp[i];
+        } else {
+          rg[u].get(gv);
+        }
+        if (addend) {
+          float ad[8];
+          ra[u].get(ad);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv[i] += ad[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float uu = se[i] * fmaf(yv[i], sc[i], sh[i]);
+          gv[i] *= act_bwd(uu, xf.act);
+        }
+        store8(gu + off, gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float r = to_f(from_f<T>(gv[i]));      // statistics of the stored (rounded) gradient
+          a1[i] += r;
+          a2[i] = fmaf(r, yv[i], a2[i]);
+        }
       }
     }
     if (stats) {

@@ -102,6 +102,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- TMA store path of the epilogue (bulk async group per epilogue warp) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float x[8]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+  return raw;
+}
+
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle mode
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -176,6 +197,7 @@ struct TcNtParams {
   int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
+  int tma_store;        // 1: bf16 output leaves through swizzled smem + cp.async.bulk.tensor (coalesced), else st.global
   int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
                         // 4 no shared atomics, 8 no global reductions, 16 no TMEM load
 };
@@ -185,7 +207,8 @@ struct TcNtParams {
 // runs at ~1 TB/s.  Hence TC_EPI_GROUPS groups work on different tiles concurrently, each draining its
 // own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
-gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcNtParams p) {
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_y, TcNtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[TC_MAX_ACC], s_tempty[TC_MAX_ACC];
   __shared__ __align__(8) uint64_t s_wfull;
@@ -198,6 +221,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t wres = (smem_u32(smem_raw) + 1023u) & ~1023u;      // resident W: [n_tiles][k_blocks][b_stage]
   const uint32_t ring = wres + (p.w_resident ? (uint32_t)p.n_tiles * k_blocks_u * (uint32_t)p.b_stage_bytes : 0u);
   const uint32_t stage_bytes = (uint32_t)(p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes));
+  // epilogue staging: per epilogue warp two [32 rows x 64 B] SWIZZLE_64B boxes (1 KB aligned)
+  const uint32_t ystage = (ring + (uint32_t)p.stages * stage_bytes + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), 1); }
@@ -206,7 +231,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < TC_EPI_GROUPS * 4 * 2 * 256; i += blockDim.x) (&s_stat[0][0][0][0])[i] = 0.f;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (p.tma_store) tma_prefetch_desc(&map_y); }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -287,6 +312,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int et = (threadIdx.x - 64) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
+    const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
+    uint32_t ysel = 0;
     for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; tile < num_tiles; tile += TC_EPI_GROUPS * gridDim.x, ti += TC_EPI_GROUPS) {
       const int as = ti % p.n_acc;
       const uint32_t aphase = (uint32_t)(ti / p.n_acc) & 1u;
@@ -299,6 +326,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool row_ok = m < p.M;
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t r[32];
+        // a full 32-column box may be stored by TMA (it clips at M and N); a chunk that would spill into the
+        // next N tile keeps the masked st.global path
+        const bool via_tma = p.tma_store && (p.n_tiles == 1 || ch * 32 + 32 <= p.block_n);
+        const uint32_t ybuf = ybuf0 + ysel * 2048u;
+        if (via_tma) {
+          if (lane == 0) bulk_wait_read_1();          // the store issued from this buffer two chunks ago has read it
+          __syncwarp();
+        }
         if (!(p.dbg & 16)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride + ch * 32), r);
         const int nb = n0 + ch * 32;
         float v[32], w2[32];
@@ -326,9 +361,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (p.yf) {
               if (!(p.dbg & 1)) store8(p.yf + off, x);
             } else {
-              if (!(p.dbg & 1)) store8(p.y + off, x);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+              const uint4 pk = pack8_bf16(x);
+              if (via_tma) sts_v4(ybuf + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4), pk);
+              else if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.y + off) = pk;
+              x[0] = __uint_as_float(pk.x << 16); x[1] = __uint_as_float(pk.x & 0xffff0000u);
+              x[2] = __uint_as_float(pk.y << 16); x[3] = __uint_as_float(pk.y & 0xffff0000u);
+              x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
+              x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
             }
             float ys[8];
             if (p.ysaved) load8(p.ysaved + off, ys);
@@ -341,6 +380,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[g * 8 + i] = 0.f; w2[g * 8 + i] = 0.f; }
           }
+        }
+        if (via_tma) {
+          fence_async_smem();                         // generic-proxy writes -> visible to the async (TMA) proxy
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            tma_store_2d(&map_y, ybuf, nb, m0 + q * 32);
+            bulk_commit();
+          }
+          ysel ^= 1u;
         }
         if (p.stats && !(p.dbg & 2)) {
           float t1 = warp_transpose_sum32_tc(v);
@@ -369,6 +417,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       if (q == 2 && lane == 0) TC_STAMP(7, ti);
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -577,7 +626,9 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
   p.w_resident = (wres_bytes <= 96 * 1024 && !env_int("TD3D_TC_NO_WRES", 0)) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
-  int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0);
+  p.tma_store = (!g.out_f32 && env_int("TD3D_TC_TMA_STORE", 0)) ? 1 : 0;   // measured slower than st.global (fence + 2-deep staging): off
+  const int ystage_bytes = p.tma_store ? TC_EPI_GROUPS * 4 * 2 * 2048 + 1024 : 0;
+  int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0) - ystage_bytes;
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
@@ -591,10 +642,12 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
   if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_y;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
-  size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + 1024;
+  if (p.tma_store) TD3D_TRY(make_map_2d(&map_y, g.y, g.M, g.N, 32, 32, 64));
+  else map_y = map_a;
+  size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + ystage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
@@ -602,7 +655,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_nt_tc_kernel<<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, p);
+  gemm_nt_tc_kernel<<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
