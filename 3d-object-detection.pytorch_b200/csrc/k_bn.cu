@@ -18,9 +18,23 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_finalize_fwd_kernel(BnFwdArg
   const int c = blockIdx.x * 32 + lane;
   double s1 = 0.0, s2 = 0.0;
   if (c < a.C) {
-    for (int s = w; s < a.slots; s += BN_WARPS) {
-      s1 += (double)a.stats[((size_t)s * 2 + 0) * a.C + c];
-      s2 += (double)a.stats[((size_t)s * 2 + 1) * a.C + c];
+    // independent loads first (the kernel is pure latency: a handful of CTAs, 2*slots/BN_WARPS loads each)
+    const float* __restrict__ st = a.stats + c;
+    const size_t C2 = 2 * (size_t)a.C;
+    int s = w;
+    for (; s + 7 * BN_WARPS < a.slots; s += 8 * BN_WARPS) {
+      float v1[8], v2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v1[u] = __ldg(st + (size_t)(s + u * BN_WARPS) * C2);
+        v2[u] = __ldg(st + (size_t)(s + u * BN_WARPS) * C2 + a.C);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s1 += (double)v1[u]; s2 += (double)v2[u]; }
+    }
+    for (; s < a.slots; s += BN_WARPS) {
+      s1 += (double)__ldg(st + (size_t)s * C2);
+      s2 += (double)__ldg(st + (size_t)s * C2 + a.C);
     }
   }
   s_sum[0][w][lane] = s1;
@@ -86,17 +100,31 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   const bool se_mode = a.se != nullptr;
   double S1 = 0.0, S2 = 0.0;
   if (on) {
-    for (int s = w; s < a.slots; s += BN_WARPS) {
-      double p1 = a.stats[((size_t)s * 2 + 0) * a.C + c];
-      double p2 = a.stats[((size_t)s * 2 + 1) * a.C + c];
-      double gate = 1.0, gp = 0.0, p0 = 0.0;
-      if (se_mode) {  // slots == B by construction
-        gate = a.se[(size_t)s * a.C + c];
-        gp = a.g_pool[(size_t)s * a.C + c];
-        p0 = a.fwd_pool[((size_t)s * 2 + 0) * a.C + c];
+    const float* __restrict__ st = a.stats + c;
+    const float* __restrict__ sep = a.se ? a.se + c : nullptr;
+    const float* __restrict__ gpp = a.g_pool ? a.g_pool + c : nullptr;
+    const float* __restrict__ fpp = a.fwd_pool ? a.fwd_pool + c : nullptr;
+    const size_t C1 = (size_t)a.C, C2 = 2 * C1;
+    for (int s0 = w; s0 < a.slots; s0 += 4 * BN_WARPS) {
+      float p1[4], p2[4], gate[4], gp[4], p0[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                   // all loads of 4 slots in flight together
+        const int s = s0 + u * BN_WARPS;
+        const bool live = s < a.slots;
+        p1[u] = live ? __ldg(st + (size_t)s * C2) : 0.f;
+        p2[u] = live ? __ldg(st + (size_t)s * C2 + C1) : 0.f;
+        gate[u] = 1.f; gp[u] = 0.f; p0[u] = 0.f;
+        if (se_mode && live) {  // slots == B by construction
+          gate[u] = __ldg(sep + (size_t)s * C1);
+          gp[u] = __ldg(gpp + (size_t)s * C1);
+          p0[u] = __ldg(fpp + (size_t)s * C2);
+        }
       }
-      S1 += gate * p1 + gp;
-      S2 += (gate * (p2 - mu * p1) + gp * (p0 * inv_hw - mu)) * is;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        S1 += (double)gate[u] * (double)p1[u] + (double)gp[u];
+        S2 += ((double)gate[u] * ((double)p2[u] - mu * (double)p1[u]) + (double)gp[u] * ((double)p0[u] * inv_hw - mu)) * is;
+      }
     }
   }
   s_sum[0][w][lane] = S1;
@@ -114,14 +142,34 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   }
   // per-sample constants in fp32 from fp64 per-channel terms (B*C cheap FMAs instead of B*C divisions)
   const float aa_f = (float)aa, g0_f = (float)(aa * (c2 * mu * is - c1)), ahw_f = (float)(aa * inv_hw);
-  for (int b = w; b < a.B; b += BN_WARPS) {
-    float gate = 1.f, gp = 0.f;
-    if (se_mode) {
-      gate = a.se[(size_t)b * a.C + c];
-      gp = a.g_pool[(size_t)b * a.C + c];
+  float* __restrict__ alpha_o = a.alpha + c;
+  float* __restrict__ gammac_o = a.gammac + c;
+  if (!se_mode) {
+#pragma unroll 4
+    for (int b = w; b < a.B; b += BN_WARPS) {
+      alpha_o[(size_t)b * a.C] = aa_f;
+      gammac_o[(size_t)b * a.C] = g0_f;
     }
-    a.alpha[(size_t)b * a.C + c] = aa_f * gate;
-    a.gammac[(size_t)b * a.C + c] = fmaf(ahw_f, gp, g0_f);
+  } else {
+    const float* __restrict__ sep = a.se + c;
+    const float* __restrict__ gpp = a.g_pool + c;
+    for (int b0 = w; b0 < a.B; b0 += 4 * BN_WARPS) {
+      float gate[4], gp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + u * BN_WARPS;
+        gate[u] = b < a.B ? __ldg(sep + (size_t)b * a.C) : 0.f;
+        gp[u] = b < a.B ? __ldg(gpp + (size_t)b * a.C) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = b0 + u * BN_WARPS;
+        if (b < a.B) {
+          alpha_o[(size_t)b * a.C] = aa_f * gate[u];
+          gammac_o[(size_t)b * a.C] = fmaf(ahw_f, gp[u], g0_f);
+        }
+      }
+    }
   }
 }
 

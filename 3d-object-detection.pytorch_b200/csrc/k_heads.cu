@@ -140,54 +140,65 @@ __global__ void __launch_bounds__(128) heads_bwd_feat_kernel(HeadsBwdArgs a) {
   }
 }
 
-// weight gradients. grid = (C/128, max_classes + 1); blockIdx.y == max_classes is the cls head.
-// A head whose class is absent from the batch gets present[k] = 0 and zero gradients.
+// weight gradients. grid = (C/32, max_classes + 1); blockIdx.y == max_classes is the cls head.
+// lane = channel, the 8 warps split the samples (fixed partition -> deterministic sums), partials
+// meet in shared memory.  A head whose class is absent from the batch gets present[k] = 0 and zero
+// gradients.
+static const int HW_WARPS = 8;
 template <typename T>
-__global__ void __launch_bounds__(128) heads_bwd_wgrad_kernel(HeadsBwdArgs a, const T* __restrict__ feat) {
-  extern __shared__ int s_cat[];    // class ids of the current chunk of samples
+__global__ void __launch_bounds__(32 * HW_WARPS) heads_bwd_wgrad_kernel(HeadsBwdArgs a, const T* __restrict__ feat) {
+  __shared__ float s_red[HW_WARPS][33][32];     // [warp][output row; 32 = bias][lane]
+  __shared__ int s_tot[HW_WARPS];
   const HeadsArgs& f = a.f;
   const int k = blockIdx.y;
   const bool is_cls = k == f.max_classes;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   const int n_out = is_cls ? f.nc : f.P;
+  const uint64_t seed = effective_seed(f);
   float acc[32];
   float accb = 0.f;
 #pragma unroll
   for (int o = 0; o < 32; ++o) acc[o] = 0.f;
   int total = 0;
-  const int CH = 1024;
-  for (int base = 0; base < f.B; base += CH) {
-    const int n = min(CH, f.B - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_cat[i] = (int)f.cats[base + i];
-    __syncthreads();
-    for (int t = 0; t < n; ++t) {                      // in sample order: deterministic sums
-      if (!is_cls && s_cat[t] != k) continue;          // block-uniform branch
-      const int b = base + t;
-      ++total;
-      const float* g = is_cls ? a.d_logits + (size_t)b * f.nc : a.g_pre + (size_t)b * f.P;
-      if (c < f.C) {
-        float x = to_f(feat[(size_t)b * f.C + c]);
-        if (is_cls) x *= dropout_keep(f.keep, effective_seed(f), f.training, b, c, f.C);
-#pragma unroll
-        for (int o = 0; o < 32; ++o)
-          if (o < n_out) acc[o] = fmaf(g[o], x, acc[o]);
-      }
-      if (blockIdx.x == 0 && (int)threadIdx.x < n_out) accb += g[threadIdx.x];
+  for (int b = warp; b < f.B; b += HW_WARPS) {
+    if (!is_cls && (int)f.cats[b] != k) continue;      // warp-uniform branch
+    ++total;
+    const float* g = is_cls ? a.d_logits + (size_t)b * f.nc : a.g_pre + (size_t)b * f.P;
+    const float gl = lane < n_out ? g[lane] : 0.f;
+    float x = 0.f;
+    if (c < f.C) {
+      x = to_f(feat[(size_t)b * f.C + c]);
+      if (is_cls) x *= dropout_keep(f.keep, seed, f.training, b, c, f.C);
     }
-  }
-  float* dw = is_cls ? a.dw_cls : a.dw_reg + (size_t)k * f.reg_stride;
-  if (c < f.C) {
 #pragma unroll
     for (int o = 0; o < 32; ++o)
-      if (o < n_out) dw[(size_t)o * f.C + c] = acc[o];
+      if (o < n_out) acc[o] = fmaf(__shfl_sync(0xffffffffu, gl, o), x, acc[o]);
+    accb += gl;
   }
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < n_out) {
+#pragma unroll
+  for (int o = 0; o < 32; ++o) s_red[warp][o][lane] = acc[o];
+  s_red[warp][32][lane] = accb;
+  if (lane == 0) s_tot[warp] = total;
+  __syncthreads();
+  float* dw = is_cls ? a.dw_cls : a.dw_reg + (size_t)k * f.reg_stride;
+  for (int i = threadIdx.x; i < 33 * 32; i += 32 * HW_WARPS) {
+    const int o = i >> 5, l = i & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < HW_WARPS; ++w) s += s_red[w][o][l];
+    if (o < 32) {
+      const int cc = blockIdx.x * 32 + l;
+      if (o < n_out && cc < f.C) dw[(size_t)o * f.C + cc] = s;
+    } else if (blockIdx.x == 0 && l < n_out) {
       float* db = is_cls ? a.db_cls : dw + (size_t)f.P * f.C;
-      db[threadIdx.x] = accb;
+      db[l] = s;
     }
-    if (threadIdx.x == 0 && !is_cls) a.present[k] = total > 0 ? 1 : 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !is_cls) {
+    int t = 0;
+    for (int w = 0; w < HW_WARPS; ++w) t += s_tot[w];
+    a.present[k] = t > 0 ? 1 : 0;
   }
 }
 
@@ -218,16 +229,15 @@ int launch_select_argmax(const float* kp_all, const float* logits, float* kp_sel
 int launch_heads_bwd(const HeadsBwdArgs& a, int dtype, cudaStream_t st) {
   const HeadsArgs& f = a.f;
   TD3D_REQUIRE(f.P + f.nc <= 64 && f.P <= 32 && f.nc <= 32, "heads bwd: too many outputs");
-  dim3 grid(ceil_div(f.C, 128), f.max_classes + 1);
-  size_t smem = sizeof(int) * 1024;
+  dim3 grid(ceil_div(f.C, 32), f.max_classes + 1);
   if (dtype == TD3D_BF16) {
     heads_bwd_feat_kernel<bf16><<<f.B, 128, 0, st>>>(a);
     TD3D_LAUNCH_CHECK();
-    heads_bwd_wgrad_kernel<bf16><<<grid, 128, smem, st>>>(a, (const bf16*)f.feat);
+    heads_bwd_wgrad_kernel<bf16><<<grid, 32 * HW_WARPS, 0, st>>>(a, (const bf16*)f.feat);
   } else {
     heads_bwd_feat_kernel<float><<<f.B, 128, 0, st>>>(a);
     TD3D_LAUNCH_CHECK();
-    heads_bwd_wgrad_kernel<float><<<grid, 128, smem, st>>>(a, (const float*)f.feat);
+    heads_bwd_wgrad_kernel<float><<<grid, 32 * HW_WARPS, 0, st>>>(a, (const float*)f.feat);
   }
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;

@@ -106,84 +106,158 @@ int launch_stem_fwd(const float* img, const float* w27xC, void* y, float* stats,
 
 // dW[co][ci][ky][kx] += sum_{b,oy,ox} gy[b,oy,ox,co] * img[b,ci,2oy+ky-1,2ox+kx-1]
 //   gy = alpha[b,co]*g + beta[co]*y + gamma[b,co]   (lazy BN backward of the stem BN)
-// Persistent blocks: thread (tap t, pixel lane pl) keeps 16 accumulators across all its tiles and
-// flushes once (432 atomics per block).
-static const int SW_PL = 8;                 // pixel lanes per tap
-static const int SW_THREADS = 27 * SW_PL;   // 216
+// Persistent CTAs walk contiguous ranges of 4x32-pixel tiles.  Warp w owns the filter row
+// (ci, ky) = (w/3, w%3) with its three kx taps, lane = output column: per pixel 3 image values and
+// the 16 gy channels feed 48 register accumulators (4 LDS.128 + 3 LDS per 48 FFMA).  The next tile's
+// image patch and (g, y) vectors are prefetched into registers while the current tile is consumed.
+static const int SW_WARPS = 9;
+static const int SW_THREADS = 32 * SW_WARPS;                   // 288
+static const int SW_NIMG = (3 * ST_IH * ST_IW + SW_THREADS - 1) / SW_THREADS;   // image values per thread and tile
+static const int SW_GS = 20;                                   // s_gy pixel stride (floats): conflict-free LDS.128
+
+template <typename T> struct SwRaw;
+template <> struct SwRaw<bf16> {
+  uint4 g, y;
+  __device__ __forceinline__ void load(const bf16* gp, const bf16* yp) {
+    g = __ldg(reinterpret_cast<const uint4*>(gp));
+    y = __ldg(reinterpret_cast<const uint4*>(yp));
+  }
+  __device__ __forceinline__ void get(float gv[8], float yv[8]) const {
+    const uint32_t a[4] = {g.x, g.y, g.z, g.w}, b[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gv[2 * i] = __uint_as_float(a[i] << 16); gv[2 * i + 1] = __uint_as_float(a[i] & 0xffff0000u);
+      yv[2 * i] = __uint_as_float(b[i] << 16); yv[2 * i + 1] = __uint_as_float(b[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct SwRaw<float> {
+  float4 g0, g1, y0, y1;
+  __device__ __forceinline__ void load(const float* gp, const float* yp) {
+    g0 = __ldg(reinterpret_cast<const float4*>(gp)); g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+    y0 = __ldg(reinterpret_cast<const float4*>(yp)); y1 = __ldg(reinterpret_cast<const float4*>(yp) + 1);
+  }
+  __device__ __forceinline__ void get(float gv[8], float yv[8]) const {
+    gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+    yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w; yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
+  }
+};
 
 template <typename T>
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, 2)
 stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const T* __restrict__ y,
                   const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gamma,
-                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo) {
-  __shared__ float s_in[3][ST_IH][ST_IW + 1];
-  __shared__ __align__(16) float s_gy[ST_TH * ST_TW][ST_C];
-  __shared__ float s_dw[27 * ST_C];
+                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int tiles_per_cta) {
+  __shared__ float s_in[3 * ST_IH * ST_IW];      // [ci][row][col], odd row stride
+  __shared__ __align__(16) float s_gy[ST_TH * ST_TW][SW_GS];
+  __shared__ float s_al[ST_C], s_be[ST_C], s_ga[ST_C];
   const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
   const int n_tiles = B * tiles_x * tiles_y;
-  const int t = threadIdx.x / SW_PL, pl = threadIdx.x % SW_PL;
-  const int ci = t / 9, ky = (t / 3) % 3, kx = t % 3;
-  float acc[ST_C];
+  const int t0 = blockIdx.x * tiles_per_cta, t1 = min(n_tiles, t0 + tiles_per_cta);
+  if (t0 >= t1) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ci = warp / 3, ky = warp % 3;
+  const bool has_gy = tid < ST_TH * ST_TW * 2;
+  const int gp = tid >> 1, ghalf = tid & 1;      // (pixel, 8-channel half) of the staged gy vector
+  if (tid < ST_C) s_be[tid] = beta[tid];
+  float acc[3][ST_C];
 #pragma unroll
-  for (int c = 0; c < ST_C; ++c) acc[c] = 0.f;
-  for (int i = threadIdx.x; i < 27 * ST_C; i += blockDim.x) s_dw[i] = 0.f;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) acc[k][c] = 0.f;
+
+  float r_img[SW_NIMG];
+  SwRaw<T> r_gy;
+  bool r_live = false;
+  auto prefetch = [&](int tile) {
     const int b = tile / (tiles_x * tiles_y);
     const int oy0 = ((tile / tiles_x) % tiles_y) * ST_TH, ox0 = (tile % tiles_x) * ST_TW;
     const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * ST_IH * ST_IW; i += blockDim.x) {
-      int c3 = i / (ST_IH * ST_IW), r = (i / ST_IW) % ST_IH, c = i % ST_IW;
-      int iy = iy0 + r, ix = ix0 + c;
-      float v = 0.f;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + c3) * H + iy) * W + ix);
-      s_in[c3][r][c] = v;
-    }
-    for (int i = threadIdx.x; i < ST_TH * ST_TW * 2; i += blockDim.x) {
-      int p = i >> 1, half = i & 1;
-      int oy = oy0 + p / ST_TW, ox = ox0 + p % ST_TW;
-      float v[8];
-      if (oy < Ho && ox < Wo) {
-        size_t off = (((size_t)b * Ho + oy) * Wo + ox) * ST_C + half * 8;
-        float gv[8], yv[8], al[8], be[8], ga[8];
-        load8(g + off, gv);
-        load8(y + off, yv);
-        loadf8(alpha + (size_t)b * ST_C + half * 8, al);
-        loadf8(beta + half * 8, be);
-        loadf8(gamma + (size_t)b * ST_C + half * 8, ga);
+    const float* ib = img + (size_t)b * 3 * H * W;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(al[j], gv[j], fmaf(be[j], yv[j], ga[j]));
+    for (int u = 0; u < SW_NIMG; ++u) {
+      float v = 0.f;
+      const int i = tid + u * SW_THREADS;            // flat index into s_in[3][ST_IH][ST_IW]
+      if (i < 3 * ST_IH * ST_IW) {
+        const int row = i / ST_IW;                    // ci * ST_IH + r
+        const int iy = iy0 + row % ST_IH, ix = ix0 + i % ST_IW;
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+          v = __ldg(ib + ((size_t)(row / ST_IH) * H + iy) * W + ix);
+      }
+      r_img[u] = v;
+    }
+    r_live = false;
+    if (has_gy) {
+      const int oy = oy0 + gp / ST_TW, ox = ox0 + gp % ST_TW;
+      if (oy < Ho && ox < Wo) {
+        const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * ST_C + ghalf * 8;
+        r_gy.load(g + off, y + off);
+        r_live = true;
+      }
+    }
+  };
+
+  prefetch(t0);
+  int cur_b = -1;
+  for (int tile = t0; tile < t1; ++tile) {
+    const int b = tile / (tiles_x * tiles_y);
+    if (b != cur_b) {           // CTA-uniform; the previous readers of s_al/s_ga are two barriers behind
+      if (tid < ST_C) {
+        s_al[tid] = alpha[(size_t)b * ST_C + tid];
+        s_ga[tid] = gamma[(size_t)b * ST_C + tid];
+      }
+      cur_b = b;
+      __syncthreads();
+    }
+    // ---- staged registers -> shared memory ----
+#pragma unroll
+    for (int u = 0; u < SW_NIMG; ++u)
+      if (tid + u * SW_THREADS < 3 * ST_IH * ST_IW) s_in[tid + u * SW_THREADS] = r_img[u];
+    if (has_gy) {
+      float v[8];
+      if (r_live) {
+        float gv[8], yv[8];
+        r_gy.get(gv, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = fmaf(s_al[ghalf * 8 + j], gv[j], fmaf(s_be[ghalf * 8 + j], yv[j], s_ga[ghalf * 8 + j]));
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s_gy[p][half * 8 + j] = v[j];
+      float4* dst = reinterpret_cast<float4*>(&s_gy[gp][ghalf * 8]);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
-    if (t < 27) {
-      for (int p = pl; p < ST_TH * ST_TW; p += SW_PL) {
-        int ty = p / ST_TW, tx = p % ST_TW;
-        float x = s_in[ci][2 * ty + ky][2 * tx + kx];
-        const float4* gy4 = reinterpret_cast<const float4*>(s_gy[p]);
+    if (tile + 1 < t1) prefetch(tile + 1);
+    // ---- accumulate ----
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 gq = gy4[q];
-          acc[4 * q + 0] = fmaf(x, gq.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(x, gq.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(x, gq.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(x, gq.w, acc[4 * q + 3]);
-        }
+    for (int it = 0; it < ST_TH; ++it) {
+      const float* xr = &s_in[(ci * ST_IH + 2 * it + ky) * ST_IW + 2 * lane];
+      const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
+      const float4* gq = reinterpret_cast<const float4*>(&s_gy[it * ST_TW + lane][0]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 gv = gq[q];
+        acc[0][4 * q + 0] = fmaf(x0, gv.x, acc[0][4 * q + 0]); acc[0][4 * q + 1] = fmaf(x0, gv.y, acc[0][4 * q + 1]);
+        acc[0][4 * q + 2] = fmaf(x0, gv.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(x0, gv.w, acc[0][4 * q + 3]);
+        acc[1][4 * q + 0] = fmaf(x1, gv.x, acc[1][4 * q + 0]); acc[1][4 * q + 1] = fmaf(x1, gv.y, acc[1][4 * q + 1]);
+        acc[1][4 * q + 2] = fmaf(x1, gv.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(x1, gv.w, acc[1][4 * q + 3]);
+        acc[2][4 * q + 0] = fmaf(x2, gv.x, acc[2][4 * q + 0]); acc[2][4 * q + 1] = fmaf(x2, gv.y, acc[2][4 * q + 1]);
+        acc[2][4 * q + 2] = fmaf(x2, gv.z, acc[2][4 * q + 2]); acc[2][4 * q + 3] = fmaf(x2, gv.w, acc[2][4 * q + 3]);
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  if (t < 27) {
+  // ---- warp reduction, one atomic per (tap, channel) and warp; reference layout [co][ci][ky][kx] ----
 #pragma unroll
-    for (int c = 0; c < ST_C; ++c) atomicAdd(&s_dw[c * 27 + t], acc[c]);   // reference layout [co][ci][ky][kx]
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * ST_C; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) {
+      const float r = warp_sum(acc[k][c]);
+      if (lane == 0) atomicAdd(&dw[c * 27 + ci * 9 + ky * 3 + k], r);
+    }
 }
 
 int launch_stem_wgrad(const float* img, const void* g, const void* y, const float* alpha, const float* beta,
@@ -191,11 +265,13 @@ int launch_stem_wgrad(const float* img, const void* g, const void* y, const floa
   TD3D_REQUIRE(C == ST_C, "stem wgrad: only %d output channels supported", ST_C);
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   int n_tiles = B * ceil_div(Wo, ST_TW) * ceil_div(Ho, ST_TH);
-  int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+  int ctas = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
+  int per = ceil_div(n_tiles, ctas);
+  int grid = ceil_div(n_tiles, per);
   if (dtype == TD3D_BF16)
-    stem_wgrad_kernel<bf16><<<grid, SW_THREADS, 0, st>>>(img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo);
+    stem_wgrad_kernel<bf16><<<grid, SW_THREADS, 0, st>>>(img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per);
   else
-    stem_wgrad_kernel<float><<<grid, SW_THREADS, 0, st>>>(img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo);
+    stem_wgrad_kernel<float><<<grid, SW_THREADS, 0, st>>>(img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -69,9 +69,10 @@ enum ProfKind { PK_STEM_FWD, PK_STEM_WGRAD, PK_GEMM_FWD, PK_GEMM_DGRAD, PK_GEMM_
 static const char* const kProfNames[PK_COUNT] = {
     "stem_fwd", "stem_wgrad", "gemm_fwd", "gemm_dgrad", "gemm_wgrad", "dw_fwd", "dw_bwd", "bn_finalize",
     "apply_xform", "affine2", "act_bwd_stats", "se_fc", "heads", "pool", "optimizer", "pack_weights"};
-struct ProfRec { int kind; double bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int kind; int tag; double bytes; cudaEvent_t e0, e1; };
 struct Prof {
   bool enabled = false;
+  int tag = 0;                           // layer tag of the launches being issued (see td3d_plan_profile_launch)
   std::vector<ProfRec> recs;
 };
 
@@ -328,7 +329,7 @@ struct Ctx {
   float* G(int64_t off) const { return pl->G + off; }
   void pb(int kind, double bytes) const {
     if (!pl->prof.enabled) return;
-    ProfRec r; r.kind = kind; r.bytes = bytes;
+    ProfRec r; r.kind = kind; r.bytes = bytes; r.tag = pl->prof.tag;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
     pl->prof.recs.push_back(r);
@@ -439,6 +440,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   const int B = pl->B, dt = pl->dtype;
   TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->fstats_begin, 0, pl->fstats_end - pl->fstats_begin, c.st));
   const float *sc, *sh;
+  pl->prof.tag = 0;
   // stem
   Bn& b0 = pl->bns[pl->bn_stem];
   TD3D_K(PK_STEM_FWD, (double)B * 3 * pl->H * pl->W * 4 + (double)B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_fwd(img, c.pkf(pl->p_stem), c.ws(pl->y0), c.wsf(b0.fstats), B, pl->H, pl->W, n.stem_ch, dt, c.st));
@@ -447,6 +449,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
                               B, pl->H1 * pl->W1, n.stem_ch, dt, c.st));
   const void* cur = c.ws(pl->x0);
   for (auto& b : pl->blocks) {
+    pl->prof.tag = (int)(&b - pl->blocks.data()) + 1;
     const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
@@ -496,6 +499,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     cur = c.ws(b.out);
   }
   // final 1x1 conv + BN + h_swish + global average pool (mobilenetv3.py:188,199-203; model_builder.py:98)
+  pl->prof.tag = (int)pl->blocks.size() + 1;
   const int HWl = pl->Hl * pl->Wl, Ml = B * HWl;
   const int Cl = pl->blocks.back().d.out_ch;
   {
@@ -592,6 +596,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
   const int Cl = pl->blocks.back().d.out_ch;
 
   if (in_range(0)) {
+    pl->prof.tag = 1000 + nblk + 1;
     TD3D_CUDA(cudaMemsetAsync(pl->G, 0, sizeof(float) * (size_t)pl->param_floats, c.st));
     TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->bstats_begin, 0, pl->bstats_end - pl->bstats_begin, c.st));
     TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->zeros_c, 0, sizeof(float) * 16, c.st));
@@ -645,6 +650,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
   for (int i = nblk - 1; i >= 0; --i) {
     if (!in_range(nblk - i)) continue;
     Block& b = pl->blocks[i];
+    pl->prof.tag = 1000 + i + 1;
     const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
@@ -747,6 +753,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     }
   }
   if (in_range(nblk + 1)) {
+    pl->prof.tag = 1000;
     // stem: x0 = h_swish(BN(y0)); gradient w.r.t. x0 is in g_narrow[0]
     Bn& b0 = pl->bns[pl->bn_stem];
     const int HW1 = pl->H1 * pl->W1;
@@ -921,6 +928,17 @@ int td3d_plan_profile_read(td3d_plan* pl, int kind, char* name, int name_cap, do
     TD3D_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
     *ms += t; *bytes += r.bytes; *launches += 1;
   }
+  return TD3D_OK;
+}
+
+int td3d_plan_profile_launch(td3d_plan* pl, int64_t index, int* kind, int* tag, double* ms, double* bytes) {
+  TD3D_REQUIRE(pl && kind && tag && ms && bytes, "profile_launch: null argument");
+  if (index < 0 || index >= (int64_t)pl->prof.recs.size()) return 1;   // end of the record list
+  ProfRec& r = pl->prof.recs[(size_t)index];
+  TD3D_CUDA(cudaEventSynchronize(r.e1));
+  float t = 0.f;
+  TD3D_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+  *kind = r.kind; *tag = r.tag; *ms = t; *bytes = r.bytes;
   return TD3D_OK;
 }
 

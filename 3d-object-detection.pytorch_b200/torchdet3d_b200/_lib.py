@@ -61,7 +61,7 @@ class OptimDesc(C.Structure):
 SYMBOLS = [
     "td3d_abi_version", "td3d_last_error", "td3d_device_check",
     "td3d_plan_create", "td3d_plan_destroy", "td3d_plan_sizes", "td3d_plan_param_info",
-    "td3d_plan_bn_info", "td3d_plan_bind", "td3d_plan_set_dropout_counter", "td3d_plan_profile", "td3d_plan_profile_read",
+    "td3d_plan_bn_info", "td3d_plan_bind", "td3d_plan_set_dropout_counter", "td3d_plan_profile", "td3d_plan_profile_read", "td3d_plan_profile_launch",
     "td3d_pack_weights",
     "td3d_forward", "td3d_forward_export", "td3d_backward_stages", "td3d_backward",
     "td3d_backward_ready_range", "td3d_loss_fwd_bwd", "td3d_metrics_accum", "td3d_optim_step",

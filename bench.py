@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch profile (kind, layer tag, ms, GB/s) as CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -273,26 +274,52 @@ def main():
         torch.cuda.synchronize(dev)
         k = 0
         tot_ms = 0.0
+        kinds_order = []
         while True:
             name = C.create_string_buffer(64)
             ms_k, by_k, n_k = C.c_double(), C.c_double(), C.c_int64()
             rc = lib.td3d_plan_profile_read(plan.handle, k, name, 64, C.byref(ms_k), C.byref(by_k), C.byref(n_k))
             if rc != 0:
                 break
+            kinds_order.append(name.value.decode())
             if n_k.value:
                 kinds[name.value.decode()] = dict(ms_per_step=ms_k.value / nprof, launches_per_step=n_k.value / nprof,
                                                   gbytes_per_step=by_k.value / nprof / 1e9,
                                                   gbs=by_k.value / 1e6 / max(ms_k.value, 1e-9))
                 tot_ms += ms_k.value / nprof
             k += 1
+        if args.dump_launches:
+            names = list(kinds_order)
+            recs = []
+            i = 0
+            while True:
+                kd, tg, ms_i, by_i = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+                if lib.td3d_plan_profile_launch(plan.handle, i, C.byref(kd), C.byref(tg), C.byref(ms_i), C.byref(by_i)) != 0:
+                    break
+                recs.append((kd.value, tg.value, ms_i.value, by_i.value))
+                i += 1
+            per = len(recs) // nprof
+            with open(args.dump_launches, "w") as f:
+                f.write("idx,kind,tag,us,mbytes,gbs\n")
+                for j in range(per):
+                    us = sum(recs[j + p * per][2] for p in range(nprof)) / nprof * 1e3
+                    kd, tg, _, by = recs[j]
+                    f.write(f"{j},{names[kd]},{tg},{us:.2f},{by / 1e6:.3f},{by / 1e3 / max(us, 1e-9):.1f}\n")
         L.check(lib.td3d_plan_profile(plan.handle, 0))
         step.use_graph = saved
         launches = int(sum(v["launches_per_step"] for v in kinds.values()))
         top = max(kinds.items(), key=lambda kv: kv[1]["ms_per_step"])
         for v in kinds.values():
             v["share"] = v["ms_per_step"] / tot_ms
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from `ncu --set full` extracts
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(top[0], {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         roofline = {"bound": "hbm", "kernel": top[0], "achieved": top[1]["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": top[1]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": top[1]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": top[1]["share"], "launches_per_step": top[1]["launches_per_step"],
                     "how": "CUDA events around every launch of this kernel kind on the launching stream, eager pass"}
 

@@ -128,6 +128,11 @@ int  td3d_plan_set_dropout_counter(td3d_plan* plan, const int32_t* counter);
 int  td3d_plan_profile(td3d_plan* plan, int enable);
 int  td3d_plan_profile_read(td3d_plan* plan, int kind, char* name, int name_cap, double* ms,
                             double* bytes, int64_t* launches);
+/* One recorded launch, in issue order: kernel kind, layer tag (forward: 0 stem, i+1 block i,
+ * n_blocks+1 tail; backward: the same + 1000), its time and algorithmic bytes. Returns 1 past
+ * the last record. */
+int  td3d_plan_profile_launch(td3d_plan* plan, int64_t index, int* kind, int* tag, double* ms,
+                              double* bytes);
 /* params -> compute-layout copies (+ eval-mode BN folding tables); call after any param change */
 int  td3d_pack_weights(td3d_plan* plan, void* stream);
 
