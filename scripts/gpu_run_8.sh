@@ -17,5 +17,5 @@ PY
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none --launch-skip 1000 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --skip-cpu --skip-profile > gpurun_out/ncu_bench.out 2>&1
 wc -l gpurun_out/launches.csv
 # --set full capture of the top kernels (a handful of launches each)
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"d2_bwd_data|d2_bwd_weight|gemm_nt_tc|gemm_tn_tc" --launch-skip 200 -c 24 -o gpurun_out/top_full python bench.py --steps 1 --warmup 3 --no-graph --skip-cpu --skip-profile > gpurun_out/ncu_full.out 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"d2_bwd_data|d2_bwd_weight|gemm_nt_tc|gemm_tn_tc" --launch-skip 353 -c 16 -o gpurun_out/top_full python bench.py --steps 1 --warmup 3 --no-graph --skip-cpu --skip-profile > gpurun_out/ncu_full.out 2>&1
 ls -la gpurun_out/
