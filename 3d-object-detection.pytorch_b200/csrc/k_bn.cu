@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
     const float* __restrict__ gpp = a.g_pool ? a.g_pool + c : nullptr;
     const float* __restrict__ fpp = a.fwd_pool ? a.fwd_pool + c : nullptr;
     const size_t C1 = (size_t)a.C, C2 = 2 * C1;
-    for (int s0 = w; s0 < a.slots; s0 += 4 * BN_WARPS) {
-      float p1[4], p2[4], gate[4], gp[4], p0[4];
+    for (int s0 = w; s0 < a.slots; s0 += 8 * BN_WARPS) {
+      float p1[8], p2[8], gate[8], gp[8], p0[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {                   // all loads of 4 slots in flight together
+      for (int u = 0; u < 8; ++u) {                   // all loads of 8 slots in flight together
         const int s = s0 + u * BN_WARPS;
         const bool live = s < a.slots;
         p1[u] = live ? __ldg(st + (size_t)s * C2) : 0.f;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         S1 += (double)gate[u] * (double)p1[u] + (double)gp[u];
         S2 += ((double)gate[u] * ((double)p2[u] - mu * (double)p1[u]) + (double)gp[u] * ((double)p0[u] * inv_hw - mu)) * is;
       }
@@ -153,16 +153,16 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   } else {
     const float* __restrict__ sep = a.se + c;
     const float* __restrict__ gpp = a.g_pool + c;
-    for (int b0 = w; b0 < a.B; b0 += 4 * BN_WARPS) {
-      float gate[4], gp[4];
+    for (int b0 = w; b0 < a.B; b0 += 8 * BN_WARPS) {
+      float gate[8], gp[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int b = b0 + u * BN_WARPS;
         gate[u] = b < a.B ? __ldg(sep + (size_t)b * a.C) : 0.f;
         gp[u] = b < a.B ? __ldg(gpp + (size_t)b * a.C) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int b = b0 + u * BN_WARPS;
         if (b < a.B) {
           alpha_o[(size_t)b * a.C] = aa_f * gate[u];

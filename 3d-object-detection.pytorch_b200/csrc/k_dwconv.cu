@@ -469,6 +469,7 @@ static int dw_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
 int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw fwd: C=%d must be a multiple of 8", a.C);
   if (dw_impl() == 0) return launch_dw_fwd_simple(a, dtype, st);
+  if (dw_impl() == 2 && dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return launch_dw_fwd_walker(a, dtype, st);
   if (dw_impl() == 2) return launch_dw_fwd_v2(a, dtype, st);
   DW_DISPATCH(dw_fwd_t, a);
   set_last_error("dw fwd: unsupported kernel=%d stride=%d", a.k, a.stride);
@@ -478,6 +479,7 @@ int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw bwd: C=%d must be a multiple of 8", a.C);
   if (dw_impl() == 0) return launch_dw_bwd_simple(a, dtype, st);
+  if (dw_impl() == 2 && dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return launch_dw_bwd_walker(a, dtype, st);
   if (dw_impl() == 2) return launch_dw_bwd_v2(a, dtype, st);
   DW_DISPATCH(dw_bwd_t, a);
   set_last_error("dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);

@@ -1,0 +1,596 @@
+// Depthwise k x k convolution, "row walker" generation for SMALL planes (W <= 32, stride 1, NHWC).
+// Reference op: nn.Conv2d(hidden, hidden, k, 1, (k-1)//2, groups=hidden) inside InvertedResidual,
+// torchdet3d/models/mobilenetv3.py:136,152, and its autograd backward.
+//
+// ncu on the tiled kernels of k_dw2.cu showed the late layers (14x14 / 7x7 planes, 184..960
+// channels) running at 0.3-0.8 TB/s: a 14x14 plane gives a 256-thread CTA only ~24 elements per
+// thread and tile, so the three CTA barriers, the halo (2.5x staged pixels for a 5x5 on 7x7) and
+// the index arithmetic of every tile dominate (64-216 issued instructions per element at an IPC
+// of 0.25-0.4 per scheduler).  For planes this small a whole image row fits the lanes of a warp:
+//   * lane = (x, v): x = pixel column (XL = 8/16/32 lanes), v = 8-channel (16 B) vector; a warp owns
+//     one (sample, 32/XL vectors) plane at a time and WALKS ITS ROWS top to bottom;
+//   * each input element is loaded ONCE with a 16-byte load, transformed once in registers
+//     (BatchNorm fold + SE gate + activation, or the BatchNorm-backward affine of the gradient);
+//     horizontal neighbours come from warp shuffles, vertical reuse from K rolling accumulator
+//     rows held in registers -- no shared-memory tile, no CTA barrier in the main loop;
+//   * rows are prefetched 2-3 deep in registers and the prefetch stream runs on into the next plane;
+//   * statistics (BatchNorm sums / SE squeeze) stay in registers for the whole plane and leave the
+//     warp as one atomic per (sample, channel); the weight-gradient taps stay in registers for the
+//     whole kernel.
+//
+//   forward   y  = dw(act(se*(scale*x+shift)))                      + sum y,  sum y^2   per (b,c)
+//   bwd-data  gx = act'(u(x)) * dw^T(alpha*g + beta*y + gamma)      + sum gx, sum gx*x  per (b,c)
+//   bwd-wgt   dW[c,ky,kx] += sum gy * x_t(shifted)
+#include "td3d_kernels.h"
+
+#include <stdlib.h>
+
+namespace td3d {
+
+namespace {
+
+constexpr int WW_WARPS = 4;
+constexpr int WW_THREADS = 32 * WW_WARPS;
+enum { WW_FWD = 0, WW_DGRAD = 1 };
+
+struct WwArgs {
+  const void* s0;            // FWD: x (raw forward input);  DGRAD / WGRAD: g
+  const void* s1;            // DGRAD / WGRAD: y_out (saved raw conv output)
+  const void* xin;           // DGRAD / WGRAD: x (raw forward input)
+  XForm xf;                  // lazily applied transform of x
+  const float* alpha; const float* beta; const float* gamma;   // gy = alpha[b,c]*g + beta[c]*y + gamma[b,c]
+  const float* w;            // [K*K][C] fp32 taps
+  void* out;                 // FWD: y; DGRAD: gx
+  float* stats;              // [B][2][C] or null
+  float* dw;                 // WGRAD: [C][K*K] (+=)
+  int B, H, W, C;
+  int xl_log2;               // lanes per image row = 1 << xl_log2 (>= W)
+};
+
+__device__ __forceinline__ float ww_act(float u, int act) {
+  if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
+  if (act == TD3D_ACT_HSWISH) return u * __saturatef(fmaf(u, 1.f / 6.f, 0.5f));
+  return u;
+}
+__device__ __forceinline__ float ww_actd(float u, int act) {
+  if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
+  return 1.f;
+}
+
+// ---- NV channels of one pixel as loaded from global memory (NV = 8: 16 B bf16 / 32 B fp32) ----
+template <typename T, int NV> struct WwRaw;
+template <> struct WwRaw<bf16, 8> {
+  uint4 r;
+  __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void get(float2 (&v)[4]) const {
+    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
+    v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
+  }
+};
+template <> struct WwRaw<float, 8> {
+  float4 a, b;
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float2 (&v)[4]) const {
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+    v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+  }
+};
+template <> struct WwRaw<bf16, 4> {
+  uint2 r;
+  __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ void get(float2 (&v)[2]) const {
+    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+  }
+};
+template <> struct WwRaw<float, 4> {
+  float4 a;
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void get(float2 (&v)[2]) const {
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+  }
+};
+
+// store 8 channels in the activation dtype; r = the values as stored (rounded) for the statistics
+__device__ __forceinline__ void ww_store8(bf16* p, const float2 (&v)[4], float2 (&r)[4]) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
+  *reinterpret_cast<uint4*>(p) = raw;
+  r[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u));
+  r[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+  r[2] = make_float2(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u));
+  r[3] = make_float2(__uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xffff0000u));
+}
+__device__ __forceinline__ void ww_store8(float* p, const float2 (&v)[4], float2 (&r)[4]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = v[i];
+}
+
+// value of lane (lane + delta) of the SAME image row, 0 outside the row.  Without SEL the caller
+// guarantees W + P <= XL, so the lanes the rotation wraps into are padding lanes holding zeros.
+template <bool SEL>
+__device__ __forceinline__ float2 ww_shift(const float2& v, int delta, int x, int W) {
+  const int src = ((int)threadIdx.x + delta) & 31;
+  float2 t;
+  t.x = __shfl_sync(0xffffffffu, v.x, src);
+  t.y = __shfl_sync(0xffffffffu, v.y, src);
+  if (SEL) {
+    const bool ok = (unsigned)(x + delta) < (unsigned)W;
+    t.x = ok ? t.x : 0.f;
+    t.y = ok ? t.y : 0.f;
+  }
+  return t;
+}
+
+struct WwCursor {           // prefetch position in the warp's stream of (plane, row) steps
+  int b, iy;
+  __device__ __forceinline__ void advance(int steps_per_plane, int b_stride) {
+    if (++iy == steps_per_plane) { iy = 0; b += b_stride; }
+  }
+};
+
+// per-warp constants in shared memory: [which][channel of the warp's span]
+enum { WK_SC = 0, WK_SH, WK_BE, WK_AL, WK_GA, WK_SE, WK_N };
+
+// ------------------------------------------------------------------------------------------------
+// forward / backward-data
+// ------------------------------------------------------------------------------------------------
+template <typename T, int K, int MODE, bool SEL>
+__global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
+ww_conv_kernel(WwArgs a) {
+  constexpr int P = (K - 1) / 2;
+  __shared__ __align__(16) float s_w[K * K * WW_WARPS * 32];     // [tap][channel of the CTA span]
+  __shared__ __align__(16) float s_k[WW_WARPS][WK_N][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int XL = 1 << a.xl_log2, VL = 32 >> a.xl_log2;
+  const int x = lane & (XL - 1), v = lane >> a.xl_log2;
+  const int span = WW_WARPS * VL * 8;
+  const int c_cta = blockIdx.x * span;
+  const int cl = (warp * VL + v) * 8;            // channel offset inside the CTA span
+  const int c = c_cta + cl;
+  const int H = a.H, W = a.W, C = a.C;
+  for (int i = threadIdx.x; i < K * K * span; i += WW_THREADS) {
+    const int tap = i / span, cc = c_cta + i % span;
+    const int src = MODE == WW_DGRAD ? K * K - 1 - tap : tap;     // data gradient = correlation with the flipped filter
+    s_w[i] = cc < C ? a.w[(size_t)src * C + cc] : 0.f;
+  }
+  const bool c_ok = c < C;
+  const bool lane_ok = c_ok && x < W;
+  float* kw = &s_k[warp][0][0];
+  if (x == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      kw[WK_SC * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
+      kw[WK_SH * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
+      kw[WK_BE * 32 + v * 8 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
+    }
+  }
+  __syncthreads();
+  const float* wq = s_w + cl;
+  const T* s0 = reinterpret_cast<const T*>(a.s0);
+  const T* s1 = reinterpret_cast<const T*>(a.s1);
+  const T* xin = reinterpret_cast<const T*>(a.xin);
+  T* out = reinterpret_cast<T*>(a.out);
+  const int act = a.xf.act;
+  const int steps = H + P;
+  const int bstride = gridDim.y;
+  const size_t row_elems = (size_t)W * C;
+  const size_t lane_off = (size_t)x * C + c;
+
+  // ---- register prefetch rings ----
+  constexpr int D = MODE == WW_FWD ? 3 : 2;
+  WwRaw<T, 8> r0[D], r1[D], rx[D];
+  WwCursor cur = {(int)blockIdx.y, 0};
+  auto fetch = [&](WwRaw<T, 8>& q0, WwRaw<T, 8>& q1, WwRaw<T, 8>& qx) {
+    q0.zero();
+    if (MODE == WW_DGRAD) { q1.zero(); qx.zero(); }
+    if (cur.b < a.B && lane_ok) {
+      const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
+      if (cur.iy < H) {
+        q0.load(s0 + plane + (size_t)cur.iy * row_elems);
+        if (MODE == WW_DGRAD) q1.load(s1 + plane + (size_t)cur.iy * row_elems);
+      }
+      if (MODE == WW_DGRAD && cur.iy >= P) qx.load(xin + plane + (size_t)(cur.iy - P) * row_elems);   // row emitted at this step
+    }
+    cur.advance(steps, bstride);
+  };
+#pragma unroll
+  for (int d = 0; d < D; ++d) fetch(r0[d], r1[d], rx[d]);
+
+  for (int b = blockIdx.y; b < a.B; b += bstride) {
+    // ---- per-plane constants ----
+    float2 se[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) se[i] = make_float2(1.f, 1.f);
+    if (MODE == WW_FWD) {
+      if (a.xf.se && c_ok) {
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.xf.se + (size_t)b * C + c));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.xf.se + (size_t)b * C + c) + 1);
+        se[0] = make_float2(e0.x, e0.y); se[1] = make_float2(e0.z, e0.w);
+        se[2] = make_float2(e1.x, e1.y); se[3] = make_float2(e1.z, e1.w);
+      }
+    } else {
+      __syncwarp();
+      if (x == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kw[WK_AL * 32 + v * 8 + i] = (c_ok && a.alpha) ? a.alpha[(size_t)b * C + c + i] : 0.f;
+          kw[WK_GA * 32 + v * 8 + i] = (c_ok && a.gamma) ? a.gamma[(size_t)b * C + c + i] : 0.f;
+          kw[WK_SE * 32 + v * 8 + i] = (c_ok && a.xf.se) ? a.xf.se[(size_t)b * C + c + i] : 1.f;
+        }
+      }
+      __syncwarp();
+    }
+    float2 acc[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[k][i] = make_float2(0.f, 0.f);
+    float2 st1[4], st2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { st1[i] = make_float2(0.f, 0.f); st2[i] = st1[i]; }
+    const size_t plane = (size_t)b * H * row_elems + lane_off;
+
+    for (int iy0 = 0; iy0 < steps; iy0 += K) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int iy = iy0 + j;
+        if (iy < steps) {                                   // warp-uniform
+          // pop the prefetch rings, refill their tails
+          WwRaw<T, 8> c0 = r0[0], c1 = r1[0], cx = rx[0];
+#pragma unroll
+          for (int d = 0; d + 1 < D; ++d) { r0[d] = r0[d + 1]; r1[d] = r1[d + 1]; rx[d] = rx[d + 1]; }
+          fetch(r0[D - 1], r1[D - 1], rx[D - 1]);
+          if (iy < H) {
+            float2 vals[K][4];
+            if (lane_ok) {
+              c0.get(vals[P]);
+              if (MODE == WW_FWD) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
+                  const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+                  float2 u = __ffma2_rn(vals[P][i], sc, sh);
+                  u = __fmul2_rn(u, se[i]);
+                  vals[P][i] = make_float2(ww_act(u.x, act), ww_act(u.y, act));
+                }
+              } else {
+                float2 yv[4];
+                c1.get(yv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 al = *reinterpret_cast<const float2*>(kw + WK_AL * 32 + v * 8 + 2 * i);
+                  const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 32 + v * 8 + 2 * i);
+                  const float2 ga = *reinterpret_cast<const float2*>(kw + WK_GA * 32 + v * 8 + 2 * i);
+                  vals[P][i] = __ffma2_rn(al, vals[P][i], __ffma2_rn(be, yv[i], ga));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) vals[P][i] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int d = 1; d <= P; ++d)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                vals[P - d][i] = ww_shift<SEL>(vals[P][i], -d, x, W);
+                vals[P + d][i] = ww_shift<SEL>(vals[P][i], d, x, W);
+              }
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              constexpr int KK = K;
+              const int idx = (j - ky + P + KK) % KK;      // output row iy - ky + P
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span);
+                const float4 w1 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span + 4);
+                acc[idx][0] = __ffma2_rn(vals[kx][0], make_float2(w0.x, w0.y), acc[idx][0]);
+                acc[idx][1] = __ffma2_rn(vals[kx][1], make_float2(w0.z, w0.w), acc[idx][1]);
+                acc[idx][2] = __ffma2_rn(vals[kx][2], make_float2(w1.x, w1.y), acc[idx][2]);
+                acc[idx][3] = __ffma2_rn(vals[kx][3], make_float2(w1.z, w1.w), acc[idx][3]);
+              }
+            }
+          }
+          // ---- output row iy - P is complete ----
+          const int oy = iy - P;
+          const int eidx = (j - P + K) % K;
+          if (oy >= 0 && lane_ok) {
+            float2 o[4], r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = acc[eidx][i];
+            if (MODE == WW_DGRAD) {
+              float2 xv[4];
+              cx.get(xv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
+                const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+                const float2 e = *reinterpret_cast<const float2*>(kw + WK_SE * 32 + v * 8 + 2 * i);
+                const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
+                o[i].x *= ww_actd(u.x, act);
+                o[i].y *= ww_actd(u.y, act);
+              }
+              ww_store8(out + plane + (size_t)oy * row_elems, o, r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                st1[i] = __fadd2_rn(st1[i], r[i]);
+                st2[i] = __ffma2_rn(r[i], xv[i], st2[i]);
+              }
+            } else {
+              ww_store8(out + plane + (size_t)oy * row_elems, o, r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                st1[i] = __fadd2_rn(st1[i], r[i]);
+                st2[i] = __ffma2_rn(r[i], r[i], st2[i]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[eidx][i] = make_float2(0.f, 0.f);
+        }
+      }
+    }
+    // ---- per-(sample, channel) statistics: sum over the image row lanes, one atomic per channel ----
+    if (a.stats) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        for (int o = 1; o < XL; o <<= 1) {
+          st1[i].x += __shfl_xor_sync(0xffffffffu, st1[i].x, o);
+          st1[i].y += __shfl_xor_sync(0xffffffffu, st1[i].y, o);
+          st2[i].x += __shfl_xor_sync(0xffffffffu, st2[i].x, o);
+          st2[i].y += __shfl_xor_sync(0xffffffffu, st2[i].y, o);
+        }
+      }
+      if (x == 0 && c_ok) {
+        float* sp = a.stats + (size_t)b * 2 * C + c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          atomicAdd(sp + 2 * i, st1[i].x);
+          atomicAdd(sp + 2 * i + 1, st1[i].y);
+          atomicAdd(sp + C + 2 * i, st2[i].x);
+          atomicAdd(sp + C + 2 * i + 1, st2[i].y);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward weights: lane = (x, q) with q a 4-channel vector.  dW[ky][kx] += sum_o gy[o] x_t[o+k-P]:
+// per walked row the window of K transformed x rows stays unshifted and only the 4 gy values are
+// shifted horizontally (K-1 shuffles per channel), K*K FMAs per channel.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int K, bool SEL>
+__global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
+ww_wgrad_kernel(WwArgs a) {
+  constexpr int P = (K - 1) / 2;
+  __shared__ __align__(16) float s_k[WW_WARPS][WK_N][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int XL = 1 << a.xl_log2, QL = 32 >> a.xl_log2;
+  const int x = lane & (XL - 1), q = lane >> a.xl_log2;
+  const int span = WW_WARPS * QL * 4;
+  const int c = blockIdx.x * span + (warp * QL + q) * 4;
+  const int H = a.H, W = a.W, C = a.C;
+  const bool c_ok = c < C;
+  const bool lane_ok = c_ok && x < W;
+  float* kw = &s_k[warp][0][0];
+  if (x == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      kw[WK_SC * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
+      kw[WK_SH * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
+      kw[WK_BE * 16 + q * 4 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
+    }
+  }
+  __syncwarp();
+  const T* gp = reinterpret_cast<const T*>(a.s0);
+  const T* yp = reinterpret_cast<const T*>(a.s1);
+  const T* xp = reinterpret_cast<const T*>(a.xin);
+  const int act = a.xf.act;
+  const int steps = H + P;
+  const int bstride = gridDim.y;
+  const size_t row_elems = (size_t)W * C;
+  const size_t lane_off = (size_t)x * C + c;
+
+  constexpr int D = 2;
+  WwRaw<T, 4> rg[D], ry[D], rx[D];
+  WwCursor cur = {(int)blockIdx.y, 0};
+  auto fetch = [&](WwRaw<T, 4>& qg, WwRaw<T, 4>& qy, WwRaw<T, 4>& qx) {
+    qg.zero(); qy.zero(); qx.zero();
+    if (cur.b < a.B && lane_ok) {
+      const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
+      if (cur.iy < H) qx.load(xp + plane + (size_t)cur.iy * row_elems);          // x row s
+      if (cur.iy >= P) {                                                           // gy row s - P
+        qg.load(gp + plane + (size_t)(cur.iy - P) * row_elems);
+        qy.load(yp + plane + (size_t)(cur.iy - P) * row_elems);
+      }
+    }
+    cur.advance(steps, bstride);
+  };
+#pragma unroll
+  for (int d = 0; d < D; ++d) fetch(rg[d], ry[d], rx[d]);
+
+  float2 dwa[K * K][2];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) { dwa[t][0] = make_float2(0.f, 0.f); dwa[t][1] = dwa[t][0]; }
+
+  for (int b = blockIdx.y; b < a.B; b += bstride) {
+    __syncwarp();
+    if (x == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        kw[WK_AL * 16 + q * 4 + i] = (c_ok && a.alpha) ? a.alpha[(size_t)b * C + c + i] : 0.f;
+        kw[WK_GA * 16 + q * 4 + i] = (c_ok && a.gamma) ? a.gamma[(size_t)b * C + c + i] : 0.f;
+        kw[WK_SE * 16 + q * 4 + i] = (c_ok && a.xf.se) ? a.xf.se[(size_t)b * C + c + i] : 1.f;
+      }
+    }
+    __syncwarp();
+    float2 xw[K][2];                // transformed x rows s-2P .. s (row o+ky-P of the current output row o = s-P)
+#pragma unroll
+    for (int k = 0; k < K; ++k) { xw[k][0] = make_float2(0.f, 0.f); xw[k][1] = xw[k][0]; }
+    for (int s = 0; s < steps; ++s) {
+      WwRaw<T, 4> cg = rg[0], cy = ry[0], cx = rx[0];
+#pragma unroll
+      for (int d = 0; d + 1 < D; ++d) { rg[d] = rg[d + 1]; ry[d] = ry[d + 1]; rx[d] = rx[d + 1]; }
+      fetch(rg[D - 1], ry[D - 1], rx[D - 1]);
+#pragma unroll
+      for (int k = 0; k + 1 < K; ++k) { xw[k][0] = xw[k + 1][0]; xw[k][1] = xw[k + 1][1]; }
+      float2 gy[2];
+      if (lane_ok) {
+        float2 xv[2], gv[2], yv[2];
+        cx.get(xv); cg.get(gv); cy.get(yv);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 16 + q * 4 + 2 * i);
+          const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 16 + q * 4 + 2 * i);
+          const float2 e = *reinterpret_cast<const float2*>(kw + WK_SE * 16 + q * 4 + 2 * i);
+          const float2 al = *reinterpret_cast<const float2*>(kw + WK_AL * 16 + q * 4 + 2 * i);
+          const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 16 + q * 4 + 2 * i);
+          const float2 ga = *reinterpret_cast<const float2*>(kw + WK_GA * 16 + q * 4 + 2 * i);
+          const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
+          const bool xrow = s < H;                           // virtual rows below the plane are zero padding
+          xw[K - 1][i] = make_float2(xrow ? ww_act(u.x, act) : 0.f, xrow ? ww_act(u.y, act) : 0.f);
+          const float2 t = __ffma2_rn(al, gv[i], __ffma2_rn(be, yv[i], ga));
+          const bool grow = s >= P;
+          gy[i] = make_float2(grow ? t.x : 0.f, grow ? t.y : 0.f);
+        }
+      } else {
+        xw[K - 1][0] = make_float2(0.f, 0.f); xw[K - 1][1] = xw[K - 1][0];
+        gy[0] = make_float2(0.f, 0.f); gy[1] = gy[0];
+      }
+      if (s >= P) {                                          // warp-uniform: output row o = s - P exists
+        // x_t[o+ky-P][x'] * gy[o][x' - kx + P] summed over x' (this lane's column)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float2 g0 = gy[0], g1 = gy[1];
+          if (kx != P) { g0 = ww_shift<SEL>(gy[0], P - kx, x, W); g1 = ww_shift<SEL>(gy[1], P - kx, x, W); }
+#pragma unroll
+          for (int ky = 0; ky < K; ++ky) {
+            dwa[ky * K + kx][0] = __ffma2_rn(xw[ky][0], g0, dwa[ky * K + kx][0]);
+            dwa[ky * K + kx][1] = __ffma2_rn(xw[ky][1], g1, dwa[ky * K + kx][1]);
+          }
+        }
+      }
+    }
+  }
+  // ---- reduce the taps over the image-row lanes; one atomic per (channel, tap) and warp ----
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float vx = dwa[t][i].x, vy = dwa[t][i].y;
+      for (int o = 1; o < XL; o <<= 1) {
+        vx += __shfl_xor_sync(0xffffffffu, vx, o);
+        vy += __shfl_xor_sync(0xffffffffu, vy, o);
+      }
+      if (x == 0 && c_ok) {
+        atomicAdd(&a.dw[(size_t)(c + 2 * i) * K * K + t], vx);       // reference layout [C,1,K,K]
+        atomicAdd(&a.dw[(size_t)(c + 2 * i + 1) * K * K + t], vy);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int ww_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int ww_xl_log2(int W) { return W <= 8 ? 3 : (W <= 16 ? 4 : 5); }
+
+// grid: x = channel spans, y = sample lanes (each CTA walks samples blockIdx.y, + gridDim.y, ...)
+dim3 ww_grid(int B, int C, int span, int ctas_per_sm) {
+  const int gx = ceil_div(C, span);
+  int gy = ceil_div(ww_num_sms() * ctas_per_sm * 2, gx);    // ~2 resident waves worth of CTAs
+  if (gy > B) gy = B;
+  if (gy < 1) gy = 1;
+  // even out the samples per CTA
+  gy = ceil_div(B, ceil_div(B, gy));
+  return dim3(gx, gy, 1);
+}
+
+template <typename T, int K, int MODE>
+int ww_conv_launch(const WwArgs& a, cudaStream_t st) {
+  const int XL = 1 << a.xl_log2;
+  const int span = WW_WARPS * (32 >> a.xl_log2) * 8;
+  const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
+  const bool sel = a.W + (K - 1) / 2 > XL;
+  if (sel) ww_conv_kernel<T, K, MODE, true><<<grid, WW_THREADS, 0, st>>>(a);
+  else ww_conv_kernel<T, K, MODE, false><<<grid, WW_THREADS, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+template <typename T, int K>
+int ww_wgrad_launch(const WwArgs& a, cudaStream_t st) {
+  const int XL = 1 << a.xl_log2;
+  const int span = WW_WARPS * (32 >> a.xl_log2) * 4;
+  const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
+  const bool sel = a.W + (K - 1) / 2 > XL;
+  if (sel) ww_wgrad_kernel<T, K, true><<<grid, WW_THREADS, 0, st>>>(a);
+  else ww_wgrad_kernel<T, K, false><<<grid, WW_THREADS, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+}  // namespace
+
+// the walker handles stride-1 layers whose image rows fit one warp
+bool dw_walker_supported(int H, int W, int C, int k, int stride) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TD3D_DW_WALKER");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return enabled && stride == 1 && (k == 3 || k == 5) && W <= 32 && H >= 1 && C % 8 == 0;
+}
+
+int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st) {
+  WwArgs w = {};
+  w.s0 = a.x; w.xf = a.xf; w.w = a.w_taps; w.out = a.y; w.stats = a.stats;
+  w.B = a.B; w.H = a.H; w.W = a.W; w.C = a.C; w.xl_log2 = ww_xl_log2(a.W);
+  if (dtype == TD3D_BF16) return a.k == 3 ? ww_conv_launch<bf16, 3, WW_FWD>(w, st) : ww_conv_launch<bf16, 5, WW_FWD>(w, st);
+  return a.k == 3 ? ww_conv_launch<float, 3, WW_FWD>(w, st) : ww_conv_launch<float, 5, WW_FWD>(w, st);
+}
+
+int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st) {
+  WwArgs w = {};
+  w.s0 = a.g; w.s1 = a.y_out; w.xin = a.x; w.xf = a.xf;
+  w.alpha = a.alpha; w.beta = a.beta; w.gamma = a.gamma; w.w = a.w_taps;
+  w.out = a.gx; w.stats = a.stats; w.dw = a.dw;
+  w.B = a.B; w.H = a.H; w.W = a.W; w.C = a.C; w.xl_log2 = ww_xl_log2(a.W);
+  if (a.gx) {
+    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_conv_launch<bf16, 3, WW_DGRAD>(w, st) : ww_conv_launch<bf16, 5, WW_DGRAD>(w, st)));
+    else TD3D_TRY((a.k == 3 ? ww_conv_launch<float, 3, WW_DGRAD>(w, st) : ww_conv_launch<float, 5, WW_DGRAD>(w, st)));
+  }
+  if (a.dw) {
+    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_wgrad_launch<bf16, 3>(w, st) : ww_wgrad_launch<bf16, 5>(w, st)));
+    else TD3D_TRY((a.k == 3 ? ww_wgrad_launch<float, 3>(w, st) : ww_wgrad_launch<float, 5>(w, st)));
+  }
+  return TD3D_OK;
+}
+
+}  // namespace td3d

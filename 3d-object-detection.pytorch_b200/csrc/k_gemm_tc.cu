@@ -670,10 +670,28 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   p.n2_boxes = ceil_div(p.n2_block, 64);
   int n1_tiles = ceil_div(g.N1, 128);
   int tiles = n1_tiles * n2_tiles;
-  int parts = ceil_div(num_sms() * 2, tiles);
-  int max_parts = ceil_div(g.M, TN_BK * 4);
-  if (parts > max_parts) parts = max_parts;
-  if (parts < 1) parts = 1;
+  // M split: every part ends with 128 x n2_block fp32 atomics into the same tile, so more parts buy
+  // streaming parallelism at the price of atomic traffic (measured: 196 parts of 256 rows spent 60 us on a
+  // 27 MB problem).  Pick the split that minimises a simple cost model: operand streaming at
+  // ring-bytes / latency per CTA and ~5 TB/s per chip, plus ~150 G atomics/s, plus waves of 1 CTA per SM.
+  int parts = 1;
+  {
+    const int max_parts = ceil_div(g.M, TN_BK * 4);
+    const double row_bytes = 2.0 * ((g.N1 < 128 ? g.N1 : 128) + (g.N2 < p.n2_block ? g.N2 : p.n2_block));
+    double best = 1e300;
+    for (int cand = 1; cand <= max_parts && tiles * cand <= num_sms() * 2; cand = cand < 8 ? cand + 1 : cand + cand / 4) {
+      const int rows = ceil_div(ceil_div(g.M, cand), TN_BK) * TN_BK;
+      const int n_ctas = tiles * ceil_div(g.M, rows);
+      const int conc = n_ctas < num_sms() ? n_ctas : num_sms();
+      double rate = 5000.0 / conc;                  // GB/s per CTA: chip share, capped by the bytes the
+      const double cap = TN_STAGES * TN_BK * row_bytes / 1.5e3;   // TMA ring keeps in flight over ~1.5 us of latency
+      if (rate > cap) rate = cap;
+      const double stream_us = (double)ceil_div(n_ctas, num_sms()) * rows * row_bytes / (rate * 1e3);
+      const double atom_us = (double)n_ctas * 128.0 * p.n2_block / 1.5e5;
+      const double cost = stream_us + atom_us;
+      if (cost < best) { best = cost; parts = cand; }
+    }
+  }
   p.m_per_part = ceil_div(ceil_div(g.M, parts), TN_BK) * TN_BK;
   parts = ceil_div(g.M, p.m_per_part);
   p.c = g.c;
