@@ -13,7 +13,10 @@
 //     (BatchNorm fold + SE gate + activation, or the BatchNorm-backward affine of the gradient);
 //     horizontal neighbours come from warp shuffles, vertical reuse from K rolling accumulator
 //     rows held in registers -- no shared-memory tile, no CTA barrier in the main loop;
-//   * rows are prefetched 2-3 deep in registers and the prefetch stream runs on into the next plane;
+//   * rows are prefetched 4-8 deep with cp.async into a per-warp shared-memory ring (each lane reads
+//     back only what it copied itself: no barrier), and the stream runs on into the next plane; the
+//     first version prefetched into registers and measured 2850 cycles per row step because the
+//     ring's register moves waited on the loads in flight;
 //   * statistics (BatchNorm sums / SE squeeze) stay in registers for the whole plane and leave the
 //     warp as one atomic per (sample, channel); the weight-gradient taps stay in registers for the
 //     whole kernel.
@@ -59,11 +62,23 @@ __device__ __forceinline__ float ww_actd(float u, int act) {
 }
 
 // ---- NV channels of one pixel as loaded from global memory (NV = 8: 16 B bf16 / 32 B fp32) ----
+__device__ __forceinline__ uint32_t ww_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ww_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ww_cp8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ww_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ww_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T, int NV> struct WwRaw;
 template <> struct WwRaw<bf16, 8> {
   uint4 r;
   __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
-  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  static constexpr int BYTES = 16;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const bf16* p) { ww_cp16(dst, p); }
+  __device__ __forceinline__ void lds(const uint8_t* p) { r = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void get(float2 (&v)[4]) const {
     v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
     v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
@@ -74,9 +89,11 @@ template <> struct WwRaw<bf16, 8> {
 template <> struct WwRaw<float, 8> {
   float4 a, b;
   __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
-  __device__ __forceinline__ void load(const float* p) {
-    a = __ldg(reinterpret_cast<const float4*>(p));
-    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  static constexpr int BYTES = 32;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const float* p) { ww_cp16(dst, p); ww_cp16(dst + 16, p + 4); }
+  __device__ __forceinline__ void lds(const uint8_t* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 16);
   }
   __device__ __forceinline__ void get(float2 (&v)[4]) const {
     v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
@@ -86,7 +103,9 @@ template <> struct WwRaw<float, 8> {
 template <> struct WwRaw<bf16, 4> {
   uint2 r;
   __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
-  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
+  static constexpr int BYTES = 8;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const bf16* p) { ww_cp8(dst, p); }
+  __device__ __forceinline__ void lds(const uint8_t* p) { r = *reinterpret_cast<const uint2*>(p); }
   __device__ __forceinline__ void get(float2 (&v)[2]) const {
     v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
     v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
@@ -95,7 +114,9 @@ template <> struct WwRaw<bf16, 4> {
 template <> struct WwRaw<float, 4> {
   float4 a;
   __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
-  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); }
+  static constexpr int BYTES = 16;
+  static __device__ __forceinline__ void fetch(uint32_t dst, const float* p) { ww_cp16(dst, p); }
+  __device__ __forceinline__ void lds(const uint8_t* p) { a = *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ void get(float2 (&v)[2]) const {
     v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
   }
@@ -143,8 +164,27 @@ struct WwCursor {           // prefetch position in the warp's stream of (plane,
   }
 };
 
-// per-warp constants in shared memory: [which][channel of the warp's span]
-enum { WK_SC = 0, WK_SH, WK_BE, WK_AL, WK_GA, WK_SE, WK_N };
+// per-channel constants in shared memory (written once per CTA): [which][channel of the warp's span]
+enum { WK_SC = 0, WK_SH, WK_BE, WK_N };
+// per-(sample, channel) constants, double buffered per warp and prefetched one plane ahead with cp.async
+enum { WP_AL = 0, WP_GA, WP_SE, WP_N };
+
+template <typename T> struct WwDepth {          // rows in flight per warp and tensor
+  static constexpr int FWD = sizeof(T) == 2 ? 8 : 4;
+  static constexpr int BWD = sizeof(T) == 2 ? 6 : 3;
+};
+
+// prefetch the per-plane constants of sample b into kp[WP_N][NC] (NC floats per kind and warp);
+// `mine` = this lane copies the 16 bytes at channel offset `off` (floats) of the warp's span
+__device__ __forceinline__ void ww_fetch_plane_consts(float* kp, int NC, const WwArgs& a, int b, int c_span0, int off,
+                                                       bool mine, bool want_gy) {
+  if (mine && b < a.B) {
+    const size_t g = (size_t)b * a.C + c_span0 + off;
+    if (want_gy && a.alpha) ww_cp16(ww_s32(kp + WP_AL * NC + off), a.alpha + g);
+    if (want_gy && a.gamma) ww_cp16(ww_s32(kp + WP_GA * NC + off), a.gamma + g);
+    if (a.xf.se) ww_cp16(ww_s32(kp + WP_SE * NC + off), a.xf.se + g);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward / backward-data
@@ -153,8 +193,14 @@ template <typename T, int K, int MODE, bool SEL>
 __global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
 ww_conv_kernel(WwArgs a) {
   constexpr int P = (K - 1) / 2;
-  __shared__ __align__(16) float s_w[K * K * WW_WARPS * 32];     // [tap][channel of the CTA span]
+  constexpr int NT = MODE == WW_FWD ? 1 : 3;                       // streamed tensors: x | g, y, x
+  constexpr int D = MODE == WW_FWD ? WwDepth<T>::FWD : WwDepth<T>::BWD;
+  constexpr int NS = D + 1;                                        // ring slots: the one consumed last step is refilled
+  constexpr int VB = WwRaw<T, 8>::BYTES;
+  extern __shared__ __align__(16) uint8_t ww_dyn[];                // [warp][tensor][slot][lane] x VB bytes
+  __shared__ __align__(16) float s_w[K * K * WW_WARPS * 32];       // [tap][channel of the CTA span]
   __shared__ __align__(16) float s_k[WW_WARPS][WK_N][32];
+  __shared__ __align__(16) float s_p[WW_WARPS][2][WP_N][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int XL = 1 << a.xl_log2, VL = 32 >> a.xl_log2;
   const int x = lane & (XL - 1), v = lane >> a.xl_log2;
@@ -177,6 +223,12 @@ ww_conv_kernel(WwArgs a) {
       kw[WK_SC * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
       kw[WK_SH * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
       kw[WK_BE * 32 + v * 8 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {              // defaults of the per-plane constants (kept when a pointer is null)
+        s_p[warp][u][WP_AL][v * 8 + i] = 0.f;
+        s_p[warp][u][WP_GA][v * 8 + i] = 0.f;
+        s_p[warp][u][WP_SE][v * 8 + i] = 1.f;
+      }
     }
   }
   __syncthreads();
@@ -190,51 +242,46 @@ ww_conv_kernel(WwArgs a) {
   const int bstride = gridDim.y;
   const size_t row_elems = (size_t)W * C;
   const size_t lane_off = (size_t)x * C + c;
+  const int c_warp = c_cta + warp * VL * 8;      // first channel of the warp's span
+  const bool kc_mine = c_ok && x < 2;            // this lane copies 16 B (4 floats) of its vector's per-plane constants
+  const int kc_off = v * 8 + x * 4;
 
-  // ---- register prefetch rings ----
-  constexpr int D = MODE == WW_FWD ? 3 : 2;
-  WwRaw<T, 8> r0[D], r1[D], rx[D];
+  uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
+  const uint32_t ring_s = ww_s32(ring);
+  auto slot_off = [&](int t, int sl) { return (uint32_t)((t * NS + sl) * 32 * VB); };
+
+  // ---- prefetch stream ----
   WwCursor cur = {(int)blockIdx.y, 0};
-  auto fetch = [&](WwRaw<T, 8>& q0, WwRaw<T, 8>& q1, WwRaw<T, 8>& qx) {
-    q0.zero();
-    if (MODE == WW_DGRAD) { q1.zero(); qx.zero(); }
+  int fslot = 0;
+  auto fetch = [&]() {
     if (cur.b < a.B && lane_ok) {
       const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
       if (cur.iy < H) {
-        q0.load(s0 + plane + (size_t)cur.iy * row_elems);
-        if (MODE == WW_DGRAD) q1.load(s1 + plane + (size_t)cur.iy * row_elems);
+        WwRaw<T, 8>::fetch(ring_s + slot_off(0, fslot), s0 + plane + (size_t)cur.iy * row_elems);
+        if (MODE == WW_DGRAD) WwRaw<T, 8>::fetch(ring_s + slot_off(1, fslot), s1 + plane + (size_t)cur.iy * row_elems);
       }
-      if (MODE == WW_DGRAD && cur.iy >= P) qx.load(xin + plane + (size_t)(cur.iy - P) * row_elems);   // row emitted at this step
+      if (MODE == WW_DGRAD && cur.iy >= P)        // the x row of the output row emitted at that step
+        WwRaw<T, 8>::fetch(ring_s + slot_off(2, fslot), xin + plane + (size_t)(cur.iy - P) * row_elems);
     }
+    ww_commit();
     cur.advance(steps, bstride);
+    fslot = fslot + 1 == NS ? 0 : fslot + 1;
   };
-#pragma unroll
-  for (int d = 0; d < D; ++d) fetch(r0[d], r1[d], rx[d]);
+  // constants of the first plane, then the first D rows
+  ww_fetch_plane_consts(&s_p[warp][0][0][0], 32, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
+  ww_commit();
+  ww_wait<0>();
+  __syncwarp();
+#pragma unroll 1
+  for (int d = 0; d < D; ++d) fetch();
+  int cslot = 0, pbuf = 0;
 
   for (int b = blockIdx.y; b < a.B; b += bstride) {
-    // ---- per-plane constants ----
-    float2 se[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) se[i] = make_float2(1.f, 1.f);
-    if (MODE == WW_FWD) {
-      if (a.xf.se && c_ok) {
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.xf.se + (size_t)b * C + c));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.xf.se + (size_t)b * C + c) + 1);
-        se[0] = make_float2(e0.x, e0.y); se[1] = make_float2(e0.z, e0.w);
-        se[2] = make_float2(e1.x, e1.y); se[3] = make_float2(e1.z, e1.w);
-      }
-    } else {
-      __syncwarp();
-      if (x == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          kw[WK_AL * 32 + v * 8 + i] = (c_ok && a.alpha) ? a.alpha[(size_t)b * C + c + i] : 0.f;
-          kw[WK_GA * 32 + v * 8 + i] = (c_ok && a.gamma) ? a.gamma[(size_t)b * C + c + i] : 0.f;
-          kw[WK_SE * 32 + v * 8 + i] = (c_ok && a.xf.se) ? a.xf.se[(size_t)b * C + c + i] : 1.f;
-        }
-      }
-      __syncwarp();
-    }
+    // ---- per-plane constants: this plane's are in s_p[pbuf] (prefetched a plane ago), start the next plane's ----
+    if (steps <= D) ww_wait<0>();                // short planes: the constants' group may be younger than the ring depth
+    __syncwarp();
+    const float* kp = &s_p[warp][pbuf][0][0];
+    ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 32, a, b + bstride, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
     float2 acc[K][4];
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -250,11 +297,12 @@ ww_conv_kernel(WwArgs a) {
       for (int j = 0; j < K; ++j) {
         const int iy = iy0 + j;
         if (iy < steps) {                                   // warp-uniform
-          // pop the prefetch rings, refill their tails
-          WwRaw<T, 8> c0 = r0[0], c1 = r1[0], cx = rx[0];
-#pragma unroll
-          for (int d = 0; d + 1 < D; ++d) { r0[d] = r0[d + 1]; r1[d] = r1[d + 1]; rx[d] = rx[d + 1]; }
-          fetch(r0[D - 1], r1[D - 1], rx[D - 1]);
+          ww_wait<D - 1>();                                 // this step's rows have landed (own copies only)
+          WwRaw<T, 8> c0, c1, cx;
+          c0.lds(ring + slot_off(0, cslot));
+          if (MODE == WW_DGRAD) { c1.lds(ring + slot_off(1, cslot)); cx.lds(ring + slot_off(2, cslot)); }
+          cslot = cslot + 1 == NS ? 0 : cslot + 1;
+          fetch();                                          // refills the slot consumed one step ago
           if (iy < H) {
             float2 vals[K][4];
             if (lane_ok) {
@@ -264,8 +312,9 @@ ww_conv_kernel(WwArgs a) {
                 for (int i = 0; i < 4; ++i) {
                   const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
                   const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+                  const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
                   float2 u = __ffma2_rn(vals[P][i], sc, sh);
-                  u = __fmul2_rn(u, se[i]);
+                  u = __fmul2_rn(u, e);
                   vals[P][i] = make_float2(ww_act(u.x, act), ww_act(u.y, act));
                 }
               } else {
@@ -273,9 +322,9 @@ ww_conv_kernel(WwArgs a) {
                 c1.get(yv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 al = *reinterpret_cast<const float2*>(kw + WK_AL * 32 + v * 8 + 2 * i);
+                  const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 32 + v * 8 + 2 * i);
                   const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 32 + v * 8 + 2 * i);
-                  const float2 ga = *reinterpret_cast<const float2*>(kw + WK_GA * 32 + v * 8 + 2 * i);
+                  const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 32 + v * 8 + 2 * i);
                   vals[P][i] = __ffma2_rn(al, vals[P][i], __ffma2_rn(be, yv[i], ga));
                 }
               }
@@ -319,7 +368,7 @@ ww_conv_kernel(WwArgs a) {
               for (int i = 0; i < 4; ++i) {
                 const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
                 const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
-                const float2 e = *reinterpret_cast<const float2*>(kw + WK_SE * 32 + v * 8 + 2 * i);
+                const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
                 const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
                 o[i].x *= ww_actd(u.x, act);
                 o[i].y *= ww_actd(u.y, act);
@@ -344,6 +393,7 @@ ww_conv_kernel(WwArgs a) {
         }
       }
     }
+    pbuf ^= 1;
     // ---- per-(sample, channel) statistics: sum over the image row lanes, one atomic per channel ----
     if (a.stats) {
 #pragma unroll
@@ -367,6 +417,7 @@ ww_conv_kernel(WwArgs a) {
       }
     }
   }
+  ww_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,12 +429,19 @@ template <typename T, int K, bool SEL>
 __global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
 ww_wgrad_kernel(WwArgs a) {
   constexpr int P = (K - 1) / 2;
+  constexpr int NT = 3;
+  constexpr int D = WwDepth<T>::FWD;
+  constexpr int NS = D + 1;
+  constexpr int VB = WwRaw<T, 4>::BYTES;
+  extern __shared__ __align__(16) uint8_t ww_dyn[];
   __shared__ __align__(16) float s_k[WW_WARPS][WK_N][16];
+  __shared__ __align__(16) float s_p[WW_WARPS][2][WP_N][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int XL = 1 << a.xl_log2, QL = 32 >> a.xl_log2;
   const int x = lane & (XL - 1), q = lane >> a.xl_log2;
   const int span = WW_WARPS * QL * 4;
-  const int c = blockIdx.x * span + (warp * QL + q) * 4;
+  const int c_warp = blockIdx.x * span + warp * QL * 4;
+  const int c = c_warp + q * 4;
   const int H = a.H, W = a.W, C = a.C;
   const bool c_ok = c < C;
   const bool lane_ok = c_ok && x < W;
@@ -394,6 +452,12 @@ ww_wgrad_kernel(WwArgs a) {
       kw[WK_SC * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
       kw[WK_SH * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
       kw[WK_BE * 16 + q * 4 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        s_p[warp][u][WP_AL][q * 4 + i] = 0.f;
+        s_p[warp][u][WP_GA][q * 4 + i] = 0.f;
+        s_p[warp][u][WP_SE][q * 4 + i] = 1.f;
+      }
     }
   }
   __syncwarp();
@@ -405,72 +469,74 @@ ww_wgrad_kernel(WwArgs a) {
   const int bstride = gridDim.y;
   const size_t row_elems = (size_t)W * C;
   const size_t lane_off = (size_t)x * C + c;
+  const bool kc_mine = c_ok && x == 0;           // one 16-byte copy per 4-channel vector and kind
+  const int kc_off = q * 4;
 
-  constexpr int D = 2;
-  WwRaw<T, 4> rg[D], ry[D], rx[D];
+  uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
+  const uint32_t ring_s = ww_s32(ring);
+  auto slot_off = [&](int t, int sl) { return (uint32_t)((t * NS + sl) * 32 * VB); };
   WwCursor cur = {(int)blockIdx.y, 0};
-  auto fetch = [&](WwRaw<T, 4>& qg, WwRaw<T, 4>& qy, WwRaw<T, 4>& qx) {
-    qg.zero(); qy.zero(); qx.zero();
+  int fslot = 0;
+  auto fetch = [&]() {
     if (cur.b < a.B && lane_ok) {
       const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
-      if (cur.iy < H) qx.load(xp + plane + (size_t)cur.iy * row_elems);          // x row s
-      if (cur.iy >= P) {                                                           // gy row s - P
-        qg.load(gp + plane + (size_t)(cur.iy - P) * row_elems);
-        qy.load(yp + plane + (size_t)(cur.iy - P) * row_elems);
+      if (cur.iy < H) WwRaw<T, 4>::fetch(ring_s + slot_off(2, fslot), xp + plane + (size_t)cur.iy * row_elems);   // x row s
+      if (cur.iy >= P) {                                                                                         // gy row s - P
+        WwRaw<T, 4>::fetch(ring_s + slot_off(0, fslot), gp + plane + (size_t)(cur.iy - P) * row_elems);
+        WwRaw<T, 4>::fetch(ring_s + slot_off(1, fslot), yp + plane + (size_t)(cur.iy - P) * row_elems);
       }
     }
+    ww_commit();
     cur.advance(steps, bstride);
+    fslot = fslot + 1 == NS ? 0 : fslot + 1;
   };
-#pragma unroll
-  for (int d = 0; d < D; ++d) fetch(rg[d], ry[d], rx[d]);
+  ww_fetch_plane_consts(&s_p[warp][0][0][0], 16, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, true);
+  ww_commit();
+  ww_wait<0>();
+  __syncwarp();
+#pragma unroll 1
+  for (int d = 0; d < D; ++d) fetch();
+  int cslot = 0, pbuf = 0;
 
   float2 dwa[K * K][2];
 #pragma unroll
   for (int t = 0; t < K * K; ++t) { dwa[t][0] = make_float2(0.f, 0.f); dwa[t][1] = dwa[t][0]; }
 
   for (int b = blockIdx.y; b < a.B; b += bstride) {
+    if (steps <= D) ww_wait<0>();
     __syncwarp();
-    if (x == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        kw[WK_AL * 16 + q * 4 + i] = (c_ok && a.alpha) ? a.alpha[(size_t)b * C + c + i] : 0.f;
-        kw[WK_GA * 16 + q * 4 + i] = (c_ok && a.gamma) ? a.gamma[(size_t)b * C + c + i] : 0.f;
-        kw[WK_SE * 16 + q * 4 + i] = (c_ok && a.xf.se) ? a.xf.se[(size_t)b * C + c + i] : 1.f;
-      }
-    }
-    __syncwarp();
+    const float* kp = &s_p[warp][pbuf][0][0];
+    ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 16, a, b + bstride, c_warp, kc_off, kc_mine, true);
     float2 xw[K][2];                // transformed x rows s-2P .. s (row o+ky-P of the current output row o = s-P)
 #pragma unroll
     for (int k = 0; k < K; ++k) { xw[k][0] = make_float2(0.f, 0.f); xw[k][1] = xw[k][0]; }
     for (int s = 0; s < steps; ++s) {
-      WwRaw<T, 4> cg = rg[0], cy = ry[0], cx = rx[0];
-#pragma unroll
-      for (int d = 0; d + 1 < D; ++d) { rg[d] = rg[d + 1]; ry[d] = ry[d + 1]; rx[d] = rx[d + 1]; }
-      fetch(rg[D - 1], ry[D - 1], rx[D - 1]);
+      ww_wait<D - 1>();
+      WwRaw<T, 4> cg, cy, cx;
+      cg.lds(ring + slot_off(0, cslot));
+      cy.lds(ring + slot_off(1, cslot));
+      cx.lds(ring + slot_off(2, cslot));
+      cslot = cslot + 1 == NS ? 0 : cslot + 1;
+      fetch();
 #pragma unroll
       for (int k = 0; k + 1 < K; ++k) { xw[k][0] = xw[k + 1][0]; xw[k][1] = xw[k + 1][1]; }
       float2 gy[2];
-      if (lane_ok) {
-        float2 xv[2], gv[2], yv[2];
-        cx.get(xv); cg.get(gv); cy.get(yv);
+      const bool xrow = lane_ok && s < H;                  // rows below the plane are zero padding
+      const bool grow = lane_ok && s >= P;
+      float2 xv[2], gv[2], yv[2];
+      cx.get(xv); cg.get(gv); cy.get(yv);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 16 + q * 4 + 2 * i);
-          const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 16 + q * 4 + 2 * i);
-          const float2 e = *reinterpret_cast<const float2*>(kw + WK_SE * 16 + q * 4 + 2 * i);
-          const float2 al = *reinterpret_cast<const float2*>(kw + WK_AL * 16 + q * 4 + 2 * i);
-          const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 16 + q * 4 + 2 * i);
-          const float2 ga = *reinterpret_cast<const float2*>(kw + WK_GA * 16 + q * 4 + 2 * i);
-          const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
-          const bool xrow = s < H;                           // virtual rows below the plane are zero padding
-          xw[K - 1][i] = make_float2(xrow ? ww_act(u.x, act) : 0.f, xrow ? ww_act(u.y, act) : 0.f);
-          const float2 t = __ffma2_rn(al, gv[i], __ffma2_rn(be, yv[i], ga));
-          const bool grow = s >= P;
-          gy[i] = make_float2(grow ? t.x : 0.f, grow ? t.y : 0.f);
-        }
-      } else {
-        xw[K - 1][0] = make_float2(0.f, 0.f); xw[K - 1][1] = xw[K - 1][0];
-        gy[0] = make_float2(0.f, 0.f); gy[1] = gy[0];
+      for (int i = 0; i < 2; ++i) {
+        const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 16 + q * 4 + 2 * i);
+        const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 16 + q * 4 + 2 * i);
+        const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 16 + q * 4 + 2 * i);
+        const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 16 + q * 4 + 2 * i);
+        const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 16 + q * 4 + 2 * i);
+        const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 16 + q * 4 + 2 * i);
+        const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
+        xw[K - 1][i] = make_float2(xrow ? ww_act(u.x, act) : 0.f, xrow ? ww_act(u.y, act) : 0.f);
+        const float2 t = __ffma2_rn(al, gv[i], __ffma2_rn(be, yv[i], ga));
+        gy[i] = make_float2(grow ? t.x : 0.f, grow ? t.y : 0.f);
       }
       if (s >= P) {                                          // warp-uniform: output row o = s - P exists
         // x_t[o+ky-P][x'] * gy[o][x' - kx + P] summed over x' (this lane's column)
@@ -486,7 +552,9 @@ ww_wgrad_kernel(WwArgs a) {
         }
       }
     }
+    pbuf ^= 1;
   }
+  ww_wait<0>();
   // ---- reduce the taps over the image-row lanes; one atomic per (channel, tap) and warp ----
 #pragma unroll
   for (int t = 0; t < K * K; ++t) {
@@ -538,8 +606,16 @@ int ww_conv_launch(const WwArgs& a, cudaStream_t st) {
   const int span = WW_WARPS * (32 >> a.xl_log2) * 8;
   const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
   const bool sel = a.W + (K - 1) / 2 > XL;
-  if (sel) ww_conv_kernel<T, K, MODE, true><<<grid, WW_THREADS, 0, st>>>(a);
-  else ww_conv_kernel<T, K, MODE, false><<<grid, WW_THREADS, 0, st>>>(a);
+  constexpr int D = MODE == WW_FWD ? WwDepth<T>::FWD : WwDepth<T>::BWD;
+  const size_t smem = (size_t)WW_WARPS * (MODE == WW_FWD ? 1 : 3) * (D + 1) * 32 * WwRaw<T, 8>::BYTES;
+  static bool once = false;
+  if (!once) {
+    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    once = true;
+  }
+  if (sel) ww_conv_kernel<T, K, MODE, true><<<grid, WW_THREADS, smem, st>>>(a);
+  else ww_conv_kernel<T, K, MODE, false><<<grid, WW_THREADS, smem, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -550,8 +626,9 @@ int ww_wgrad_launch(const WwArgs& a, cudaStream_t st) {
   const int span = WW_WARPS * (32 >> a.xl_log2) * 4;
   const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
   const bool sel = a.W + (K - 1) / 2 > XL;
-  if (sel) ww_wgrad_kernel<T, K, true><<<grid, WW_THREADS, 0, st>>>(a);
-  else ww_wgrad_kernel<T, K, false><<<grid, WW_THREADS, 0, st>>>(a);
+  const size_t smem = (size_t)WW_WARPS * 3 * (WwDepth<T>::FWD + 1) * 32 * WwRaw<T, 4>::BYTES;
+  if (sel) ww_wgrad_kernel<T, K, true><<<grid, WW_THREADS, smem, st>>>(a);
+  else ww_wgrad_kernel<T, K, false><<<grid, WW_THREADS, smem, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
