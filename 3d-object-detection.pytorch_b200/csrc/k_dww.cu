@@ -157,13 +157,6 @@ __device__ __forceinline__ float2 ww_shift(const float2& v, int delta, int x, in
   return t;
 }
 
-struct WwCursor {           // prefetch position in the warp's stream of (plane, row) steps
-  int b, iy;
-  __device__ __forceinline__ void advance(int steps_per_plane, int b_stride) {
-    if (++iy == steps_per_plane) { iy = 0; b += b_stride; }
-  }
-};
-
 // per-channel constants in shared memory (written once per CTA): [which][channel of the warp's span]
 enum { WK_SC = 0, WK_SH, WK_BE, WK_N };
 // per-(sample, channel) constants, double buffered per warp and prefetched one plane ahead with cp.async
@@ -240,32 +233,35 @@ ww_conv_kernel(WwArgs a) {
   const int act = a.xf.act;
   const int steps = H + P;
   const int bstride = gridDim.y;
-  const size_t row_elems = (size_t)W * C;
-  const size_t lane_off = (size_t)x * C + c;
   const int c_warp = c_cta + warp * VL * 8;      // first channel of the warp's span
   const bool kc_mine = c_ok && x < 2;            // this lane copies 16 B (4 floats) of its vector's per-plane constants
   const int kc_off = v * 8 + x * 4;
 
   uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
   const uint32_t ring_s = ww_s32(ring);
-  auto slot_off = [&](int t, int sl) { return (uint32_t)((t * NS + sl) * 32 * VB); };
+  constexpr uint32_t SLOT = 32 * VB, TSTRIDE = NS * SLOT;          // bytes per ring slot / per tensor ring
 
-  // ---- prefetch stream ----
-  WwCursor cur = {(int)blockIdx.y, 0};
-  int fslot = 0;
+  // ---- prefetch stream: 32-bit element offsets, advanced incrementally ----
+  const uint32_t row_e = (uint32_t)W * (uint32_t)C;
+  const uint32_t lane_e = (uint32_t)x * (uint32_t)C + (uint32_t)c;
+  const uint32_t plane_jump = ((uint32_t)bstride * (uint32_t)H - (uint32_t)steps) * row_e;
+  int pb = blockIdx.y, piy = 0;
+  uint32_t foff = (uint32_t)pb * (uint32_t)H * row_e + lane_e;     // element offset of row (pb, piy) for this lane
+  uint32_t fslot = 0;                                              // byte offset of the slot to fill
   auto fetch = [&]() {
-    if (cur.b < a.B && lane_ok) {
-      const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
-      if (cur.iy < H) {
-        WwRaw<T, 8>::fetch(ring_s + slot_off(0, fslot), s0 + plane + (size_t)cur.iy * row_elems);
-        if (MODE == WW_DGRAD) WwRaw<T, 8>::fetch(ring_s + slot_off(1, fslot), s1 + plane + (size_t)cur.iy * row_elems);
+    if (pb < a.B && lane_ok) {
+      if (piy < H) {
+        WwRaw<T, 8>::fetch(ring_s + fslot, s0 + foff);
+        if (MODE == WW_DGRAD) WwRaw<T, 8>::fetch(ring_s + TSTRIDE + fslot, s1 + foff);
       }
-      if (MODE == WW_DGRAD && cur.iy >= P)        // the x row of the output row emitted at that step
-        WwRaw<T, 8>::fetch(ring_s + slot_off(2, fslot), xin + plane + (size_t)(cur.iy - P) * row_elems);
+      if (MODE == WW_DGRAD && piy >= P)          // the x row of the output row emitted at that step
+        WwRaw<T, 8>::fetch(ring_s + 2 * TSTRIDE + fslot, xin + (foff - (uint32_t)P * row_e));
     }
     ww_commit();
-    cur.advance(steps, bstride);
-    fslot = fslot + 1 == NS ? 0 : fslot + 1;
+    foff += row_e;
+    if (++piy == steps) { piy = 0; pb += bstride; foff += plane_jump; }
+    fslot += SLOT;
+    if (fslot == TSTRIDE) fslot = 0;
   };
   // constants of the first plane, then the first D rows
   ww_fetch_plane_consts(&s_p[warp][0][0][0], 32, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
@@ -274,7 +270,8 @@ ww_conv_kernel(WwArgs a) {
   __syncwarp();
 #pragma unroll 1
   for (int d = 0; d < D; ++d) fetch();
-  int cslot = 0, pbuf = 0;
+  uint32_t cslot = 0;
+  int pbuf = 0;
 
   for (int b = blockIdx.y; b < a.B; b += bstride) {
     // ---- per-plane constants: this plane's are in s_p[pbuf] (prefetched a plane ago), start the next plane's ----
@@ -282,115 +279,126 @@ ww_conv_kernel(WwArgs a) {
     __syncwarp();
     const float* kp = &s_p[warp][pbuf][0][0];
     ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 32, a, b + bstride, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
-    float2 acc[K][4];
+    // S[k] = partial sums of output row (iy - P + k) before row iy is processed; row iy adds filter row 2P - k
+    float2 S[K - 1][4];
 #pragma unroll
-    for (int k = 0; k < K; ++k)
+    for (int k = 0; k < K - 1; ++k)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[k][i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < 4; ++i) S[k][i] = make_float2(0.f, 0.f);
     float2 st1[4], st2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { st1[i] = make_float2(0.f, 0.f); st2[i] = st1[i]; }
-    const size_t plane = (size_t)b * H * row_elems + lane_off;
+    uint32_t ooff = (uint32_t)b * (uint32_t)H * row_e + lane_e;    // next output row of this lane
 
-    for (int iy0 = 0; iy0 < steps; iy0 += K) {
+#pragma unroll 1
+    for (int iy = 0; iy < steps; ++iy) {
+      ww_wait<D - 1>();                                   // this step's rows have landed (own copies only)
+      WwRaw<T, 8> c0, c1, cx;
+      c0.lds(ring + cslot);
+      if (MODE == WW_DGRAD) { c1.lds(ring + TSTRIDE + cslot); cx.lds(ring + 2 * TSTRIDE + cslot); }
+      cslot += SLOT;
+      if (cslot == TSTRIDE) cslot = 0;
+      fetch();                                            // refills the slot consumed one step ago
+      float2 o[4];
+      if (iy < H) {                                       // warp-uniform
+        float2 vals[K][4];
+        if (lane_ok) {
+          c0.get(vals[P]);
+          if (MODE == WW_FWD) {
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const int iy = iy0 + j;
-        if (iy < steps) {                                   // warp-uniform
-          ww_wait<D - 1>();                                 // this step's rows have landed (own copies only)
-          WwRaw<T, 8> c0, c1, cx;
-          c0.lds(ring + slot_off(0, cslot));
-          if (MODE == WW_DGRAD) { c1.lds(ring + slot_off(1, cslot)); cx.lds(ring + slot_off(2, cslot)); }
-          cslot = cslot + 1 == NS ? 0 : cslot + 1;
-          fetch();                                          // refills the slot consumed one step ago
-          if (iy < H) {
-            float2 vals[K][4];
-            if (lane_ok) {
-              c0.get(vals[P]);
-              if (MODE == WW_FWD) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
-                  const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
-                  const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
-                  float2 u = __ffma2_rn(vals[P][i], sc, sh);
-                  u = __fmul2_rn(u, e);
-                  vals[P][i] = make_float2(ww_act(u.x, act), ww_act(u.y, act));
-                }
-              } else {
-                float2 yv[4];
-                c1.get(yv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 32 + v * 8 + 2 * i);
-                  const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 32 + v * 8 + 2 * i);
-                  const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 32 + v * 8 + 2 * i);
-                  vals[P][i] = __ffma2_rn(al, vals[P][i], __ffma2_rn(be, yv[i], ga));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) vals[P][i] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 4; ++i) {
+              const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
+              const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+              const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
+              float2 u = __ffma2_rn(vals[P][i], sc, sh);
+              u = __fmul2_rn(u, e);
+              vals[P][i] = make_float2(ww_act(u.x, act), ww_act(u.y, act));
             }
+          } else {
+            float2 yv[4];
+            c1.get(yv);
 #pragma unroll
-            for (int d = 1; d <= P; ++d)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                vals[P - d][i] = ww_shift<SEL>(vals[P][i], -d, x, W);
-                vals[P + d][i] = ww_shift<SEL>(vals[P][i], d, x, W);
-              }
-#pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-              constexpr int KK = K;
-              const int idx = (j - ky + P + KK) % KK;      // output row iy - ky + P
-#pragma unroll
-              for (int kx = 0; kx < K; ++kx) {
-                const float4 w0 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span);
-                const float4 w1 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span + 4);
-                acc[idx][0] = __ffma2_rn(vals[kx][0], make_float2(w0.x, w0.y), acc[idx][0]);
-                acc[idx][1] = __ffma2_rn(vals[kx][1], make_float2(w0.z, w0.w), acc[idx][1]);
-                acc[idx][2] = __ffma2_rn(vals[kx][2], make_float2(w1.x, w1.y), acc[idx][2]);
-                acc[idx][3] = __ffma2_rn(vals[kx][3], make_float2(w1.z, w1.w), acc[idx][3]);
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 32 + v * 8 + 2 * i);
+              const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 32 + v * 8 + 2 * i);
+              const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 32 + v * 8 + 2 * i);
+              vals[P][i] = __ffma2_rn(al, vals[P][i], __ffma2_rn(be, yv[i], ga));
             }
           }
-          // ---- output row iy - P is complete ----
-          const int oy = iy - P;
-          const int eidx = (j - P + K) % K;
-          if (oy >= 0 && lane_ok) {
-            float2 o[4], r[4];
+        } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = acc[eidx][i];
-            if (MODE == WW_DGRAD) {
-              float2 xv[4];
-              cx.get(xv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
-                const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
-                const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
-                const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
-                o[i].x *= ww_actd(u.x, act);
-                o[i].y *= ww_actd(u.y, act);
-              }
-              ww_store8(out + plane + (size_t)oy * row_elems, o, r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                st1[i] = __fadd2_rn(st1[i], r[i]);
-                st2[i] = __ffma2_rn(r[i], xv[i], st2[i]);
-              }
-            } else {
-              ww_store8(out + plane + (size_t)oy * row_elems, o, r);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                st1[i] = __fadd2_rn(st1[i], r[i]);
-                st2[i] = __ffma2_rn(r[i], r[i], st2[i]);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[eidx][i] = make_float2(0.f, 0.f);
+          for (int i = 0; i < 4; ++i) vals[P][i] = make_float2(0.f, 0.f);
         }
+#pragma unroll
+        for (int d = 1; d <= P; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            vals[P - d][i] = ww_shift<SEL>(vals[P][i], -d, x, W);
+            vals[P + d][i] = ww_shift<SEL>(vals[P][i], d, x, W);
+          }
+        // slot k receives filter row ky = 2P - k; the shift of the slots is folded into the accumulation
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float2 t[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t[i] = k < K - 1 ? S[k < K - 1 ? k : 0][i] : make_float2(0.f, 0.f);
+          const int ky = 2 * P - k;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span);
+            const float4 w1 = *reinterpret_cast<const float4*>(wq + (ky * K + kx) * span + 4);
+            t[0] = __ffma2_rn(vals[kx][0], make_float2(w0.x, w0.y), t[0]);
+            t[1] = __ffma2_rn(vals[kx][1], make_float2(w0.z, w0.w), t[1]);
+            t[2] = __ffma2_rn(vals[kx][2], make_float2(w1.x, w1.y), t[2]);
+            t[3] = __ffma2_rn(vals[kx][3], make_float2(w1.z, w1.w), t[3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (k == 0) o[i] = t[i];
+            else S[k - 1][i] = t[i];
+          }
+        }
+      } else {                                            // zero rows below the plane: only drain the slots
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[i] = S[0][i];
+#pragma unroll
+          for (int k = 0; k + 2 < K; ++k) S[k][i] = S[k + 1][i];
+          S[K - 2][i] = make_float2(0.f, 0.f);
+        }
+      }
+      // ---- output row iy - P is complete ----
+      if (iy >= P) {
+        if (lane_ok) {
+          float2 r[4];
+          if (MODE == WW_DGRAD) {
+            float2 xv[4];
+            cx.get(xv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
+              const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+              const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
+              const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
+              o[i].x *= ww_actd(u.x, act);
+              o[i].y *= ww_actd(u.y, act);
+            }
+            ww_store8(out + ooff, o, r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              st1[i] = __fadd2_rn(st1[i], r[i]);
+              st2[i] = __ffma2_rn(r[i], xv[i], st2[i]);
+            }
+          } else {
+            ww_store8(out + ooff, o, r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              st1[i] = __fadd2_rn(st1[i], r[i]);
+              st2[i] = __ffma2_rn(r[i], r[i], st2[i]);
+            }
+          }
+        }
+        ooff += row_e;
       }
     }
     pbuf ^= 1;
@@ -398,11 +406,11 @@ ww_conv_kernel(WwArgs a) {
     if (a.stats) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        for (int o = 1; o < XL; o <<= 1) {
-          st1[i].x += __shfl_xor_sync(0xffffffffu, st1[i].x, o);
-          st1[i].y += __shfl_xor_sync(0xffffffffu, st1[i].y, o);
-          st2[i].x += __shfl_xor_sync(0xffffffffu, st2[i].x, o);
-          st2[i].y += __shfl_xor_sync(0xffffffffu, st2[i].y, o);
+        for (int o2 = 1; o2 < XL; o2 <<= 1) {
+          st1[i].x += __shfl_xor_sync(0xffffffffu, st1[i].x, o2);
+          st1[i].y += __shfl_xor_sync(0xffffffffu, st1[i].y, o2);
+          st2[i].x += __shfl_xor_sync(0xffffffffu, st2[i].x, o2);
+          st2[i].y += __shfl_xor_sync(0xffffffffu, st2[i].y, o2);
         }
       }
       if (x == 0 && c_ok) {
@@ -467,28 +475,31 @@ ww_wgrad_kernel(WwArgs a) {
   const int act = a.xf.act;
   const int steps = H + P;
   const int bstride = gridDim.y;
-  const size_t row_elems = (size_t)W * C;
-  const size_t lane_off = (size_t)x * C + c;
   const bool kc_mine = c_ok && x == 0;           // one 16-byte copy per 4-channel vector and kind
   const int kc_off = q * 4;
 
   uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
   const uint32_t ring_s = ww_s32(ring);
-  auto slot_off = [&](int t, int sl) { return (uint32_t)((t * NS + sl) * 32 * VB); };
-  WwCursor cur = {(int)blockIdx.y, 0};
-  int fslot = 0;
+  constexpr uint32_t SLOT = 32 * VB, TSTRIDE = NS * SLOT;
+  const uint32_t row_e = (uint32_t)W * (uint32_t)C;
+  const uint32_t lane_e = (uint32_t)x * (uint32_t)C + (uint32_t)c;
+  const uint32_t plane_jump = ((uint32_t)bstride * (uint32_t)H - (uint32_t)steps) * row_e;
+  int pb = blockIdx.y, piy = 0;
+  uint32_t foff = (uint32_t)pb * (uint32_t)H * row_e + lane_e;
+  uint32_t fslot = 0;
   auto fetch = [&]() {
-    if (cur.b < a.B && lane_ok) {
-      const size_t plane = (size_t)cur.b * H * row_elems + lane_off;
-      if (cur.iy < H) WwRaw<T, 4>::fetch(ring_s + slot_off(2, fslot), xp + plane + (size_t)cur.iy * row_elems);   // x row s
-      if (cur.iy >= P) {                                                                                         // gy row s - P
-        WwRaw<T, 4>::fetch(ring_s + slot_off(0, fslot), gp + plane + (size_t)(cur.iy - P) * row_elems);
-        WwRaw<T, 4>::fetch(ring_s + slot_off(1, fslot), yp + plane + (size_t)(cur.iy - P) * row_elems);
+    if (pb < a.B && lane_ok) {
+      if (piy < H) WwRaw<T, 4>::fetch(ring_s + 2 * TSTRIDE + fslot, xp + foff);                 // x row s
+      if (piy >= P) {                                                                           // gy row s - P
+        WwRaw<T, 4>::fetch(ring_s + fslot, gp + (foff - (uint32_t)P * row_e));
+        WwRaw<T, 4>::fetch(ring_s + TSTRIDE + fslot, yp + (foff - (uint32_t)P * row_e));
       }
     }
     ww_commit();
-    cur.advance(steps, bstride);
-    fslot = fslot + 1 == NS ? 0 : fslot + 1;
+    foff += row_e;
+    if (++piy == steps) { piy = 0; pb += bstride; foff += plane_jump; }
+    fslot += SLOT;
+    if (fslot == TSTRIDE) fslot = 0;
   };
   ww_fetch_plane_consts(&s_p[warp][0][0][0], 16, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, true);
   ww_commit();
@@ -496,7 +507,8 @@ ww_wgrad_kernel(WwArgs a) {
   __syncwarp();
 #pragma unroll 1
   for (int d = 0; d < D; ++d) fetch();
-  int cslot = 0, pbuf = 0;
+  uint32_t cslot = 0;
+  int pbuf = 0;
 
   float2 dwa[K * K][2];
 #pragma unroll
@@ -510,13 +522,15 @@ ww_wgrad_kernel(WwArgs a) {
     float2 xw[K][2];                // transformed x rows s-2P .. s (row o+ky-P of the current output row o = s-P)
 #pragma unroll
     for (int k = 0; k < K; ++k) { xw[k][0] = make_float2(0.f, 0.f); xw[k][1] = xw[k][0]; }
+#pragma unroll 1
     for (int s = 0; s < steps; ++s) {
       ww_wait<D - 1>();
       WwRaw<T, 4> cg, cy, cx;
-      cg.lds(ring + slot_off(0, cslot));
-      cy.lds(ring + slot_off(1, cslot));
-      cx.lds(ring + slot_off(2, cslot));
-      cslot = cslot + 1 == NS ? 0 : cslot + 1;
+      cg.lds(ring + cslot);
+      cy.lds(ring + TSTRIDE + cslot);
+      cx.lds(ring + 2 * TSTRIDE + cslot);
+      cslot += SLOT;
+      if (cslot == TSTRIDE) cslot = 0;
       fetch();
 #pragma unroll
       for (int k = 0; k + 1 < K; ++k) { xw[k][0] = xw[k + 1][0]; xw[k][1] = xw[k + 1][1]; }
@@ -646,6 +660,7 @@ bool dw_walker_supported(int H, int W, int C, int k, int stride) {
 }
 
 int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st) {
+  TD3D_REQUIRE((double)a.B * a.H * a.W * a.C < 4294967296.0, "dw walker: tensor exceeds the 32-bit offset range");
   WwArgs w = {};
   w.s0 = a.x; w.xf = a.xf; w.w = a.w_taps; w.out = a.y; w.stats = a.stats;
   w.B = a.B; w.H = a.H; w.W = a.W; w.C = a.C; w.xl_log2 = ww_xl_log2(a.W);
@@ -654,6 +669,7 @@ int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st) {
 }
 
 int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st) {
+  TD3D_REQUIRE((double)a.B * a.H * a.W * a.C < 4294967296.0, "dw walker: tensor exceeds the 32-bit offset range");
   WwArgs w = {};
   w.s0 = a.g; w.s1 = a.y_out; w.xin = a.x; w.xf = a.xf;
   w.alpha = a.alpha; w.beta = a.beta; w.gamma = a.gamma; w.w = a.w_taps;
