@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   for (int i = 0; i < BN_WARPS; ++i) { S1 += s_sum[0][i][lane]; S2 += s_sum[1][i][lane]; }
   const double c1 = S1 / M, c2 = S2 / M;
   const double aa = (double)a.gamma[c] * is;
-  if (w == 0) {
+  // gridDim.y CTAs repeat the (L2-resident) slot reduction and split the B per-sample writes
+  const int b_chunk = (a.B + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int b_begin = (int)blockIdx.y * b_chunk, b_end = min(a.B, b_begin + b_chunk);
+  if (w == 0 && blockIdx.y == 0) {
     a.beta[c] = (float)(-aa * c2 * is);
     a.dgamma[c] = (float)S2;
     a.dbeta[c] = (float)S1;
@@ -146,25 +149,25 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
   float* __restrict__ gammac_o = a.gammac + c;
   if (!se_mode) {
 #pragma unroll 4
-    for (int b = w; b < a.B; b += BN_WARPS) {
+    for (int b = b_begin + w; b < b_end; b += BN_WARPS) {
       alpha_o[(size_t)b * a.C] = aa_f;
       gammac_o[(size_t)b * a.C] = g0_f;
     }
   } else {
     const float* __restrict__ sep = a.se + c;
     const float* __restrict__ gpp = a.g_pool + c;
-    for (int b0 = w; b0 < a.B; b0 += 8 * BN_WARPS) {
+    for (int b0 = b_begin + w; b0 < b_end; b0 += 8 * BN_WARPS) {
       float gate[8], gp[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int b = b0 + u * BN_WARPS;
-        gate[u] = b < a.B ? __ldg(sep + (size_t)b * a.C) : 0.f;
-        gp[u] = b < a.B ? __ldg(gpp + (size_t)b * a.C) : 0.f;
+        gate[u] = b < b_end ? __ldg(sep + (size_t)b * a.C) : 0.f;
+        gp[u] = b < b_end ? __ldg(gpp + (size_t)b * a.C) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int b = b0 + u * BN_WARPS;
-        if (b < a.B) {
+        if (b < b_end) {
           alpha_o[(size_t)b * a.C] = aa_f * gate[u];
           gammac_o[(size_t)b * a.C] = fmaf(ahw_f, gp[u], g0_f);
         }
@@ -175,7 +178,8 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
 
 int launch_bn_bwd_finalize(const BnBwdArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(!a.se || a.slots == a.B, "bn_bwd_finalize: SE mode needs slots == B");
-  bn_bwd_finalize_kernel<<<ceil_div(a.C, 32), 32 * BN_WARPS, 0, st>>>(a);
+  const int gy = a.B >= 64 ? 8 : 1;
+  bn_bwd_finalize_kernel<<<dim3(ceil_div(a.C, 32), gy), 32 * BN_WARPS, 0, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

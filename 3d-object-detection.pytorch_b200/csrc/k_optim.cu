@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128) bn_fold_table_kernel(const __grid_constan
 }
 int launch_pack_table(const PackTable& t, cudaStream_t st) {
   if (t.n <= 0) return TD3D_OK;
-  pack_table_kernel<<<dim3(32, t.n), 256, 0, st>>>(t);
+  pack_table_kernel<<<dim3(148, t.n), 256, 0, st>>>(t);   // the two 1.2 M-element classifier segments set the duration
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

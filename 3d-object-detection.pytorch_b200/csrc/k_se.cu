@@ -58,25 +58,42 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(SeFc p) {
   extern __shared__ __align__(16) float se_sa[];     // [SE_SB][K]
   const int b0 = blockIdx.x * SE_SB, n0 = blockIdx.y * SE_NB;
   const int K = p.K;
-  // ---- stage A (zero rows past the batch) ----
-  for (int i = threadIdx.x; i < SE_SB * K; i += SE_THREADS) {
-    const int s = i / K, k = i - s * K, b = b0 + s;
-    float v = 0.f;
-    if (b < p.B) {
-      if (AMODE == SE_A_PLAIN) {
-        v = p.a[(size_t)b * K + k];
-      } else if (AMODE == SE_A_ZBAR) {
-        v = p.stats[((size_t)b * 2 + 0) * K + k] * p.inv_hw;
-        if (p.scale) v = fmaf(v, p.scale[k], p.shift[k]);
-      } else {
-        const float p1 = p.stats[((size_t)b * 2 + 0) * K + k];
-        const float p2 = p.stats[((size_t)b * 2 + 1) * K + k];
-        const float gs = p.scale ? fmaf(p.scale[k], p2, p.shift[k] * p1) : p2;
-        v = gs * hsigmoid_bwd(p.pre[(size_t)b * K + k]);
+  // ---- stage A (zero rows past the batch): batches of 4 elements so that their loads are in flight together ----
+  const int nA = SE_SB * K;
+  for (int i0 = threadIdx.x; i0 < nA; i0 += 4 * SE_THREADS) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * SE_THREADS;
+      v[u] = 0.f;
+      if (i < nA) {
+        const int s = i / K, k = i - s * K, b = b0 + s;
+        if (b < p.B) {
+          if (AMODE == SE_A_PLAIN) {
+            v[u] = __ldg(p.a + (size_t)b * K + k);
+          } else if (AMODE == SE_A_ZBAR) {
+            v[u] = __ldg(p.stats + ((size_t)b * 2 + 0) * K + k) * p.inv_hw;
+            if (p.scale) v[u] = fmaf(v[u], __ldg(p.scale + k), __ldg(p.shift + k));
+          } else {
+            const float p1 = __ldg(p.stats + ((size_t)b * 2 + 0) * K + k);
+            const float p2 = __ldg(p.stats + ((size_t)b * 2 + 1) * K + k);
+            const float gs = p.scale ? fmaf(__ldg(p.scale + k), p2, __ldg(p.shift + k) * p1) : p2;
+            v[u] = gs * hsigmoid_bwd(__ldg(p.pre + (size_t)b * K + k));
+          }
+        }
       }
-      if (AMODE != SE_A_PLAIN && blockIdx.y == 0) p.a_out[(size_t)b * K + k] = v;
     }
-    se_sa[i] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * SE_THREADS;
+      if (i < nA) {
+        se_sa[i] = v[u];
+        if (AMODE != SE_A_PLAIN && blockIdx.y == 0) {
+          const int s = i / K, k = i - s * K, b = b0 + s;
+          if (b < p.B) p.a_out[(size_t)b * K + k] = v[u];
+        }
+      }
+    }
   }
   __syncthreads();
   // ---- 4 columns per warp ----
@@ -88,6 +105,7 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(SeFc p) {
   const float* wr[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wr[j] = p.w + (size_t)min(nw + j, p.N - 1) * K;   // clamped rows are discarded below
+#pragma unroll 2
   for (int k = lane * 4; k < K; k += 128) {
     float4 wv[4];
 #pragma unroll
