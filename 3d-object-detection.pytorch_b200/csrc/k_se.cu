@@ -58,41 +58,43 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(SeFc p) {
   extern __shared__ __align__(16) float se_sa[];     // [SE_SB][K]
   const int b0 = blockIdx.x * SE_SB, n0 = blockIdx.y * SE_NB;
   const int K = p.K;
-  // ---- stage A (zero rows past the batch): batches of 4 elements so that their loads are in flight together ----
-  const int nA = SE_SB * K;
-  for (int i0 = threadIdx.x; i0 < nA; i0 += 4 * SE_THREADS) {
-    float v[4];
+  // ---- stage A (zero rows past the batch): a thread owns column k of all SE_SB rows, so the loads of the 8
+  // samples are in flight together and the per-column constants are read once ----
+  for (int k = threadIdx.x; k < K; k += SE_THREADS) {
+    float v[SE_SB];
+    float sck = 1.f, shk = 0.f;
+    if (AMODE != SE_A_PLAIN && p.scale) { sck = __ldg(p.scale + k); shk = __ldg(p.shift + k); }
+    if (AMODE == SE_A_PLAIN) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * SE_THREADS;
-      v[u] = 0.f;
-      if (i < nA) {
-        const int s = i / K, k = i - s * K, b = b0 + s;
-        if (b < p.B) {
-          if (AMODE == SE_A_PLAIN) {
-            v[u] = __ldg(p.a + (size_t)b * K + k);
-          } else if (AMODE == SE_A_ZBAR) {
-            v[u] = __ldg(p.stats + ((size_t)b * 2 + 0) * K + k) * p.inv_hw;
-            if (p.scale) v[u] = fmaf(v[u], __ldg(p.scale + k), __ldg(p.shift + k));
-          } else {
-            const float p1 = __ldg(p.stats + ((size_t)b * 2 + 0) * K + k);
-            const float p2 = __ldg(p.stats + ((size_t)b * 2 + 1) * K + k);
-            const float gs = p.scale ? fmaf(__ldg(p.scale + k), p2, __ldg(p.shift + k) * p1) : p2;
-            v[u] = gs * hsigmoid_bwd(__ldg(p.pre + (size_t)b * K + k));
-          }
-        }
+      for (int s = 0; s < SE_SB; ++s) v[s] = b0 + s < p.B ? __ldg(p.a + (size_t)(b0 + s) * K + k) : 0.f;
+    } else if (AMODE == SE_A_ZBAR) {
+#pragma unroll
+      for (int s = 0; s < SE_SB; ++s) v[s] = b0 + s < p.B ? __ldg(p.stats + ((size_t)(b0 + s) * 2 + 0) * K + k) : 0.f;
+#pragma unroll
+      for (int s = 0; s < SE_SB; ++s) {
+        v[s] *= p.inv_hw;
+        if (p.scale) v[s] = fmaf(v[s], sck, shk);
+        if (b0 + s >= p.B) v[s] = 0.f;
+      }
+    } else {
+      float p1[SE_SB], p2[SE_SB], pr[SE_SB];
+#pragma unroll
+      for (int s = 0; s < SE_SB; ++s) {
+        const bool on = b0 + s < p.B;
+        p1[s] = on ? __ldg(p.stats + ((size_t)(b0 + s) * 2 + 0) * K + k) : 0.f;
+        p2[s] = on ? __ldg(p.stats + ((size_t)(b0 + s) * 2 + 1) * K + k) : 0.f;
+        pr[s] = on ? __ldg(p.pre + (size_t)(b0 + s) * K + k) : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < SE_SB; ++s) {
+        const float gs = p.scale ? fmaf(sck, p2[s], shk * p1[s]) : p2[s];
+        v[s] = b0 + s < p.B ? gs * hsigmoid_bwd(pr[s]) : 0.f;
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * SE_THREADS;
-      if (i < nA) {
-        se_sa[i] = v[u];
-        if (AMODE != SE_A_PLAIN && blockIdx.y == 0) {
-          const int s = i / K, k = i - s * K, b = b0 + s;
-          if (b < p.B) p.a_out[(size_t)b * K + k] = v[u];
-        }
-      }
+    for (int s = 0; s < SE_SB; ++s) {
+      se_sa[s * K + k] = v[s];
+      if (AMODE != SE_A_PLAIN && blockIdx.y == 0 && b0 + s < p.B) p.a_out[(size_t)(b0 + s) * K + k] = v[s];
     }
   }
   __syncthreads();
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(SeFc p) {
   const float* wr[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) wr[j] = p.w + (size_t)min(nw + j, p.N - 1) * K;   // clamped rows are discarded below
-#pragma unroll 2
+#pragma unroll 4
   for (int k = lane * 4; k < K; k += 128) {
     float4 wv[4];
 #pragma unroll
