@@ -947,8 +947,9 @@ int d2_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
     const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2WGeo<K, S>::OY, D2WGeo<K, S>::OX, S, K, 1, 1, V, K, sizeof(T),
                                (D2_THREADS / 32) * K * K * cg);
     TD3D_REQUIRE(t.cg > 0, "dw bwd-weight: no tile fits");
-    if (t.cg == 32) TD3D_TRY((d2_bwd_weight_launch<T, K, S, 32>(a, t, Ho, Wo, st)));
-    else TD3D_TRY((d2_bwd_weight_launch<T, K, S, 16>(a, t, Ho, Wo, st)));
+    cudaStream_t wst = a.wgrad_stream ? (cudaStream_t)a.wgrad_stream : st;
+    if (t.cg == 32) TD3D_TRY((d2_bwd_weight_launch<T, K, S, 32>(a, t, Ho, Wo, wst)));
+    else TD3D_TRY((d2_bwd_weight_launch<T, K, S, 16>(a, t, Ho, Wo, wst)));
   }
   return TD3D_OK;
 }

@@ -680,8 +680,9 @@ int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st) {
     else TD3D_TRY((a.k == 3 ? ww_conv_launch<float, 3, WW_DGRAD>(w, st) : ww_conv_launch<float, 5, WW_DGRAD>(w, st)));
   }
   if (a.dw) {
-    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_wgrad_launch<bf16, 3>(w, st) : ww_wgrad_launch<bf16, 5>(w, st)));
-    else TD3D_TRY((a.k == 3 ? ww_wgrad_launch<float, 3>(w, st) : ww_wgrad_launch<float, 5>(w, st)));
+    cudaStream_t wst = a.wgrad_stream ? (cudaStream_t)a.wgrad_stream : st;
+    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_wgrad_launch<bf16, 3>(w, wst) : ww_wgrad_launch<bf16, 5>(w, wst)));
+    else TD3D_TRY((a.k == 3 ? ww_wgrad_launch<float, 3>(w, wst) : ww_wgrad_launch<float, 5>(w, wst)));
   }
   return TD3D_OK;
 }

@@ -9,6 +9,7 @@
 //   loss.backward()/step() torchdet3d/trainer/train.py:50-52
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -111,6 +112,12 @@ struct td3d_plan {
   uint64_t last_seed = 0; int last_training = 0;
   const int32_t* dropout_counter = nullptr;
   Prof prof;
+  // side streams of backward (created at bind time, outside any graph capture): [0] runs the weight-gradient
+  // GEMMs, [1] the depthwise weight-gradient kernels, concurrently with the data-gradient chain on the caller's stream
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool side_pending[2] = {false, false};
+  int overlap = 1;
   td3d::PackTable pack_table;
   td3d::BnFoldTable fold_table;
 };
@@ -341,6 +348,35 @@ struct Ctx {
   double esz() const { return (double)pl->esz; }
 };
 
+// ---- backward side streams ---------------------------------------------------------------------
+// fork: work launched on the returned context starts after everything issued so far on c.st.
+// join: c.st waits for everything issued on that side stream.  Both are plain event record / wait
+// pairs, so a CUDA-graph capture of the caller's stream records them as graph edges.
+static bool side_on(const Ctx& c, int which) {
+  return c.pl->overlap && !c.pl->prof.enabled && c.pl->side[which] != nullptr;
+}
+static int side_fork(const Ctx& c, int which, Ctx* out) {
+  *out = c;
+  if (!side_on(c, which)) return TD3D_OK;
+  td3d_plan* pl = c.pl;
+  TD3D_CUDA(cudaEventRecord(pl->ev_fork[which], c.st));
+  TD3D_CUDA(cudaStreamWaitEvent(pl->side[which], pl->ev_fork[which], 0));
+  out->st = pl->side[which];
+  return TD3D_OK;
+}
+static int side_done(const Ctx& c, int which) {        // call after the side launches of one fork
+  if (!side_on(c, which)) return TD3D_OK;
+  TD3D_CUDA(cudaEventRecord(c.pl->ev_join[which], c.pl->side[which]));
+  c.pl->side_pending[which] = true;
+  return TD3D_OK;
+}
+static int side_join(const Ctx& c, int which) {
+  if (!c.pl->side_pending[which]) return TD3D_OK;
+  TD3D_CUDA(cudaStreamWaitEvent(c.st, c.pl->ev_join[which], 0));
+  c.pl->side_pending[which] = false;
+  return TD3D_OK;
+}
+
 // run a launcher under the profiler: K = kind, BYTES = algorithmic bytes this launch must move
 #define TD3D_K(K, BYTES, expr)        \
   do {                                \
@@ -377,11 +413,22 @@ static int p_dwf(const Ctx& c, const DwArgs& a, int dt, cudaStream_t st) {
   TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd(a, dt, st));
   return TD3D_OK;
 }
-static int p_dwb(const Ctx& c, const DwBwdArgs& a, int dt, cudaStream_t st) {
+static int p_dwb(const Ctx& c, const DwBwdArgs& a0, int dt, cudaStream_t st) {
+  DwBwdArgs a = a0;
   int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
   double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
+  // the weight-gradient kernel runs on side stream 1, concurrently with the data-gradient kernel (both
+  // read g, y_out, x: the second reader mostly hits L2); joined right after, because the next BatchNorm
+  // finalize overwrites the alpha/beta/gamma it reads
+  Ctx sc;
+  TD3D_TRY(side_fork(c, 1, &sc));
+  a.wgrad_stream = sc.st != c.st ? (void*)sc.st : nullptr;
   // fused ideal: read g, y_out, x once; write gx once
   TD3D_K(PK_DW_BWD, (2 * out + 2 * in) * c.esz(), launch_dw_bwd(a, dt, st));
+  if (a.wgrad_stream) {
+    TD3D_TRY(side_done(c, 1));
+    TD3D_TRY(side_join(c, 1));
+  }
   return TD3D_OK;
 }
 
@@ -399,7 +446,17 @@ static int gemm_nt(const Ctx& c, GemmNT g, int kind = PK_GEMM_FWD) {
   else { TD3D_K(kind, bytes, launch_gemm_nt_simt(g, c.pl->dtype, c.st)); }
   return TD3D_OK;
 }
+static int gemm_tn_main(const Ctx& c, GemmTN g);
+// weight-gradient GEMM on side stream 0; the caller joins (side_join(c, 0)) before the next kernel on
+// c.st that overwrites an operand it reads
 static int gemm_tn(const Ctx& c, GemmTN g) {
+  Ctx sc;
+  TD3D_TRY(side_fork(c, 0, &sc));
+  TD3D_TRY(gemm_tn_main(sc, g));
+  if (sc.st != c.st) TD3D_TRY(side_done(c, 0));
+  return TD3D_OK;
+}
+static int gemm_tn_main(const Ctx& c, GemmTN g) {
   double bytes = ((double)g.M * g.N1 + (double)g.M * g.N2) * c.esz() + 4.0 * g.N1 * g.N2;
   if (c.pl->dtype == TD3D_BF16 && c.pl->gemm_impl != TD3D_GEMM_SIMT && g.N1 % 8 == 0 && g.N2 % 8 == 0) {
     TD3D_K(PK_GEMM_WGRAD, bytes, launch_gemm_tn_tc(g, c.st));
@@ -627,6 +684,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       g.M = B; g.N = n.last_ch; g.K = n.head_ch;
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
+    TD3D_TRY(side_join(c, 0));        // the classifier weight-gradient GEMM reads g_wide_a, rewritten next
     // avg-pool backward + h_swish + BN of the final conv
     Bn& bl = pl->bns[pl->bn_last];
     XForm xl = xf_make(c.wsf(bl.scale), c.wsf(bl.shift), nullptr, TD3D_ACT_HSWISH);
@@ -651,6 +709,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     if (!in_range(nblk - i)) continue;
     Block& b = pl->blocks[i];
     pl->prof.tag = 1000 + i + 1;
+    TD3D_TRY(side_join(c, 0));        // weight-gradient GEMMs of the previous stage read g_wide_a/b and g_y3, rewritten below
     const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
@@ -754,6 +813,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
   }
   if (in_range(nblk + 1)) {
     pl->prof.tag = 1000;
+    TD3D_TRY(side_join(c, 0));
     // stem: x0 = h_swish(BN(y0)); gradient w.r.t. x0 is in g_narrow[0]
     Bn& b0 = pl->bns[pl->bn_stem];
     const int HW1 = pl->H1 * pl->W1;
@@ -764,6 +824,8 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     TD3D_K(PK_STEM_WGRAD, (double)B * 3 * pl->H * pl->W * 4 + 2.0 * B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_wgrad(pl->last_img, g0, c.ws(pl->y0), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                                c.G(pl->w_stem), B, pl->H, pl->W, n.stem_ch, dt, c.st));
   }
+  TD3D_TRY(side_join(c, 0));          // every gradient of this stage range is final on c.st when the call returns
+  TD3D_TRY(side_join(c, 1));
   return TD3D_OK;
 }
 
@@ -863,7 +925,15 @@ int td3d_plan_create(const td3d_net_desc* net, int batch, int height, int width,
   return TD3D_OK;
 }
 
-void td3d_plan_destroy(td3d_plan* plan) { delete plan; }
+void td3d_plan_destroy(td3d_plan* plan) {
+  if (!plan) return;
+  for (int i = 0; i < 2; ++i) {
+    if (plan->side[i]) cudaStreamDestroy(plan->side[i]);
+    if (plan->ev_fork[i]) cudaEventDestroy(plan->ev_fork[i]);
+    if (plan->ev_join[i]) cudaEventDestroy(plan->ev_join[i]);
+  }
+  delete plan;
+}
 
 int td3d_plan_sizes(const td3d_plan* pl, td3d_sizes* out) {
   TD3D_REQUIRE(pl && out, "plan_sizes: null argument");
@@ -899,6 +969,15 @@ int td3d_plan_bind(td3d_plan* pl, float* params, float* grads, float* bn_stats, 
                "plan_bind: buffers must be 256-byte aligned");
   pl->P = params; pl->G = grads; pl->BNB = bn_stats; pl->NBT = nbt;
   pl->PK = (uint8_t*)packed; pl->WS = (uint8_t*)workspace;
+  if (!pl->side[0]) {
+    const char* e = getenv("TD3D_OVERLAP");
+    pl->overlap = (e && atoi(e) == 0) ? 0 : 1;
+    for (int i = 0; i < 2; ++i) {
+      TD3D_CUDA(cudaStreamCreateWithFlags(&pl->side[i], cudaStreamNonBlocking));
+      TD3D_CUDA(cudaEventCreateWithFlags(&pl->ev_fork[i], cudaEventDisableTiming));
+      TD3D_CUDA(cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming));
+    }
+  }
   return build_tables(pl);
 }
 

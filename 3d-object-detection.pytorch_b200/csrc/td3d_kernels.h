@@ -81,6 +81,8 @@ struct DwBwdArgs {
   float* stats;                                     // out: [B][2][C] sum gu_in, sum gu_in*x
   float* dw;                                        // out: grads arena, reference layout [C,1,k,k] (+=)
   int B, H, W, C, k, stride;
+  void* wgrad_stream = nullptr;                     // optional cudaStream_t for the weight-gradient kernel (null: same stream);
+                                                    // the caller orders it against the launching stream with events
 };
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
 int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu (default)
