@@ -50,11 +50,6 @@ struct WwArgs {
   int xl_log2;               // lanes per image row = 1 << xl_log2 (>= W)
 };
 
-__device__ __forceinline__ float ww_act(float u, int act) {
-  if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
-  if (act == TD3D_ACT_HSWISH) return u * __saturatef(fmaf(u, 1.f / 6.f, 0.5f));
-  return u;
-}
 __device__ __forceinline__ float ww_actd(float u, int act) {
   if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
   if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
@@ -231,6 +226,7 @@ ww_conv_kernel(WwArgs a) {
   const T* xin = reinterpret_cast<const T*>(a.xin);
   T* out = reinterpret_cast<T*>(a.out);
   const int act = a.xf.act;
+  const ActK ak = make_actk(act);
   const int steps = H + P;
   const int bstride = gridDim.y;
   const int c_warp = c_cta + warp * VL * 8;      // first channel of the warp's span
@@ -312,7 +308,7 @@ ww_conv_kernel(WwArgs a) {
               const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
               float2 u = __ffma2_rn(vals[P][i], sc, sh);
               u = __fmul2_rn(u, e);
-              vals[P][i] = make_float2(ww_act(u.x, act), ww_act(u.y, act));
+              vals[P][i] = make_float2(actk_fwd(u.x, ak), actk_fwd(u.y, ak));
             }
           } else {
             float2 yv[4];
@@ -472,7 +468,7 @@ ww_wgrad_kernel(WwArgs a) {
   const T* gp = reinterpret_cast<const T*>(a.s0);
   const T* yp = reinterpret_cast<const T*>(a.s1);
   const T* xp = reinterpret_cast<const T*>(a.xin);
-  const int act = a.xf.act;
+  const ActK ak = make_actk(a.xf.act);
   const int steps = H + P;
   const int bstride = gridDim.y;
   const bool kc_mine = c_ok && x == 0;           // one 16-byte copy per 4-channel vector and kind
@@ -548,7 +544,7 @@ ww_wgrad_kernel(WwArgs a) {
         const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 16 + q * 4 + 2 * i);
         const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 16 + q * 4 + 2 * i);
         const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
-        xw[K - 1][i] = make_float2(xrow ? ww_act(u.x, act) : 0.f, xrow ? ww_act(u.y, act) : 0.f);
+        xw[K - 1][i] = make_float2(xrow ? actk_fwd(u.x, ak) : 0.f, xrow ? actk_fwd(u.y, ak) : 0.f);
         const float2 t = __ffma2_rn(al, gv[i], __ffma2_rn(be, yv[i], ga));
         gy[i] = make_float2(grow ? t.x : 0.f, grow ? t.y : 0.f);
       }

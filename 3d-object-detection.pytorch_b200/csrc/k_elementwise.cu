@@ -78,6 +78,7 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
                    float* __restrict__ stats, int HW, int C, int pix_per_block) {
   extern __shared__ float s_acc[];  // [C] when stats
   const int b = blockIdx.y;
+  const ActK ak = make_actk(xf.act);
   if (stats) {
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
@@ -96,33 +97,37 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
     if (xf.se) loadf4(xf.se + (size_t)b * C + c, se);
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
+    const size_t base = (size_t)b * HW * C + c;          // per-thread base; pixel offsets p*C fit 32 bits
+    const T* yb = y + base;
+    const T* rb = res ? res + base : nullptr;
+    T* ob = out ? out + base : nullptr;
     for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
       RawV4<T> rv[EW_U], rr[EW_U];
 #pragma unroll
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
         if (p < p1) {
-          const size_t off = ((size_t)b * HW + p) * C + c;
-          rv[u].load(y + off);
-          if (res) rr[u].load(res + off);
+          const uint32_t off = (uint32_t)p * (uint32_t)C;
+          rv[u].load(yb + off);
+          if (res) rr[u].load(rb + off);
         }
       }
 #pragma unroll
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
         if (p >= p1) continue;
-        const size_t off = ((size_t)b * HW + p) * C + c;
+        const uint32_t off = (uint32_t)p * (uint32_t)C;
         float v[4];
         rv[u].get(v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = act_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), xf.act);
+        for (int i = 0; i < 4; ++i) v[i] = actk_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), ak);
         if (res) {
           float r[4];
           rr[u].get(r);
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] += r[i];
         }
-        if (out) store4(out + off, v);
+        if (out) store4(ob + off, v);
         if (stats) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
@@ -181,6 +186,7 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
                      const T* __restrict__ addend, int HW, int C, int pix_per_block) {
   extern __shared__ float s_acc[];  // [2][C]
   const int b = blockIdx.y;
+  const ActK ak = make_actk(xf.act);
   if (stats) {
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
@@ -203,6 +209,11 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
     }
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
+    const size_t base = (size_t)b * HW * C + c;          // per-thread base; pixel offsets p*C fit 32 bits
+    const T* yb = y + base;
+    const T* gb = g_pooled ? nullptr : g + base;
+    const T* ab = addend ? addend + base : nullptr;
+    T* ub = gu + base;
     // batches of EW_U pixels: all loads of a batch are issued before the first use (memory-level parallelism)
     for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
       RawV4<T> rg[EW_U], ry[EW_U], ra[EW_U];
@@ -210,17 +221,17 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
         if (p < p1) {
-          const size_t off = ((size_t)b * HW + p) * C + c;
-          ry[u].load(y + off);
-          if (!g_pooled) rg[u].load(g + off);
-          if (addend) ra[u].load(addend + off);
+          const uint32_t off = (uint32_t)p * (uint32_t)C;
+          ry[u].load(yb + off);
+          if (!g_pooled) rg[u].load(gb + off);
+          if (addend) ra[u].load(ab + off);
         }
       }
 #pragma unroll
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
         if (p >= p1) continue;
-        const size_t off = ((size_t)b * HW + p) * C + c;
+        const uint32_t off = (uint32_t)p * (uint32_t)C;
         float gv[4], yv[4];
         ry[u].get(yv);
         if (g_pooled) {
@@ -238,9 +249,9 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float uu = se[i] * fmaf(yv[i], sc[i], sh[i]);
-          gv[i] *= act_bwd(uu, xf.act);
+          gv[i] *= actk_bwd(uu, ak);
         }
-        store4(gu + off, gv);
+        store4(ub + off, gv);
         if (stats) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -293,7 +304,7 @@ static void ew_grid(int B, int HW, int C, dim3* grid, int* pix_per_block, int nv
 
 int launch_apply_xform(const void* y, const XForm& xf, const void* res, void* out, float* pool_stats,
                        int B, int HW, int C, int dtype, cudaStream_t st) {
-  TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0, "apply_xform: bad shape B=%d HW=%d C=%d", B, HW, C);
+  TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0 && (double)HW * C < 2147483648.0, "apply_xform: bad shape B=%d HW=%d C=%d", B, HW, C);
   dim3 grid; int ppb;
   ew_grid(B, HW, C, &grid, &ppb, 4);
   size_t smem = pool_stats ? sizeof(float) * C : 0;
@@ -320,7 +331,7 @@ int launch_affine2(const void* g, const void* y, const float* alpha, const float
 
 int launch_act_bwd_stats(const void* g, const float* g_pooled, float g_scale, const void* y, const XForm& xf,
                          void* gu, float* stats, int B, int HW, int C, int dtype, cudaStream_t st, const void* addend) {
-  TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0, "act_bwd_stats: bad shape");
+  TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0 && (double)HW * C < 2147483648.0, "act_bwd_stats: bad shape");
   dim3 grid; int ppb;
   ew_grid(B, HW, C, &grid, &ppb, 4);
   size_t smem = stats ? sizeof(float) * 2 * C : 0;
