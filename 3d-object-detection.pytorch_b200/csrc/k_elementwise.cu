@@ -38,42 +38,9 @@ template <> struct RawV8<float> {
   }
 };
 
-// NV = 4 channels per thread (8-byte bf16 / 16-byte fp32 accesses).  apply_xform and act_bwd_stats keep
-// 3-6 per-channel constants, 1-2 accumulators per channel and EW_U pixels x 2-3 tensors in registers: at 8
-// channels per thread that took 98 / 128 registers = 16 resident warps per SM and 2.9 TB/s, while affine2
-// (62 registers, 32 warps) streams at 4.4-5.9 TB/s.  Halving the channels per thread halves all of it.
-template <typename T> struct RawV4;
-template <> struct RawV4<bf16> {
-  uint2 r;
-  __device__ __forceinline__ void load(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
-  __device__ __forceinline__ void get(float v[4]) const {
-    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-  }
-};
-template <> struct RawV4<float> {
-  float4 a;
-  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); }
-  __device__ __forceinline__ void get(float v[4]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
-};
-__device__ __forceinline__ void store4(float* p, const float v[4]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-__device__ __forceinline__ void store4(bf16* p, const float v[4]) {
-  uint2 raw;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-  h[0] = __floats2bfloat162_rn(v[0], v[1]);
-  h[1] = __floats2bfloat162_rn(v[2], v[3]);
-  *reinterpret_cast<uint2*>(p) = raw;
-}
-__device__ __forceinline__ void loadf4(const float* p, float v[4]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-}
-
 // out = act(se*(scale*y+shift)) (+res);  pool (optional): stats[b][0][c] += sum_pixels out
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS, 4)
+__global__ void __launch_bounds__(EW_THREADS)
 apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res, T* __restrict__ out,
                    float* __restrict__ stats, int HW, int C, int pix_per_block) {
   extern __shared__ float s_acc[];  // [C] when stats
@@ -83,18 +50,18 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
   }
-  // channel vectors beyond blockDim (C/4 > 256) are covered by an outer loop
-  for (int cv0 = 0; cv0 < (C >> 2); cv0 += blockDim.x) {
-    int CV = min((int)blockDim.x, (C >> 2) - cv0);
+  // channel vectors beyond blockDim (C/8 > 256) are covered by an outer loop
+  for (int cv0 = 0; cv0 < (C >> 3); cv0 += blockDim.x) {
+    int CV = min((int)blockDim.x, (C >> 3) - cv0);
     int PL = max(1, (int)blockDim.x / CV);
     int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
     if (pl >= PL) continue;
-    const int c = (cv0 + cv) << 2;
-    float sc[4], sh[4], se[4], acc[4];
+    const int c = (cv0 + cv) << 3;
+    float sc[8], sh[8], se[8], acc[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { sc[i] = 1.f; sh[i] = 0.f; se[i] = 1.f; acc[i] = 0.f; }
-    if (xf.scale) { loadf4(xf.scale + c, sc); loadf4(xf.shift + c, sh); }
-    if (xf.se) loadf4(xf.se + (size_t)b * C + c, se);
+    for (int i = 0; i < 8; ++i) { sc[i] = 1.f; sh[i] = 0.f; se[i] = 1.f; acc[i] = 0.f; }
+    if (xf.scale) { loadf8(xf.scale + c, sc); loadf8(xf.shift + c, sh); }
+    if (xf.se) loadf8(xf.se + (size_t)b * C + c, se);
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
     const size_t base = (size_t)b * HW * C + c;          // per-thread base; pixel offsets p*C fit 32 bits
@@ -102,7 +69,7 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
     const T* rb = res ? res + base : nullptr;
     T* ob = out ? out + base : nullptr;
     for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
-      RawV4<T> rv[EW_U], rr[EW_U];
+      RawV8<T> rv[EW_U], rr[EW_U];
 #pragma unroll
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
@@ -117,26 +84,28 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
         const int p = pb + u * PL;
         if (p >= p1) continue;
         const uint32_t off = (uint32_t)p * (uint32_t)C;
-        float v[4];
+        float v[8];
         rv[u].get(v);
+        // branch-free activation from per-kernel constants: the `act` switch cost two uniform compare+branch
+        // pairs per element (ncu: 30 % of the issued instructions)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = actk_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), ak);
+        for (int i = 0; i < 8; ++i) v[i] = actk_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), ak);
         if (res) {
-          float r[4];
+          float r[8];
           rr[u].get(r);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] += r[i];
+          for (int i = 0; i < 8; ++i) v[i] += r[i];
         }
-        if (out) store4(ob + off, v);
+        if (out) store8(ob + off, v);
         if (stats) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
+          for (int i = 0; i < 8; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
         }
       }
     }
     if (stats) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[c + i], acc[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_acc[c + i], acc[i]);
     }
   }
   if (stats) {
@@ -180,7 +149,7 @@ affine2_kernel(const T* g, const T* __restrict__ y, const float* __restrict__ al
 // gu = g * act'(u(y));  stats[b][0][c] += sum gu ; stats[b][1][c] += sum gu*y
 // g_pooled != nullptr: the incoming gradient is g_pooled[b,c] * g_scale for every pixel (avg-pool bwd)
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS, 4)
+__global__ void __launch_bounds__(EW_THREADS, 2)
 act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_scale,
                      const T* __restrict__ y, XForm xf, T* gu, float* __restrict__ stats,
                      const T* __restrict__ addend, int HW, int C, int pix_per_block) {
@@ -191,21 +160,21 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
   }
-  for (int cv0 = 0; cv0 < (C >> 2); cv0 += blockDim.x) {
-    int CV = min((int)blockDim.x, (C >> 2) - cv0);
+  for (int cv0 = 0; cv0 < (C >> 3); cv0 += blockDim.x) {
+    int CV = min((int)blockDim.x, (C >> 3) - cv0);
     int PL = max(1, (int)blockDim.x / CV);
     int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
     if (pl >= PL) continue;
-    const int c = (cv0 + cv) << 2;
-    float sc[4], sh[4], se[4], a1[4], a2[4], gp[4];
+    const int c = (cv0 + cv) << 3;
+    float sc[8], sh[8], se[8], a1[8], a2[8], gp[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { sc[i] = 1.f; sh[i] = 0.f; se[i] = 1.f; a1[i] = 0.f; a2[i] = 0.f; gp[i] = 0.f; }
-    if (xf.scale) { loadf4(xf.scale + c, sc); loadf4(xf.shift + c, sh); }
-    if (xf.se) loadf4(xf.se + (size_t)b * C + c, se);
+    for (int i = 0; i < 8; ++i) { sc[i] = 1.f; sh[i] = 0.f; se[i] = 1.f; a1[i] = 0.f; a2[i] = 0.f; gp[i] = 0.f; }
+    if (xf.scale) { loadf8(xf.scale + c, sc); loadf8(xf.shift + c, sh); }
+    if (xf.se) loadf8(xf.se + (size_t)b * C + c, se);
     if (g_pooled) {
-      loadf4(g_pooled + (size_t)b * C + c, gp);
+      loadf8(g_pooled + (size_t)b * C + c, gp);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) gp[i] *= g_scale;
+      for (int i = 0; i < 8; ++i) gp[i] *= g_scale;
     }
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
@@ -216,7 +185,7 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
     T* ub = gu + base;
     // batches of EW_U pixels: all loads of a batch are issued before the first use (memory-level parallelism)
     for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
-      RawV4<T> rg[EW_U], ry[EW_U], ra[EW_U];
+      RawV8<T> rg[EW_U], ry[EW_U], ra[EW_U];
 #pragma unroll
       for (int u = 0; u < EW_U; ++u) {
         const int p = pb + u * PL;
@@ -232,39 +201,37 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
         const int p = pb + u * PL;
         if (p >= p1) continue;
         const uint32_t off = (uint32_t)p * (uint32_t)C;
-        float gv[4], yv[4];
+        float gv[8], yv[8];
         ry[u].get(yv);
         if (g_pooled) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gv[i] = gp[i];
+          for (int i = 0; i < 8; ++i) gv[i] = gp[i];
         } else {
           rg[u].get(gv);
         }
         if (addend) {
-          float ad[4];
+          float ad[8];
           ra[u].get(ad);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gv[i] += ad[i];
+          for (int i = 0; i < 8; ++i) gv[i] += ad[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float uu = se[i] * fmaf(yv[i], sc[i], sh[i]);
           gv[i] *= actk_bwd(uu, ak);
         }
-        store4(ub + off, gv);
-        if (stats) {
+        store8(ub + off, gv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float r = to_f(from_f<T>(gv[i]));      // statistics of the stored (rounded) gradient
-            a1[i] += r;
-            a2[i] = fmaf(r, yv[i], a2[i]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float r = to_f(from_f<T>(gv[i]));      // statistics of the stored (rounded) gradient
+          a1[i] += r;
+          a2[i] = fmaf(r, yv[i], a2[i]);
         }
       }
     }
     if (stats) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         atomicAdd(&s_acc[c + i], a1[i]);
         atomicAdd(&s_acc[C + c + i], a2[i]);
       }
@@ -289,8 +256,8 @@ __global__ void pool_finalize_kernel(const float* __restrict__ stats, float scal
 
 // Pixels per block: long per-thread pixel loops amortise the per-block reduction (shared + global
 // atomics per channel), but the grid must still fill the machine (>= ~4 blocks per SM).
-static void ew_grid(int B, int HW, int C, dim3* grid, int* pix_per_block, int nv = 8) {
-  int CV = C / nv;
+static void ew_grid(int B, int HW, int C, dim3* grid, int* pix_per_block) {
+  int CV = C >> 3;
   if (CV > EW_THREADS) CV = EW_THREADS;
   int PL = EW_THREADS / CV;
   if (PL < 1) PL = 1;
@@ -306,7 +273,7 @@ int launch_apply_xform(const void* y, const XForm& xf, const void* res, void* ou
                        int B, int HW, int C, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0 && (double)HW * C < 2147483648.0, "apply_xform: bad shape B=%d HW=%d C=%d", B, HW, C);
   dim3 grid; int ppb;
-  ew_grid(B, HW, C, &grid, &ppb, 4);
+  ew_grid(B, HW, C, &grid, &ppb);
   size_t smem = pool_stats ? sizeof(float) * C : 0;
   if (dtype == TD3D_BF16)
     apply_xform_kernel<bf16><<<grid, EW_THREADS, smem, st>>>((const bf16*)y, xf, (const bf16*)res, (bf16*)out, pool_stats, HW, C, ppb);
@@ -333,7 +300,7 @@ int launch_act_bwd_stats(const void* g, const float* g_pooled, float g_scale, co
                          void* gu, float* stats, int B, int HW, int C, int dtype, cudaStream_t st, const void* addend) {
   TD3D_REQUIRE(C % 8 == 0 && B > 0 && HW > 0 && (double)HW * C < 2147483648.0, "act_bwd_stats: bad shape");
   dim3 grid; int ppb;
-  ew_grid(B, HW, C, &grid, &ppb, 4);
+  ew_grid(B, HW, C, &grid, &ppb);
   size_t smem = stats ? sizeof(float) * 2 * C : 0;
   if (dtype == TD3D_BF16)
     act_bwd_stats_kernel<bf16><<<grid, EW_THREADS, smem, st>>>((const bf16*)g, g_pooled, g_scale, (const bf16*)y, xf, (bf16*)gu, stats, (const bf16*)addend, HW, C, ppb);

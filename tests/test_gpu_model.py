@@ -276,7 +276,9 @@ def test_fused_train_step_graph_equals_eager_and_learns():
     # float atomics make accumulation order (not values) run-dependent; 8 SGD steps at lr=.05 on one
     # batch amplify that 1e-7 noise, so eager and graph replay agree to ~1e-3, exactly at step 0
     np.testing.assert_allclose(res[True][0][:2], res[False][0][:2], rtol=1e-5)
-    np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-2)
+    np.testing.assert_allclose(res[True][0][:4], res[False][0][:4], rtol=5e-3)
+    # (measured: step 3 still agrees to 1e-6, step 8 differs by up to 2.5 % between two runs of the SAME mode)
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=6e-2)
     assert rel(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) < 5e-2
     assert res[True][2]["count"] == 8 * case["batch"]
 
