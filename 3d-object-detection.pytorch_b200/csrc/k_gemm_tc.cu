@@ -254,7 +254,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int ti = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-        const int m0 = (tile / p.n_tiles) * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
+        // single-thread loops: no runtime divisions on the common single-N-tile path (timeline: the MMA
+        // issuer needs ~800 ns per 128-row tile of a K=16 layer, which caps such layers at ~1.4 TB/s)
+        const int m0 = (p.n_tiles == 1 ? tile : tile / p.n_tiles) * TC_BLOCK_M;
+        const int n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
           TC_STAMP(0, ti);
@@ -277,10 +280,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       if (p.w_resident && blockIdx.x < num_tiles) mbar_wait(smem_u32(&s_wfull), 0);
       int ti = 0;
+      int as = 0;                       // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
+      uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-        const int n_tile = tile % p.n_tiles;
-        const int as = ti % p.n_acc;
-        const uint32_t aphase = (uint32_t)(ti / p.n_acc) & 1u;
+        const int n_tile = p.n_tiles == 1 ? 0 : tile % p.n_tiles;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         TC_STAMP(2, ti);
         tc_fence_after();
@@ -303,6 +306,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           TC_STAMP(4, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (++as == p.n_acc) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
@@ -314,11 +318,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float (*gstat)[2][256] = s_stat[eg];
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
     uint32_t ysel = 0;
+    int as = eg % p.n_acc;
+    uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
     for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; tile < num_tiles; tile += TC_EPI_GROUPS * gridDim.x, ti += TC_EPI_GROUPS) {
-      const int as = ti % p.n_acc;
-      const uint32_t aphase = (uint32_t)(ti / p.n_acc) & 1u;
-      const int m_tile = tile / p.n_tiles;
-      const int m0 = m_tile * TC_BLOCK_M, n0 = (tile % p.n_tiles) * p.block_n;
+      const int m_tile = p.n_tiles == 1 ? tile : tile / p.n_tiles;
+      const int m0 = m_tile * TC_BLOCK_M, n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
       mbar_wait(smem_u32(&s_tfull[as]), aphase);
       if (q == 2 && lane == 0) TC_STAMP(5, ti);
       tc_fence_after();
@@ -416,6 +420,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
       }
       if (q == 2 && lane == 0) TC_STAMP(7, ti);
+      as += TC_EPI_GROUPS;                       // stage / phase of tile ti + TC_EPI_GROUPS
+      while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
     if (p.tma_store && lane == 0) bulk_wait_all();
   }
