@@ -175,7 +175,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // ------------------------------------------------------------------------------------------------
 static const int TC_THREADS = 192;          // 6 warps (TN kernel)
 static const int TC_EPI_GROUPS = 3;         // NT kernel: independent 4-warp epilogue groups (one warp per TMEM lane quarter)
-static const int TC_NT_THREADS = 64 + TC_EPI_GROUPS * 128;
+static const int TC_MMA_WARPS = 2;          // NT kernel: MMA issuer warps, tile ti is issued by warp 1 + ti % TC_MMA_WARPS
+static const int TC_NT_THREADS = 32 * (1 + TC_MMA_WARPS) + TC_EPI_GROUPS * 128;
 static const int TC_MAX_ACC = 8;            // TMEM accumulator stages
 static const int TC_BLOCK_M = 128;
 static const int TC_MAX_STAGES = 12;
@@ -271,18 +272,26 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
+  } else if (warp <= TC_MMA_WARPS) {
+    // ===================== MMA issuers (one elected thread per warp) =====================
+    // Timeline (TD3D_TC_DBG=32): one thread needs ~650 ns per tile for wait / descriptors / tcgen05.mma /
+    // 2 x tcgen05.commit, which capped K=16 layers at ~1.7 TB/s.  The tiles are therefore dealt round-robin to
+    // TC_MMA_WARPS issuer warps; every tile has its own smem stages and TMEM accumulator stage, and a
+    // tcgen05.commit tracks the MMAs of its own thread, so the issuers never have to talk to each other.
     if (lane == 0) {
+      const int mw = warp - 1;
       const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)p.block_n, 0, 0);
       const uint32_t layout_type = p.swizzle_bytes == 128 ? 2u : (p.swizzle_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
       int stage = 0; uint32_t phase = 0;
+      // smem stages / accumulator stage of this warp's first tile (ti = mw)
+      for (int i = 0; i < mw * k_blocks; ++i)
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       if (p.w_resident && blockIdx.x < num_tiles) mbar_wait(smem_u32(&s_wfull), 0);
-      int ti = 0;
-      int as = 0;                       // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      int ti = mw;
+      int as = mw % p.n_acc;            // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
+      uint32_t aphase = (uint32_t)(mw / p.n_acc) & 1u;
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < num_tiles; tile += TC_MMA_WARPS * gridDim.x, ti += TC_MMA_WARPS) {
         const int n_tile = p.n_tiles == 1 ? 0 : tile % p.n_tiles;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         TC_STAMP(2, ti);
@@ -306,14 +315,17 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           TC_STAMP(4, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (++as == p.n_acc) { as = 0; aphase ^= 1u; }
+        for (int i = 0; i < (TC_MMA_WARPS - 1) * k_blocks; ++i)      // skip the stages of the other issuers' tiles
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        as += TC_MMA_WARPS;
+        while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int eg = (warp - 2) >> 2;         // epilogue group
-    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the epilogue group
+    const int eg = (warp - 1 - TC_MMA_WARPS) >> 2;         // epilogue group (any 4 consecutive warps cover the 4 quarters)
+    const int et = (threadIdx.x - 32 * (1 + TC_MMA_WARPS)) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
