@@ -199,6 +199,8 @@ struct TcNtParams {
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
   int tma_store;        // 1: bf16 output leaves through swizzled smem + cp.async.bulk.tensor (coalesced), else st.global
+  int mma_warps;        // 1 or 2 MMA issuer warps (2 only when a tile's k blocks of both issuers fit the smem ring at once:
+                        // a parity wait must never be more than one phase away from its barrier)
   int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
                         // 4 no shared atomics, 8 no global reductions, 16 no TMEM load
 };
@@ -278,8 +280,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // 2 x tcgen05.commit, which capped K=16 layers at ~1.7 TB/s.  The tiles are therefore dealt round-robin to
     // TC_MMA_WARPS issuer warps; every tile has its own smem stages and TMEM accumulator stage, and a
     // tcgen05.commit tracks the MMAs of its own thread, so the issuers never have to talk to each other.
-    if (lane == 0) {
-      const int mw = warp - 1;
+    const int mw = warp - 1;
+    if (lane == 0 && mw < p.mma_warps) {
       const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)p.block_n, 0, 0);
       const uint32_t layout_type = p.swizzle_bytes == 128 ? 2u : (p.swizzle_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
@@ -291,7 +293,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int ti = mw;
       int as = mw % p.n_acc;            // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
       uint32_t aphase = (uint32_t)(mw / p.n_acc) & 1u;
-      for (int tile = blockIdx.x + mw * gridDim.x; tile < num_tiles; tile += TC_MMA_WARPS * gridDim.x, ti += TC_MMA_WARPS) {
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < num_tiles; tile += p.mma_warps * gridDim.x, ti += p.mma_warps) {
         const int n_tile = p.n_tiles == 1 ? 0 : tile % p.n_tiles;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         TC_STAMP(2, ti);
@@ -315,9 +317,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           TC_STAMP(4, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        for (int i = 0; i < (TC_MMA_WARPS - 1) * k_blocks; ++i)      // skip the stages of the other issuers' tiles
+        for (int i = 0; i < (p.mma_warps - 1) * k_blocks; ++i)      // skip the stages of the other issuer's tiles
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        as += TC_MMA_WARPS;
+        as += p.mma_warps;
         while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
       }
     }
@@ -656,6 +658,9 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
   p.dbg = env_int("TD3D_TC_DBG", 0);
+  // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
+  // costs the statistics epilogue 4-8 % of its issue slots -> only without statistics
+  p.mma_warps = (!g.stats && TC_MMA_WARPS * k_blocks <= p.stages && !env_int("TD3D_TC_ONE_ISSUER", 0)) ? TC_MMA_WARPS : 1;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
