@@ -146,6 +146,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
+    ap.add_argument("--skip-infer", action="store_true")
+    ap.add_argument("--infer-batch", type=int, default=2048,
+                    help="inference leg batch (BASELINE configs[3] says 4096; the depthwise kernels use 32-bit element offsets, "
+                         "which caps the widest layer at 2048 crops per launch)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch profile (kind, layer tag, ms, GB/s) as CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -336,6 +340,35 @@ def main():
         cpu = {"value": cb / sec, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"2 steps x {cb} crops of the same {MODEL} train step, fp32, oracle/torch_port.py"}
 
+    # ---- inference leg (BASELINE configs[3]): eval-mode forward with folded running statistics, all nine heads + argmax select
+    infer = None
+    if rank == 0 and world == 1 and not args.skip_infer:
+        try:
+            del step
+            torch.cuda.empty_cache()
+            IB = args.infer_batch
+            m2 = build_model(cfg)
+            m2.load_state_dict(tp.synth_state(MODEL, seed=0))
+            m2 = m2.to(dev).eval()
+            xi = torch.rand(IB, 3, RES, RES, device=dev)          # 1.2 GB at 2048 crops: far beyond the 126 MB L2
+            for _ in range(3):
+                m2.forward_to_onnx(xi, select=True)
+            torch.cuda.synchronize(dev)
+            n_it = 10
+            e0.record()
+            for _ in range(n_it):
+                m2.forward_to_onnx(xi, select=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ims = e0.elapsed_time(e1) / n_it
+            fwd_bytes = algorithmic_bytes_per_crop(esz) / 3.0     # forward = s(I+O) = one third of the train figure
+            infer = {"value": IB / (ims / 1e3), "unit": "crops/s", "batch": IB, "ms_per_batch": ims,
+                     "workload": f"{MODEL} eval forward (running-stat BN), 9 heads + argmax select, {args.dtype}, inputs resident in HBM",
+                     "roofline_frac": (fwd_bytes * IB / (peak * 1e9) * 1e3) / ims}
+            del m2, xi
+        except Exception as ex:          # never lose the train line over the extra leg
+            infer = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -354,6 +387,7 @@ def main():
                               "frac": step_roof_ms / ms_step, "peak_gbs": peak, "peak_source": peak_src},
             "kernel_kinds": kinds,
             "cpu_baseline": cpu,
+            "infer": infer,
             "final_loss": loss_now,
         }
         print(json.dumps(line))
