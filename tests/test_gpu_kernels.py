@@ -122,6 +122,15 @@ def test_depthwise(code, k, stride, shape):
     torch.testing.assert_close(bst[:, 1], (gxf * x.float()).sum(dim=(1, 2)), rtol=1e-4, atol=5e-2)
 
 
+# row-walker edge cases (k_dww.cu): rows that fill all lanes of their segment (shuffle wrap needs the select path),
+# single-row planes, channel spans that end inside a warp, more samples than sample lanes in the grid
+@pytest.mark.parametrize("code", CODES)
+@pytest.mark.parametrize("k", [3, 5])
+@pytest.mark.parametrize("shape", [(5, 8, 8, 40), (3, 32, 32, 24), (2, 1, 5, 16), (9, 16, 16, 8), (300, 7, 7, 24), (2, 3, 31, 48)])
+def test_depthwise_walker_edges(code, k, shape):
+    test_depthwise(code, k, 1, shape)
+
+
 GEMM_SHAPES = [(300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (5000, 16, 64),
                (130, 200, 80), (128, 184, 80), (77, 40, 120)]
 
