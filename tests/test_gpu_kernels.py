@@ -93,7 +93,7 @@ def test_stem(code, hw):
 @pytest.mark.parametrize("code", CODES)
 @pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1), (5, 2)])
 @pytest.mark.parametrize("shape", [(2, 14, 14, 240), (3, 7, 7, 96), (2, 29, 23, 16), (1, 56, 56, 72)])
-def test_depthwise(code, k, stride, shape):
+def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
     B, H, W, Cn = shape
     act = L.ACT_HSWISH
     x = (torch.randn(shape, device=DEV) * 2).to(K.dt(code))
@@ -115,7 +115,7 @@ def test_depthwise(code, k, stride, shape):
     gx, dw, bst = K.dw_bwd(g, y, alpha, beta, gamma, x, scale, shift, se, act, taps, k, stride, code)
     gy = alpha[:, None, None] * g.float() + beta * yf + gamma[:, None, None]
     ref.backward(gy.permute(0, 3, 1, 2))
-    assert rel_err(gx.float(), xt.grad) < (2e-5 if code == L.F32 else 1e-2)
+    assert rel_err(gx.float(), xt.grad) < (2e-5 if code == L.F32 else gx_tol_bf16)
     assert rel_err(dw, wr.grad) < (2e-4 if code == L.F32 else 2e-2)
     gxf = gx.float()
     torch.testing.assert_close(bst[:, 0], gxf.sum(dim=(1, 2)), rtol=1e-4, atol=2e-2)
@@ -128,7 +128,9 @@ def test_depthwise(code, k, stride, shape):
 @pytest.mark.parametrize("k", [3, 5])
 @pytest.mark.parametrize("shape", [(5, 8, 8, 40), (3, 32, 32, 24), (2, 1, 5, 16), (9, 16, 16, 8), (300, 7, 7, 24), (2, 3, 31, 48)])
 def test_depthwise_walker_edges(code, k, shape):
-    test_depthwise(code, k, 1, shape)
+    # bf16: h_swish' jumps at |u| = 3, and u is evaluated from bf16-rounded operands in a different FMA order than the
+    # fp32 reference, so the larger planes see a few flipped elements (measured 1.5e-2 on 3x32x32x24; fp32 stays < 2e-5)
+    test_depthwise(code, k, 1, shape, gx_tol_bf16=3e-2)
 
 
 GEMM_SHAPES = [(300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (5000, 16, 64),
