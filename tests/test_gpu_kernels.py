@@ -115,7 +115,10 @@ def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
     gx, dw, bst = K.dw_bwd(g, y, alpha, beta, gamma, x, scale, shift, se, act, taps, k, stride, code)
     gy = alpha[:, None, None] * g.float() + beta * yf + gamma[:, None, None]
     ref.backward(gy.permute(0, 3, 1, 2))
-    assert rel_err(gx.float(), xt.grad) < (2e-5 if code == L.F32 else gx_tol_bf16)
+    # h_swish' jumps at |u| = 3: an element whose pre-activation lies within rounding of the jump legitimately takes either
+    # branch (seed 0 puts one at u = 3 - 1ulp for channel 5), so those elements are left out of the comparison
+    safe = ((xt.detach().abs() - 3.0).abs() > 1e-4).float()
+    assert rel_err(gx.float() * safe, xt.grad * safe) < (2e-5 if code == L.F32 else gx_tol_bf16)
     assert rel_err(dw, wr.grad) < (2e-4 if code == L.F32 else 2e-2)
     gxf = gx.float()
     torch.testing.assert_close(bst[:, 0], gxf.sum(dim=(1, 2)), rtol=1e-4, atol=2e-2)
@@ -128,9 +131,7 @@ def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
 @pytest.mark.parametrize("k", [3, 5])
 @pytest.mark.parametrize("shape", [(5, 8, 8, 40), (3, 32, 32, 24), (2, 1, 5, 16), (9, 16, 16, 8), (300, 7, 7, 24), (2, 3, 31, 48)])
 def test_depthwise_walker_edges(code, k, shape):
-    # bf16: h_swish' jumps at |u| = 3, and u is evaluated from bf16-rounded operands in a different FMA order than the
-    # fp32 reference, so the larger planes see a few flipped elements (measured 1.5e-2 on 3x32x32x24; fp32 stays < 2e-5)
-    test_depthwise(code, k, 1, shape, gx_tol_bf16=3e-2)
+    test_depthwise(code, k, 1, shape)
 
 
 GEMM_SHAPES = [(300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (5000, 16, 64),
