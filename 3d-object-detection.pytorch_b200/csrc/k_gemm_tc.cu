@@ -659,8 +659,11 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
   p.dbg = env_int("TD3D_TC_DBG", 0);
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
-  // costs the statistics epilogue 4-8 % of its issue slots -> only without statistics
-  p.mma_warps = (!g.stats && TC_MMA_WARPS * k_blocks <= p.stages && !env_int("TD3D_TC_ONE_ISSUER", 0)) ? TC_MMA_WARPS : 1;
+  // costs the statistics epilogue 4-8 % of its issue slots, and with two issuers the accumulator stages are no longer
+  // committed in tile order: an epilogue group that runs >= 5 tiles ahead of the slower issuer could see the parity of
+  // a stage's previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the
+  // second issuer is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
+  p.mma_warps = (env_int("TD3D_TC_TWO_ISSUERS", 0) && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
