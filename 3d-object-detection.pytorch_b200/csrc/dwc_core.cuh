@@ -1,0 +1,401 @@
+// Depthwise k x k convolution BACKWARD in ONE pass ("column walker"), NHWC.
+// Reference op: autograd backward of nn.Conv2d(hidden, hidden, k, s, (k-1)//2, groups=hidden) inside
+// InvertedResidual (torchdet3d/models/mobilenetv3.py:136,152), fused with the BatchNorm-backward affine of the
+// incoming gradient and the activation backward of the layer's input:
+//
+//   gy  = alpha[b,c]*g + beta[c]*y_out + gamma[b,c]                  (zero outside the output plane)
+//   t   = se[b,c]*(scale[c]*x + shift[c]);  xa = act(t)
+//   gx  = act'(t) * sum_{i,j} w[i][j] * gy[(q + pad - (i,j)) / s]    (data gradient, written once)
+//   dW[c][i][j] += sum_q xa[q] * gy[(q + pad - (i,j)) / s]           (weight gradient)
+//   stats += (sum gx, sum gx*x)                                       (BatchNorm backward of the producer of x)
+//
+// Round 1 ran this as two kernels (data / weight gradient) that each re-read g, y_out and x: 1.66x the algorithmic
+// DRAM bytes and ~40 thread-instructions per element.  Here every thread owns CPT adjacent channels (lanes of a warp
+// are channel-contiguous: a warp request is one 128-byte line) and a band of R output rows (R*S input rows) of one
+// sample, and WALKS THE COLUMNS of the plane: the gradient window (R+lo+hi rows x 1+lo+hi columns) slides in
+// registers, the k*k taps and the k*k weight-gradient accumulators stay in registers for the thread's whole life
+// (it loops over many (sample, band) items), g / y_out / x are each loaded once per band (halo rows come from
+// L1/L2), and no shared memory or barrier is used in the main loop.
+//
+// The per-thread body is __host__ __device__ so tests/host/dwc_emul.cu can run the exact index logic on the CPU.
+#pragma once
+#include <string.h>
+
+#include "td3d_common.cuh"
+
+namespace td3d {
+
+struct DwcArgs {
+  const void* g; const void* y_out;          // [B,Ho,Wo,C]
+  const float* alpha; const float* beta; const float* gamma;   // [B,C], [C], [B,C]
+  const void* x;                              // [B,H,W,C] raw forward input
+  const float* scale; const float* shift;     // [C] or null (identity)
+  const float* se;                            // [B,C] or null
+  int act;
+  const float* w_taps;                        // [K*K][C]
+  void* gx;                                   // [B,H,W,C]
+  float* stats;                               // [slots][2][C] or null (only the sum over slots is meaningful)
+  float* dw;                                  // [C][K*K] (+=)
+  int B, H, W, C, Ho, Wo;
+  int slots;
+  int n_bands, n_items, item_lanes;           // items = B * n_bands; lane il handles items il, il + item_lanes, ...
+  int cw;                                     // channel groups (of CPT channels) per block column chunk
+  int n_cchunks;                              // ceil((C / CPT) / cw)
+  int ilb;                                    // item lanes per block
+  int pf_dist;                                // L2 prefetch distance in walk steps (0 = off)
+};
+
+// ---- CPT-wide fp32 vectors -------------------------------------------------------------------------------------
+template <int CPT> struct DwcVec;
+template <> struct DwcVec<2> { typedef float2 V; };
+template <> struct DwcVec<1> { typedef float V; };
+
+__host__ __device__ __forceinline__ float2 dv_fma(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(a.x * b.x + c.x, a.y * b.y + c.y);
+#endif
+}
+__host__ __device__ __forceinline__ float dv_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return fmaf(a, b, c);
+#else
+  return a * b + c;
+#endif
+}
+__host__ __device__ __forceinline__ float2 dv_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__host__ __device__ __forceinline__ float dv_mul(float a, float b) { return a * b; }
+__host__ __device__ __forceinline__ float2 dv_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float dv_add(float a, float b) { return a + b; }
+__host__ __device__ __forceinline__ void dv_set(float2& v, float s) { v = make_float2(s, s); }
+__host__ __device__ __forceinline__ void dv_set(float& v, float s) { v = s; }
+__host__ __device__ __forceinline__ float dv_get(const float2& v, int i) { return i ? v.y : v.x; }
+__host__ __device__ __forceinline__ float dv_get(const float& v, int) { return v; }
+
+// activation constants: act(u) = u * sat(a*u + b);  act'(u) = u <= lo ? 0 : (u >= hi ? 1 : da*u + db)
+struct DwcAct { float a, b, da, db, lo, hi; };
+__host__ __device__ inline DwcAct dwc_make_act(int act) {
+  DwcAct k;
+  const bool hs = act == TD3D_ACT_HSWISH, re = act == TD3D_ACT_RELU;
+  k.a = hs ? (1.f / 6.f) : (re ? 1.2676506e30f : 0.f);
+  k.b = hs ? 0.5f : (re ? 0.f : 1.f);
+  k.da = hs ? (1.f / 3.f) : 0.f;
+  k.db = hs ? 0.5f : 1.f;
+  k.lo = hs ? -3.f : (re ? 0.f : -3.0e38f);
+  k.hi = hs ? 3.f : 3.0e38f;
+  return k;
+}
+__host__ __device__ __forceinline__ float dwc_sat(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
+__host__ __device__ __forceinline__ float dwc_act1(float u, const DwcAct& k) { return u * dwc_sat(u * k.a + k.b); }
+__host__ __device__ __forceinline__ float dwc_actd1(float u, const DwcAct& k) {
+  float d = u * k.da + k.db;
+  d = u >= k.hi ? 1.f : d;
+  return u <= k.lo ? 0.f : d;
+}
+__host__ __device__ __forceinline__ float2 dwc_act(float2 u, const DwcAct& k) { return make_float2(dwc_act1(u.x, k), dwc_act1(u.y, k)); }
+__host__ __device__ __forceinline__ float dwc_act(float u, const DwcAct& k) { return dwc_act1(u, k); }
+__host__ __device__ __forceinline__ float2 dwc_actd(float2 u, const DwcAct& k) { return make_float2(dwc_actd1(u.x, k), dwc_actd1(u.y, k)); }
+__host__ __device__ __forceinline__ float dwc_actd(float u, const DwcAct& k) { return dwc_actd1(u, k); }
+
+// ---- raw loads / stores of CPT channels in the activation dtype ----------------------------------------------
+template <typename T, int CPT> struct DwcIo;
+template <> struct DwcIo<bf16, 2> {
+  typedef uint32_t Raw;
+  static __host__ __device__ __forceinline__ Raw zero() { return 0u; }
+  static __host__ __device__ __forceinline__ Raw ld(const bf16* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const unsigned int*>(p));
+#else
+    return *reinterpret_cast<const uint32_t*>(p);
+#endif
+  }
+  static __host__ __device__ __forceinline__ float2 cvt(Raw r) {
+#ifdef __CUDA_ARCH__
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+#else
+    uint32_t lo = r << 16, hi = r & 0xffff0000u;
+    float2 v;
+    memcpy(&v.x, &lo, 4); memcpy(&v.y, &hi, 4);
+    return v;
+#endif
+  }
+  // stores v rounded to bf16 (RNE) and returns the rounded values
+  static __host__ __device__ __forceinline__ float2 st(bf16* p, float2 v) {
+#ifdef __CUDA_ARCH__
+    __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(p) = h;
+    return __bfloat1622float2(h);
+#else
+    p[0] = __float2bfloat16_rn(v.x); p[1] = __float2bfloat16_rn(v.y);
+    return make_float2(__bfloat162float(p[0]), __bfloat162float(p[1]));
+#endif
+  }
+};
+template <> struct DwcIo<bf16, 1> {
+  typedef uint16_t Raw;
+  static __host__ __device__ __forceinline__ Raw zero() { return 0; }
+  static __host__ __device__ __forceinline__ Raw ld(const bf16* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const unsigned short*>(p));
+#else
+    return *reinterpret_cast<const uint16_t*>(p);
+#endif
+  }
+  static __host__ __device__ __forceinline__ float cvt(Raw r) {
+    uint32_t u = (uint32_t)r << 16;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+  }
+  static __host__ __device__ __forceinline__ float st(bf16* p, float v) {
+    bf16 h = __float2bfloat16_rn(v);
+    *p = h;
+    return __bfloat162float(h);
+  }
+};
+template <> struct DwcIo<float, 2> {
+  typedef float2 Raw;
+  static __host__ __device__ __forceinline__ Raw zero() { return make_float2(0.f, 0.f); }
+  static __host__ __device__ __forceinline__ Raw ld(const float* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const float2*>(p));
+#else
+    return *reinterpret_cast<const float2*>(p);
+#endif
+  }
+  static __host__ __device__ __forceinline__ float2 cvt(Raw r) { return r; }
+  static __host__ __device__ __forceinline__ float2 st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; return v; }
+};
+template <> struct DwcIo<float, 1> {
+  typedef float Raw;
+  static __host__ __device__ __forceinline__ Raw zero() { return 0.f; }
+  static __host__ __device__ __forceinline__ Raw ld(const float* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+  }
+  static __host__ __device__ __forceinline__ float cvt(Raw r) { return r; }
+  static __host__ __device__ __forceinline__ float st(float* p, float v) { *p = v; return v; }
+};
+
+template <int CPT> __host__ __device__ __forceinline__ typename DwcVec<CPT>::V dwc_ldc(const float* p);
+template <> __host__ __device__ __forceinline__ float2 dwc_ldc<2>(const float* p) { return make_float2(p[0], p[1]); }
+template <> __host__ __device__ __forceinline__ float dwc_ldc<1>(const float* p) { return p[0]; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One thread's whole life.  `c` = first of its CPT channels, `il` = item lane.  `Sink` receives the final sums:
+//   sink.dw(c + i, tap, value), sink.stat(which, c + i, value)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int K, int S, int R, int CPT>
+struct DwcBwd {
+  typedef typename DwcVec<CPT>::V V;
+  typedef DwcIo<T, CPT> Io;
+  typedef typename Io::Raw Raw;
+  static constexpr int PAD = (K - 1) / 2;
+  static constexpr int LO = PAD / S;                 // gradient halo (rows / columns) before the band
+  static constexpr int HI = (S - 1 + PAD) / S;       // ... after it
+  static constexpr int NA = R + LO + HI;             // gradient window rows
+  static constexpr int NB = 1 + LO + HI;             // gradient window columns
+  static constexpr int RI = R * S;                   // input rows of a band
+
+  struct State {
+    V G[NA][NB];        // gradient window; column slot (wb + phase) % NB holds gy column px - LO + wb
+    V wt[K * K];        // taps
+    V dwa[K * K];       // weight-gradient accumulators
+    V s1, s2;           // sum gx, sum gx * x
+    Raw rg[NA], ry[NA]; // prefetched raw gradient column
+    Raw rx[RI][S];      // prefetched raw input pixels of the next step
+  };
+
+  // prefetch the raw data step `px` needs: gradient column px + HI, input columns S*px .. S*px + S-1
+  static __host__ __device__ __forceinline__ void prefetch(State& st, const DwcArgs& a, const T* gb, const T* yb,
+                                                           const T* xb, int r0, int px, bool pf_lane) {
+    const int cg = px + HI;
+    const bool col_ok = cg >= 0 && cg < a.Wo;
+#pragma unroll
+    for (int ar = 0; ar < NA; ++ar) {
+      const int py = r0 + ar - LO;
+      const bool ok = col_ok && py >= 0 && py < a.Ho;
+      st.rg[ar] = Io::zero(); st.ry[ar] = Io::zero();
+      if (ok) {
+        const size_t off = ((size_t)py * a.Wo + cg) * a.C;
+        st.rg[ar] = Io::ld(gb + off);
+        st.ry[ar] = Io::ld(yb + off);
+      }
+    }
+    if (px >= 0) {
+#pragma unroll
+      for (int ey = 0; ey < RI; ++ey) {
+        const int qy = S * r0 + ey;
+#pragma unroll
+        for (int ex = 0; ex < S; ++ex) {
+          const int qx = S * px + ex;
+          st.rx[ey][ex] = Io::zero();
+          if (qy < a.H && qx < a.W) st.rx[ey][ex] = Io::ld(xb + ((size_t)qy * a.W + qx) * a.C);
+        }
+      }
+    }
+#ifdef __CUDA_ARCH__
+    // The register prefetch above runs one step ahead (a few hundred ns): too short for a DRAM round trip.  One lane
+    // per 128-byte line therefore asks L2 for the lines `pf_dist` steps further along the walk; they cost no registers.
+    if (pf_lane) {
+      const int cg2 = cg + a.pf_dist;
+      if (cg2 < a.Wo) {
+#pragma unroll
+        for (int ar = 0; ar < NA; ++ar) {
+          const int py = r0 + ar - LO;
+          if (py >= 0 && py < a.Ho) {
+            const size_t off = ((size_t)py * a.Wo + cg2) * a.C;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gb + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + off));
+          }
+        }
+      }
+      const int qx2 = S * (px + a.pf_dist);
+      if (qx2 < a.W) {
+#pragma unroll
+        for (int ey = 0; ey < RI; ++ey) {
+          const int qy = S * r0 + ey;
+          if (qy < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + ((size_t)qy * a.W + qx2) * a.C));
+        }
+      }
+    }
+#endif
+  }
+
+  template <int PH>
+  static __host__ __device__ __forceinline__ void step(State& st, const DwcArgs& a, const T* gb, const T* yb, const T* xb,
+                                                       T* ob, int r0, int px, V al, V be, V ga, V sc, V sh, V se,
+                                                       const DwcAct& ak, bool want_stats, bool pf_lane) {
+    // 1. the prefetched gradient column enters the window (slot of column px + HI)
+    constexpr int SLOT_NEW = (NB - 1 + PH) % NB;
+    {
+      const int cg = px + HI;
+      const bool col_ok = cg >= 0 && cg < a.Wo;
+#pragma unroll
+      for (int ar = 0; ar < NA; ++ar) {
+        const int py = r0 + ar - LO;
+        const bool ok = col_ok && py >= 0 && py < a.Ho;
+        V v = dv_fma(al, Io::cvt(st.rg[ar]), dv_fma(be, Io::cvt(st.ry[ar]), ga));
+        if (!ok) dv_set(v, 0.f);
+        st.G[ar][SLOT_NEW] = v;
+      }
+    }
+    V xv[RI][S];
+#pragma unroll
+    for (int ey = 0; ey < RI; ++ey)
+#pragma unroll
+      for (int ex = 0; ex < S; ++ex) xv[ey][ex] = Io::cvt(st.rx[ey][ex]);
+    // 2. next step's loads go out before this step's math
+    prefetch(st, a, gb, yb, xb, r0, px + 1, pf_lane);
+    if (px < 0) return;
+    // 3. every input pixel of this step: S*r0 + ey, S*px + ex
+#pragma unroll
+    for (int ey = 0; ey < RI; ++ey) {
+      const int qy = S * r0 + ey;
+      if (qy >= a.H) continue;
+#pragma unroll
+      for (int ex = 0; ex < S; ++ex) {
+        const int qx = S * px + ex;
+        if (qx >= a.W) continue;
+        const V xr = xv[ey][ex];
+        const V t = dv_mul(se, dv_fma(sc, xr, sh));
+        const V xa = dwc_act(t, ak);
+        const V da = dwc_actd(t, ak);
+        V acc;
+        dv_set(acc, 0.f);
+        const int r = ey / S, e = ey % S;
+#pragma unroll
+        for (int ar = 0; ar < NA; ++ar) {
+          const int i = S * r + e + PAD - S * (ar - LO);          // tap row that links input row qy to window row ar
+          if (i < 0 || i >= K) continue;
+#pragma unroll
+          for (int wb = 0; wb < NB; ++wb) {
+            const int j = ex + PAD - S * (wb - LO);
+            if (j < 0 || j >= K) continue;
+            const V gv = st.G[ar][(wb + PH) % NB];
+            acc = dv_fma(st.wt[i * K + j], gv, acc);
+            st.dwa[i * K + j] = dv_fma(xa, gv, st.dwa[i * K + j]);
+          }
+        }
+        const V gxr = Io::st(ob + ((size_t)qy * a.W + qx) * a.C, dv_mul(acc, da));
+        if (want_stats) {
+          st.s1 = dv_add(st.s1, gxr);
+          st.s2 = dv_fma(gxr, xr, st.s2);
+        }
+      }
+    }
+  }
+
+  template <class Sink>
+  static __host__ __device__ void thread_main(const DwcArgs& a, int c, int il, Sink& sink) {
+    const T* g = reinterpret_cast<const T*>(a.g);
+    const T* y = reinterpret_cast<const T*>(a.y_out);
+    const T* x = reinterpret_cast<const T*>(a.x);
+    T* gx = reinterpret_cast<T*>(a.gx);
+    State st;
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      st.wt[t] = dwc_ldc<CPT>(a.w_taps + (size_t)t * a.C + c);
+      dv_set(st.dwa[t], 0.f);
+    }
+    dv_set(st.s1, 0.f); dv_set(st.s2, 0.f);
+#pragma unroll
+    for (int ey = 0; ey < RI; ++ey)
+#pragma unroll
+      for (int ex = 0; ex < S; ++ex) st.rx[ey][ex] = Io::zero();
+    V be = dwc_ldc<CPT>(a.beta + c), sc, sh;
+    dv_set(sc, 1.f); dv_set(sh, 0.f);
+    if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
+    const DwcAct ak = dwc_make_act(a.act);
+    const bool want_stats = a.stats != nullptr;
+    const bool pf_lane = a.pf_dist > 0 && ((size_t)c * sizeof(T)) % 128 == 0;
+    for (int item = il; item < a.n_items; item += a.item_lanes) {
+      const int b = item / a.n_bands, band = item - b * a.n_bands;
+      const int r0 = band * R;
+      const V al = dwc_ldc<CPT>(a.alpha + (size_t)b * a.C + c), ga = dwc_ldc<CPT>(a.gamma + (size_t)b * a.C + c);
+      V se;
+      dv_set(se, 1.f);
+      if (a.se) se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+      const T* gb = g + (size_t)b * a.Ho * a.Wo * a.C + c;
+      const T* yb = y + (size_t)b * a.Ho * a.Wo * a.C + c;
+      const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
+      T* ob = gx + (size_t)b * a.H * a.W * a.C + c;
+      // window fill: steps px = -(LO+HI) .. -1 only shift columns in; compute starts at px = 0
+      const int px_begin = -(LO + HI);
+      prefetch(st, a, gb, yb, xb, r0, px_begin, pf_lane);
+      for (int px0 = px_begin; px0 < a.Wo; px0 += NB) {
+        // NB phases with compile-time window slots (no register moves when the window slides)
+        run_phases(st, a, gb, yb, xb, ob, r0, px0, a.Wo, al, be, ga, sc, sh, se, ak, want_stats, pf_lane);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < K * K; ++t)
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) sink.dw(c + i, t, dv_get(st.dwa[t], i));
+    if (want_stats) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        sink.stat(0, c + i, dv_get(st.s1, i));
+        sink.stat(1, c + i, dv_get(st.s2, i));
+      }
+    }
+  }
+
+  static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcArgs& a, const T* gb, const T* yb,
+                                                             const T* xb, T* ob, int r0, int px0, int px_end, V al, V be,
+                                                             V ga, V sc, V sh, V se, const DwcAct& ak, bool ws, bool pf) {
+    if (px0 + 0 < px_end) step<0>(st, a, gb, yb, xb, ob, r0, px0 + 0, al, be, ga, sc, sh, se, ak, ws, pf);
+    if (NB > 1 && px0 + 1 < px_end) step<(NB > 1 ? 1 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 1, al, be, ga, sc, sh, se, ak, ws, pf);
+    if (NB > 2 && px0 + 2 < px_end) step<(NB > 2 ? 2 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 2, al, be, ga, sc, sh, se, ak, ws, pf);
+    if (NB > 3 && px0 + 3 < px_end) step<(NB > 3 ? 3 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 3, al, be, ga, sc, sh, se, ak, ws, pf);
+    if (NB > 4 && px0 + 4 < px_end) step<(NB > 4 ? 4 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 4, al, be, ga, sc, sh, se, ak, ws, pf);
+  }
+};
+
+}  // namespace td3d

@@ -90,8 +90,7 @@ int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st);
 bool dw_walker_supported(int H, int W, int C, int k, int stride);       // k_dww.cu: small planes (W <= 32), stride 1
 int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st);
 int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st);
-int launch_dw_fwd_simple(const DwArgs& a, int dtype, cudaStream_t st);
-int launch_dw_bwd_simple(const DwBwdArgs& a, int dtype, cudaStream_t st);
+int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);   // k_dwc.cu: one pass (data + weight gradient + sums)
 
 // ---- k_gemm_simple.cu / k_gemm_tc.cu ----
 struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m,n])

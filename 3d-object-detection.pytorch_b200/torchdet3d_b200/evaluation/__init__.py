@@ -1,4 +1,6 @@
-from .metrics import (compute_average_distance, compute_accuracy, compute_metrics_per_cls, MetricAccumulator)
+from .metrics import (compute_average_distance, compute_accuracy, compute_metrics_per_cls, MetricAccumulator,
+                      set_iou_backend)
 from .evaluate import Evaluator
 
-__all__ = ["compute_average_distance", "compute_accuracy", "compute_metrics_per_cls", "MetricAccumulator", "Evaluator"]
+__all__ = ["compute_average_distance", "compute_accuracy", "compute_metrics_per_cls", "MetricAccumulator",
+           "set_iou_backend", "Evaluator"]

@@ -3,9 +3,12 @@ eval-mode forward with the GROUND-TRUTH class selecting the regressor head (:92)
 per-class ADD / SADD / accuracy meters weighted by the full batch size (:96-106), TensorBoard
 scalars and a per-class table.
 
-Per-batch metrics come from one fused kernel launch; `visual_test` (drawing) and the 3D-IoU
-column (CPU EPnP + Qhull per sample) are outside the B200 hot path.
+Per-batch metrics come from one fused kernel launch.  `visual_test` (dataset + drawing) and the
+3D-IoU column (CPU EPnP + Qhull per sample) are outside the B200 hot path: both keep the reference
+call signature (scripts/main.py:105-106 runs unchanged) and delegate to the reference package when
+it is importable, else degrade with a warning (IOU = 0, no pictures) instead of raising.
 """
+import warnings
 from dataclasses import dataclass
 
 import torch
@@ -31,10 +34,9 @@ class Evaluator:
     debug_steps: int = 30
 
     @torch.no_grad()
-    def val(self, epoch=None, compute_iou=False):
-        if compute_iou:
-            raise NotImplementedError("3D IoU is outside the B200 hot path (evaluation/metrics.py:70-89 of the reference)")
-        ADD_meter, SADD_meter, ACC_meter = AverageMeter(), AverageMeter(), AverageMeter()
+    def val(self, epoch=None, compute_iou=True):
+        ADD_meter, SADD_meter, ACC_meter, IOU_meter = AverageMeter(), AverageMeter(), AverageMeter(), AverageMeter()
+        IOU_cls = [AverageMeter() for _ in range(self.num_classes)]
         ADD_cls = [AverageMeter() for _ in range(self.num_classes)]
         SADD_cls = [AverageMeter() for _ in range(self.num_classes)]
         ACC_cls = [AverageMeter() for _ in range(self.num_classes)]
@@ -42,30 +44,59 @@ class Evaluator:
         for it, (imgs, gt_kp, gt_cats) in enumerate(self.val_loader):
             imgs, gt_kp, gt_cats = put_on_device([imgs, gt_kp, gt_cats], self.device)
             pred_kp, pred_cats = self.model(imgs, gt_cats)
-            per_cls, ADD, SADD, _, ACC = compute_metrics_per_cls(pred_kp, gt_kp, pred_cats, gt_cats, False)
+            per_cls, ADD, SADD, IOU, ACC = compute_metrics_per_cls(pred_kp, gt_kp, pred_cats, gt_cats, compute_iou)
             n = imgs.size(0)
-            for cl, a, s, _, c in per_cls:        # weighted by the whole batch size, as the reference does
+            for cl, a, s, i, c in per_cls:        # weighted by the whole batch size, as the reference does
                 ADD_cls[cl].update(a, n)
                 SADD_cls[cl].update(s, n)
                 ACC_cls[cl].update(c, n)
+                IOU_cls[cl].update(i, n)
             ADD_meter.update(ADD, n)
             SADD_meter.update(SADD, n)
             ACC_meter.update(ACC, n)
+            IOU_meter.update(IOU, n)
             if self.debug and it == self.debug_steps:
                 break
         if epoch is not None and self.writer is not None:
             self.writer.add_scalar('Val/ADD', ADD_meter.avg, global_step=epoch)
             self.writer.add_scalar('Val/SADD', SADD_meter.avg, global_step=epoch)
             self.writer.add_scalar('Val/ACC', ACC_meter.avg, global_step=epoch)
-        rows = [("Average metrics", ADD_meter.avg, SADD_meter.avg, ACC_meter.avg)]
+            if compute_iou:
+                self.writer.add_scalar('Val/IOU', IOU_meter.avg, global_step=epoch)
+        rows = [("Average metrics", ADD_meter.avg, SADD_meter.avg, ACC_meter.avg, IOU_meter.avg)]
         rows += [(OBJECTRON_CLASSES[k] if k < len(OBJECTRON_CLASSES) else str(k), ADD_cls[k].avg, SADD_cls[k].avg,
-                  ACC_cls[k].avg) for k in range(self.num_classes)]
-        head = f"{'category name':<18}{'ADD':>10}{'SADD':>10}{'accuracy':>10}"
-        body = "\n".join(f"{r[0]:<18}{r[1]:>10.4f}{r[2]:>10.4f}{r[3]:>10.4f}" for r in rows)
+                  ACC_cls[k].avg, IOU_cls[k].avg) for k in range(self.num_classes)]
+        ncol = 5 if compute_iou else 4
+        head = f"{'category name':<18}" + "".join(f"{h:>10}" for h in ('ADD', 'SADD', 'accuracy', 'IOU')[:ncol - 1])
+        body = "\n".join(f"{r[0]:<18}" + "".join(f"{v:>10.4f}" for v in r[1:ncol]) for r in rows)
         print("\nComputed val metrics:\n" + (f"epoch: {epoch}\n" if epoch is not None else "") + head + "\n" + body)
-        self.results = dict(ADD=ADD_meter.avg, SADD=SADD_meter.avg, ACC=ACC_meter.avg, per_class=rows[1:])
+        self.results = dict(ADD=ADD_meter.avg, SADD=SADD_meter.avg, ACC=ACC_meter.avg, IOU=IOU_meter.avg,
+                            per_class=[r[:4] for r in rows[1:]], per_class_iou=[r[4] for r in rows[1:]])
         return self.results
 
+    def visual_test(self):
+        """Reference: draws predictions on `num_samples` test images (evaluate.py:31-72) -- dataset access and
+        OpenCV drawing, nothing of the B200 path.  Delegates to the reference implementation when `torchdet3d`
+        is importable (same dataclass fields), else warns and returns, so scripts/main.py:106 runs unchanged."""
+        try:
+            from torchdet3d.evaluation.evaluate import Evaluator as _RefEvaluator
+        except Exception as ex:                                              # noqa: BLE001
+            warnings.warn(f"visual_test skipped: the reference drawing pipeline is not importable ({type(ex).__name__})")
+            return None
+        return _RefEvaluator.visual_test(self)
+
+    @staticmethod
+    def transform_kp(kp, crop_cords):
+        """evaluate.py:157-165: crop-normalised keypoints -> pixel coordinates of the uncropped frame."""
+        x0, y0, x1, y1 = crop_cords
+        kp[:, 0] = kp[:, 0] * (x1 - x0)
+        kp[:, 1] = kp[:, 1] * (y1 - y0)
+        kp[:, 0] += x0
+        kp[:, 1] += y0
+        return kp
+
     def run_eval_pipe(self, visual_only=False):
+        print('.' * 10, 'Run evaluating protocol', '.' * 10)
         if not visual_only:
-            self.val(compute_iou=False)
+            self.val(compute_iou=True)
+        self.visual_test()

@@ -3,9 +3,14 @@
 Drop-in for torchdet3d/evaluation/metrics.py:10-68 (`compute_average_distance`, `compute_accuracy`,
 `compute_metrics_per_cls`).  The reference runs a 9x9 Python loop of tiny kernels plus three host
 syncs per call; here one launch (one warp per sample) accumulates everything -- totals and the
-per-class breakdown -- into a device-side f64 accumulator.  The 3D-IoU branch (EPnP lift + Qhull,
-metrics.py:70-89) is CPU numpy/scipy per sample and out of scope; `compute_iou=True` raises.
+per-class breakdown -- into a device-side f64 accumulator.  The 3D-IoU column (EPnP lift + Qhull,
+metrics.py:70-89) is CPU numpy/scipy per sample in the reference and outside the B200 hot path
+(SURVEY.md 8f-4): `compute_iou=True` keeps working for unmodified callers (scripts/main.py:105) by
+delegating to an IoU backend -- the reference's own `compute_2d_based_iou` when `torchdet3d` is
+importable, or whatever `set_iou_backend` installed -- and otherwise warns once and reports 0.
 """
+import warnings
+
 import torch
 
 from .. import _lib as L
@@ -72,17 +77,46 @@ def compute_accuracy(pred_cats, gt_cats, reduce_mean=True, **kwargs):
     return a[2] / B if reduce_mean else a[2]
 
 
+_iou_backend = None          # callable(pred_kp[n,9,2], gt_kp[n,9,2], reduce_mean=False) -> summed IoU
+_iou_probe_done = False
+
+
+def set_iou_backend(fn):
+    """Install the 3D-IoU implementation used when `compute_iou=True` (signature of the reference's
+    `compute_2d_based_iou`, metrics.py:70-89).  `None` restores the default lookup."""
+    global _iou_backend, _iou_probe_done
+    _iou_backend, _iou_probe_done = fn, fn is not None
+
+
+def _iou_fn():
+    global _iou_backend, _iou_probe_done
+    if not _iou_probe_done:
+        _iou_probe_done = True
+        try:
+            from torchdet3d.evaluation.metrics import compute_2d_based_iou   # the reference package, if installed
+            _iou_backend = compute_2d_based_iou
+        except Exception as ex:                                              # noqa: BLE001
+            warnings.warn("compute_iou=True: no 3D-IoU backend (the reference's EPnP + Qhull CPU path, torchdet3d."
+                          f"evaluation.metrics.compute_2d_based_iou, is not importable: {type(ex).__name__}); the IOU "
+                          "column is reported as 0. Install one with torchdet3d_b200.evaluation.set_iou_backend(fn).")
+    return _iou_backend
+
+
 @torch.no_grad()
-def compute_metrics_per_cls(pred_kp, gt_kp, pred_cats, gt_cats, compute_iou=False, **kwargs):
-    """-> ([(cls, ADD, SADD, IOU, acc)], ADD, SADD, IOU, acc) as metrics.py:39-68 (IOU == 0.)."""
-    if compute_iou:
-        raise NotImplementedError("3D IoU (CPU EPnP lift + Qhull per sample, metrics.py:70-89) is outside the "
-                                  "B200 hot path; call the reference implementation for it")
+def compute_metrics_per_cls(pred_kp, gt_kp, pred_cats, gt_cats, compute_iou=True, **kwargs):
+    """-> ([(cls, ADD, SADD, IOU, acc)], ADD, SADD, IOU, acc) as metrics.py:39-68.  ADD / SADD / acc come
+    from one kernel launch; the IOU column from the CPU backend (see module docstring) or 0."""
     a = _run(pred_kp, gt_kp, pred_cats, gt_cats)
     B = pred_kp.shape[0]
-    rows = []
+    iou = _iou_fn() if compute_iou else None
+    rows, tot_iou = [], 0.
     for k in range(MAX_CLASSES):
         s_add, s_sadd, hits, n = a[4 + 4 * k: 8 + 4 * k]
         if n > 0:
-            rows.append((k, s_add / n, s_sadd / n, 0., hits / n))
-    return rows, a[0] / B, a[1] / B, 0., a[2] / B
+            s_iou = 0.
+            if iou is not None:
+                sel = gt_cats == k
+                s_iou = float(iou(pred_kp[sel], gt_kp[sel], reduce_mean=False))
+            tot_iou += s_iou
+            rows.append((k, s_add / n, s_sadd / n, s_iou / n, hits / n))
+    return rows, a[0] / B, a[1] / B, tot_iou / B, a[2] / B

@@ -230,8 +230,10 @@ class Regressor(nn.Module):
             self._eval_fold_stale = False
 
     def mark_packed(self):
-        """The fused optimizer re-packs inside td3d_optim_step."""
+        """The fused optimizer re-packs the weights inside td3d_optim_step -- but not the eval-mode
+        BatchNorm fold (gamma/beta moved too), which the next eval forward has to rebuild."""
         self._packed_version = self._param_version()
+        self._eval_fold_stale = True
 
     # ---- forward / backward ------------------------------------------------------------------
     def _forward_impl(self, img, cats, keep, training):

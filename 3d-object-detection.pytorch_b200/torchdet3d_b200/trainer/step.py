@@ -36,6 +36,7 @@ class FusedTrainStep:
         self.loss_terms = torch.zeros(8, device=dev)
         self.loss_sum = torch.zeros(8, dtype=torch.float64, device=dev)   # sum over steps of terms * B
         self.metrics = MetricAccumulator(dev)
+        self.keep = None                 # optional injected cls_fc dropout mask [B, head_ch] (parity tests); None = in-kernel Philox
         self.batch = batch
         self.steps_done = 0
         self._graph = None
@@ -52,7 +53,7 @@ class FusedTrainStep:
         L.check(lib.td3d_plan_set_dropout_counter(plan.handle, L.ptr(self.optimizer.steps)))
         m.pack(plan)
         st = L.stream()
-        L.check(lib.td3d_forward(plan.handle, L.ptr(self.imgs), L.ptr(self.cats), None, C.c_uint64(m.dropout_seed), 1,
+        L.check(lib.td3d_forward(plan.handle, L.ptr(self.imgs), L.ptr(self.cats), L.ptr(self.keep), C.c_uint64(m.dropout_seed), 1,
                                  L.ptr(self.kp), L.ptr(self.logits), st))
         desc = self.loss_manager.loss_desc()
         has_cls = bool(self.loss_manager.class_criterions)
@@ -70,7 +71,6 @@ class FusedTrainStep:
         if self.with_metrics:
             self.metrics.update(self.kp, self.gt_kp, self.logits, self.cats)
         self.loss_sum.add_(self.loss_terms.double() * self.batch)
-        m._eval_fold_stale = True
 
     def _key(self):
         g = self.optimizer.param_groups[0]
@@ -78,11 +78,17 @@ class FusedTrainStep:
         return (float(g['lr']), float(g['weight_decay']), float(self.optimizer.grad_scale),
                 float(lm.lam_cls) if lm.use_alwa else 1.0, self.model._flat.data_ptr())
 
-    def load(self, imgs, gt_kp, cats):
+    def load(self, imgs, gt_kp, cats, dropout_keep=None):
         """Stage one batch (pinned host or device tensors) into the static device buffers."""
         self.imgs.copy_(imgs, non_blocking=True)
         self.gt_kp.copy_(gt_kp, non_blocking=True)
         self.cats.copy_(cats, non_blocking=True)
+        if dropout_keep is not None:
+            if self.keep is None:
+                if self._graph is not None:
+                    raise L.Td3dError("dropout_keep must be injected from the first step on (the captured graph has no mask input)")
+                self.keep = torch.ones(self.batch, self.model.head_ch, device=self.device)
+            self.keep.copy_(dropout_keep, non_blocking=True)
 
     def run(self):
         """Execute one step on the staged batch. Asynchronous."""
@@ -93,7 +99,8 @@ class FusedTrainStep:
             # capture (also after an LR / loss-weight change: scalars are baked into kernel arguments)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread may touch CUDA events while this thread captures (N > 1)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._sequence()
             self._graph, self._graph_key = g, key
             g.replay()
@@ -102,9 +109,12 @@ class FusedTrainStep:
             self._warm += 1
         self.steps_done += 1
         self.model.mark_packed()
+        # running statistics and BN affine parameters moved on EVERY branch (a graph replay never runs the Python
+        # of _sequence): the eval-mode fold must be rebuilt before the next eval forward
+        self.model._eval_fold_stale = True
 
-    def __call__(self, imgs, gt_kp, cats):
-        self.load(imgs, gt_kp, cats)
+    def __call__(self, imgs, gt_kp, cats, dropout_keep=None):
+        self.load(imgs, gt_kp, cats, dropout_keep)
         self.run()
         return self.loss_terms
 

@@ -307,8 +307,9 @@ def main():
     if rank == 0 and not args.skip_profile:
         lib = L.lib()
         plan = model._last_plan
-        saved = step.use_graph
+        saved, saved_ar = step.use_graph, step.allreduce
         step.use_graph = False
+        step.allreduce = None      # rank 0 profiles ALONE: no collective may be issued here (the other ranks are not in this block)
         step.run()
         torch.cuda.synchronize(dev)
         L.check(lib.td3d_plan_profile(plan.handle, 1))
@@ -350,7 +351,7 @@ def main():
                     kd, tg, _, by = recs[j]
                     f.write(f"{j},{names[kd]},{tg},{us:.2f},{by / 1e6:.3f},{by / 1e3 / max(us, 1e-9):.1f}\n")
         L.check(lib.td3d_plan_profile(plan.handle, 0))
-        step.use_graph = saved
+        step.use_graph, step.allreduce = saved, saved_ar
         launches = int(sum(v["launches_per_step"] for v in kinds.values()))
         top = max(kinds.items(), key=lambda kv: kv[1]["ms_per_step"])
         for v in kinds.values():
@@ -413,9 +414,16 @@ def main():
             "infer": infer,
             "final_loss": loss_now,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Observed on 2 x B200: ncclCommDestroy blocks forever while a CUDA graph that captured NCCL kernels is alive.
+        # Drop the graph, drain the device, meet the other ranks, then leave without tearing the communicator down.
+        step._graph = None
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
