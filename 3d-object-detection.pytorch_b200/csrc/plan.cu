@@ -413,22 +413,11 @@ static int p_dwf(const Ctx& c, const DwArgs& a, int dt, cudaStream_t st) {
   TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd(a, dt, st));
   return TD3D_OK;
 }
-static int p_dwb(const Ctx& c, const DwBwdArgs& a0, int dt, cudaStream_t st) {
-  DwBwdArgs a = a0;
+static int p_dwb(const Ctx& c, const DwBwdArgs& a, int dt, cudaStream_t st) {
   int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
   double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
-  // the weight-gradient kernel runs on side stream 1, concurrently with the data-gradient kernel (both
-  // read g, y_out, x: the second reader mostly hits L2); joined right after, because the next BatchNorm
-  // finalize overwrites the alpha/beta/gamma it reads
-  Ctx sc;
-  TD3D_TRY(side_fork(c, 1, &sc));
-  a.wgrad_stream = sc.st != c.st ? (void*)sc.st : nullptr;
-  // fused ideal: read g, y_out, x once; write gx once
+  // one pass: read g, y_out, x once; write gx once (data gradient, weight gradient and BatchNorm sums together)
   TD3D_K(PK_DW_BWD, (2 * out + 2 * in) * c.esz(), launch_dw_bwd(a, dt, st));
-  if (a.wgrad_stream) {
-    TD3D_TRY(side_done(c, 1));
-    TD3D_TRY(side_join(c, 1));
-  }
   return TD3D_OK;
 }
 

@@ -120,9 +120,10 @@ def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
     safe = ((xt.detach().abs() - 3.0).abs() > 1e-4).float()
     assert rel_err(gx.float() * safe, xt.grad * safe) < (2e-5 if code == L.F32 else gx_tol_bf16)
     assert rel_err(dw, wr.grad) < (2e-4 if code == L.F32 else 2e-2)
+    # the backward sums feed a BatchNorm backward over the whole batch: only their total over the slots is defined
     gxf = gx.float()
-    torch.testing.assert_close(bst[:, 0], gxf.sum(dim=(1, 2)), rtol=1e-4, atol=2e-2)
-    torch.testing.assert_close(bst[:, 1], (gxf * x.float()).sum(dim=(1, 2)), rtol=1e-4, atol=5e-2)
+    torch.testing.assert_close(bst[:, 0].sum(0), gxf.sum(dim=(0, 1, 2)), rtol=1e-4, atol=2e-2 * B ** 0.5)
+    torch.testing.assert_close(bst[:, 1].sum(0), (gxf * x.float()).sum(dim=(0, 1, 2)), rtol=1e-4, atol=5e-2 * B ** 0.5)
 
 
 # row-walker edge cases (k_dww.cu): rows that fill all lanes of their segment (shuffle wrap needs the select path),
