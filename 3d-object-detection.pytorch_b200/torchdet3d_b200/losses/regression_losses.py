@@ -189,4 +189,8 @@ class LossManager:
             if cls > reg:
                 self.lam_cls = (1 - (cls - reg) / cls).item()
                 print(f"classification coefficient changed : {self.lam_cls}")
+                # the reference returns lam_reg*reg + lam_cls*cls with the NEW lam_cls (regression_losses.py:115):
+                # re-evaluate the fused sum (forward + gradient) with the updated weight; one extra launch every C iterations
+                total, terms = fused_loss(self.loss_desc(), pred_kp, gt_kp, pred_cats, gt_cats)
+                self.last_terms = terms
         return total

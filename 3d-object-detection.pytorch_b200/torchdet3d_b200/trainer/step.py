@@ -18,7 +18,7 @@ from ..models.regressor import Regressor, MAX_CLASSES, NUM_POINTS
 
 class FusedTrainStep:
     def __init__(self, model, loss_manager, optimizer, batch, height, width, use_graph=True, allreduce=None,
-                 metrics=True):
+                 metrics=True, shared=None):
         assert isinstance(model, Regressor) and isinstance(optimizer, FusedOptimizer)
         self.model, self.loss_manager, self.optimizer = model, loss_manager, optimizer
         self.use_graph, self.allreduce, self.with_metrics = use_graph, allreduce, metrics
@@ -34,8 +34,14 @@ class FusedTrainStep:
         self.d_kp = torch.zeros(batch, NUM_POINTS, device=dev)
         self.d_logits = torch.zeros(batch, model.num_classes, device=dev)
         self.loss_terms = torch.zeros(8, device=dev)
-        self.loss_sum = torch.zeros(8, dtype=torch.float64, device=dev)   # sum over steps of terms * B
-        self.metrics = MetricAccumulator(dev)
+        # epoch accumulators; `shared` = another FusedTrainStep whose accumulators this one adds to (the Trainer uses
+        # one step object per batch shape: a partial last batch must land in the same epoch sums)
+        if shared is not None:
+            self.loss_sum, self.metrics, self._crops = shared.loss_sum, shared.metrics, shared._crops
+        else:
+            self.loss_sum = torch.zeros(8, dtype=torch.float64, device=dev)   # sum over steps of terms * B
+            self.metrics = MetricAccumulator(dev)
+            self._crops = [0]
         self.keep = None                 # optional injected cls_fc dropout mask [B, head_ch] (parity tests); None = in-kernel Philox
         self.batch = batch
         self.steps_done = 0
@@ -51,6 +57,7 @@ class FusedTrainStep:
         plan = m._plan_for(self.imgs)
         m._last_plan = plan
         L.check(lib.td3d_plan_set_dropout_counter(plan.handle, L.ptr(self.optimizer.steps)))
+        m._dropout_counter_ref = self.optimizer.steps        # the plan keeps the raw pointer: keep the tensor alive with the model
         m.pack(plan)
         st = L.stream()
         L.check(lib.td3d_forward(plan.handle, L.ptr(self.imgs), L.ptr(self.cats), L.ptr(self.keep), C.c_uint64(m.dropout_seed), 1,
@@ -108,6 +115,7 @@ class FusedTrainStep:
             self._sequence()
             self._warm += 1
         self.steps_done += 1
+        self._crops[0] += self.batch
         self.model.mark_packed()
         # running statistics and BN affine parameters moved on EVERY branch (a graph replay never runs the Python
         # of _sequence): the eval-mode fold must be rebuilt before the next eval forward
@@ -122,10 +130,11 @@ class FusedTrainStep:
         """One D2H sync: (mean loss terms[8], ADD, SADD, acc, per-class rows) since the last reset."""
         acc = self.metrics.read()
         n = max(acc[3], 1.0)
-        loss = (self.loss_sum / max(self.steps_done * self.batch, 1)).cpu().tolist()
+        loss = (self.loss_sum / max(self._crops[0], 1)).cpu().tolist()
         return dict(loss=loss, ADD=acc[0] / n, SADD=acc[1] / n, acc=acc[2] / n, count=acc[3], raw=acc)
 
     def reset_epoch(self):
         self.metrics.reset()
         self.loss_sum.zero_()
         self.steps_done = 0
+        self._crops[0] = 0

@@ -65,8 +65,10 @@ class Trainer:
         pending = 0
         for it, (imgs, gt_kp, gt_cats) in enumerate(self.train_loader):
             if step is None or step.imgs.shape != imgs.shape:
-                step = self._get_step(net, imgs.shape)
-                step.reset_epoch()
+                first = step is None
+                step = self._get_step(net, imgs.shape)      # all step objects of this trainer share the epoch accumulators
+                if first:
+                    step.reset_epoch()
             step(imgs, gt_kp, gt_cats)
             self.train_step += 1
             pending += 1
@@ -102,8 +104,9 @@ class Trainer:
         cache = self.__dict__.setdefault("_steps", {})
         key = tuple(shape)
         if key not in cache:
+            shared = next(iter(cache.values())) if cache else None
             cache[key] = FusedTrainStep(net, self.loss_manager, self.optimizer, shape[0], shape[2], shape[3],
-                                        use_graph=self.use_graph, allreduce=self.allreduce)
+                                        use_graph=self.use_graph, allreduce=self.allreduce, shared=shared)
         return cache[key]
 
     # ---- reference-style loop (train.py:42-108) on the same hooks ------------------------------

@@ -117,7 +117,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 32
+    # same per-step batch as the GPU arm (256 crops) whenever the whole run then stays within ~4 minutes at the ~65 crops/s
+    # the port reaches on 16 host cores; otherwise the largest power-of-two sample that does
+    batch = args.batch
+    while batch > 32 and (args.steps + args.warmup) * batch / 65.0 > 240.0:
+        batch //= 2
     sec = cpu_reference_step(batch, args.steps, args.warmup, threads)
     v = batch / sec
     line = {
@@ -125,7 +129,7 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{MODEL} regressor train step (fwd+loss+bwd+AdamW+metrics), {RES}x{RES} crops, "
-                               f"CPU sample of {batch} crops/step (GPU arm: batch 256/GPU)"},
+                               f"CPU sample of {batch} crops/step (GPU arm: batch {args.batch}/GPU)", "same_batch_as_gpu_arm": batch == args.batch},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x {batch} crops, oracle/torch_port.py (reference is pure Python and "
                                    "cannot travel to the GPU box)"},

@@ -174,13 +174,50 @@ def run_loss_metric_golden():
     print("loss_metrics ->", sum(v.nbytes for v in out.values()) // 1024, "KiB")
 
 
+def run_alwa_golden():
+    """The reference LossManager with ALWA re-weighting on (regression_losses.py:96-115): returned loss, its gradients
+    and lam_cls for 9 iterations with C=3 (updates at iterations 3 and 6), both variants (with / without std)."""
+    from torchdet3d.builders import build_loss
+    from torchdet3d.losses import LossManager
+    out = {}
+    for ver, compute_std in (("v1", True), ("v2", False)):
+        cfg = refshim.reference_config("mobilenetv3_small")
+        cfg.loss.names = ["l1", "add_loss", "cross_entropy"]
+        cfg.loss.coeffs = ([1.0, 0.1], [1.0])
+        cfg.loss.alwa = dict(use=True, lam_cls=1., lam_reg=1., C=3, compute_std=compute_std)
+        lm = LossManager(build_loss(cfg), cfg.loss.coeffs, cfg.loss.alwa)
+        rng = np.random.default_rng(7)
+        B = 16
+        for it in range(9):
+            pred = torch.tensor(rng.random((B, 9, 2), dtype=np.float32), requires_grad=True)
+            gt = torch.tensor(rng.random((B, 9, 2), dtype=np.float32))
+            logits = torch.tensor((rng.standard_normal((B, 9)) * (3.0 if it < 5 else 0.3)).astype(np.float32), requires_grad=True)
+            cats = torch.tensor(rng.integers(0, 9, size=(B,)), dtype=torch.int64)
+            loss = lm.parse_losses(pred, gt, logits, cats, it)
+            loss.backward()
+            k = f"{ver}_i{it}_"
+            out[k + "pred"], out[k + "gt"] = pred.detach().numpy(), gt.numpy()
+            out[k + "logits"], out[k + "cats"] = logits.detach().numpy(), cats.numpy()
+            out[k + "loss"] = np.array([loss.item()], dtype=np.float64)
+            out[k + "lam_cls"] = np.array([float(lm.lam_cls)], dtype=np.float64)
+            out[k + "g_pred"], out[k + "g_logits"] = pred.grad.numpy().copy(), logits.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "alwa.npz"), **out)
+    print("alwa ->", sum(v.nbytes for v in out.values()) // 1024, "KiB; lam_cls trajectory",
+          [round(float(out[f"v1_i{i}_lam_cls"][0]), 4) for i in range(9)])
+
+
 def main():
     refshim.install()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    run_loss_metric_golden()
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only in (None, "alwa"):
+        run_alwa_golden()
+    if only in (None, "loss"):
+        run_loss_metric_golden()
     for case in CASES:
-        run_case(*case)
+        if only in (None, case[0]):
+            run_case(*case)
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "depthwise" 2>&1 | tail -15 > gpurun_out/t_dw.log; tail -n 6 gpurun_out/t_dw.log
 timeout 900 python -m pytest tests/test_gpu_model.py -x -q 2>&1 | tail -15 > gpurun_out/t_model.log; tail -n 6 gpurun_out/t_model.log
+timeout 900 python -m pytest tests/test_gpu_surface.py -q 2>&1 | tail -40 > gpurun_out/t_surface.log; tail -n 25 gpurun_out/t_surface.log | cut -c1-400
 for pf in 6 0 12; do
   TD3D_DWC_PF=$pf timeout 300 python bench.py --steps 20 --warmup 5 --skip-infer --skip-cpu --dump-launches gpurun_out/launches_pf$pf.csv > gpurun_out/bench_pf$pf.json 2> gpurun_out/bench_pf$pf.err; echo "pf=$pf rc=$?"
   python - <<PY
