@@ -398,4 +398,157 @@ struct DwcBwd {
   }
 };
 
+
+// =================================================================================================================
+// FORWARD column walker:  y = out_act( dw(act(se*(scale*x+shift))) + out_bias )   (+ per-sample sums of y, y^2)
+//   training  : input transform = BatchNorm fold (+SE gate) + activation of the producer, raw y + sums for this BatchNorm
+//   inference : BatchNorm folded into the taps / out_bias, activation applied before the single store
+// Thread = CPT channels x a band of R output rows; the K-column input window slides in registers (slot of an input
+// column is compile time after unrolling the walk K times), every input element is loaded and transformed once per band.
+// =================================================================================================================
+struct DwcFwdArgs {
+  const void* x;                              // [B,H,W,C]
+  const float* scale; const float* shift;     // [C] or null
+  const float* se;                            // [B,C] or null
+  int act;
+  const float* w_taps;                        // [K*K][C]
+  const float* out_bias;                      // [C] or null
+  int out_act;
+  void* y;                                    // [B,Ho,Wo,C]
+  float* stats;                               // [B][2][C] per-sample sums (SE squeeze needs them per sample) or null
+  int B, H, W, C, Ho, Wo;
+  int n_bands, n_items, item_lanes;
+  int cw, n_cchunks, ilb;
+  int pf_dist;
+};
+
+template <typename T, int K, int S, int R, int CPT>
+struct DwcFwd {
+  typedef typename DwcVec<CPT>::V V;
+  typedef DwcIo<T, CPT> Io;
+  typedef typename Io::Raw Raw;
+  static constexpr int PAD = (K - 1) / 2;
+  static constexpr int NAI = S * (R - 1) + K;        // input rows of a band
+  static constexpr int PXB = -((K - 1) / S);         // first (fill) step: every window column of step 0 has entered by then
+  static constexpr int QX0 = S * PXB + PAD - S + 1;  // first input column that ever enters the window
+
+  struct State {
+    V Wn[NAI][K];       // transformed input window
+    V wt[K * K];
+    Raw rx[NAI][S];     // prefetched raw input columns of the next step
+  };
+
+  static __host__ __device__ __forceinline__ void prefetch(State& st, const DwcFwdArgs& a, const T* xb, int r0, int px,
+                                                           bool pf_lane) {
+#pragma unroll
+    for (int e = 0; e < S; ++e) {
+      const int qx = S * px + PAD - S + 1 + e;
+      const bool col_ok = qx >= 0 && qx < a.W;
+#pragma unroll
+      for (int ai = 0; ai < NAI; ++ai) {
+        const int qy = S * r0 - PAD + ai;
+        st.rx[ai][e] = Io::zero();
+        if (col_ok && qy >= 0 && qy < a.H) st.rx[ai][e] = Io::ld(xb + ((size_t)qy * a.W + qx) * a.C);
+      }
+    }
+#ifdef __CUDA_ARCH__
+    if (pf_lane) {
+      const int qx2 = S * (px + a.pf_dist) + PAD;
+      if (qx2 < a.W) {
+#pragma unroll
+        for (int ai = 0; ai < NAI; ++ai) {
+          const int qy = S * r0 - PAD + ai;
+          if (qy >= 0 && qy < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + ((size_t)qy * a.W + qx2) * a.C));
+        }
+      }
+    }
+#endif
+  }
+
+  template <int PH>
+  static __host__ __device__ __forceinline__ void step(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0, int px,
+                                                       V sc, V sh, V se, const DwcAct& ak, V ob_bias, const DwcAct& oak,
+                                                       V& s1, V& s2, bool pf_lane) {
+    // 1. the prefetched columns enter the window, transformed once (zero outside the image: conv padding)
+#pragma unroll
+    for (int e = 0; e < S; ++e) {
+      const int qx = S * px + PAD - S + 1 + e;
+      const bool col_ok = qx >= 0 && qx < a.W;
+#pragma unroll
+      for (int ai = 0; ai < NAI; ++ai) {
+        const int qy = S * r0 - PAD + ai;
+        V v = dwc_act(dv_mul(se, dv_fma(sc, Io::cvt(st.rx[ai][e]), sh)), ak);
+        if (!(col_ok && qy >= 0 && qy < a.H)) dv_set(v, 0.f);
+        st.Wn[ai][(S * PH + e) % K] = v;
+      }
+    }
+    prefetch(st, a, xb, r0, px + 1, pf_lane);
+    if (px < 0) return;
+    // 2. R outputs of this column
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int py = r0 + r;
+      if (py >= a.Ho) continue;
+      V acc = ob_bias;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = dv_fma(st.wt[i * K + j], st.Wn[S * r + i][(S * PH + j + S) % K], acc);
+      const V yr = Io::st(ob + ((size_t)py * a.Wo + px) * a.C, dwc_act(acc, oak));
+      s1 = dv_add(s1, yr);
+      s2 = dv_fma(yr, yr, s2);
+    }
+  }
+
+  static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0,
+                                                             int px0, V sc, V sh, V se, const DwcAct& ak, V obb,
+                                                             const DwcAct& oak, V& s1, V& s2, bool pf) {
+    if (px0 + 0 < a.Wo) step<0>(st, a, xb, ob, r0, px0 + 0, sc, sh, se, ak, obb, oak, s1, s2, pf);
+    if (K > 1 && px0 + 1 < a.Wo) step<(K > 1 ? 1 : 0)>(st, a, xb, ob, r0, px0 + 1, sc, sh, se, ak, obb, oak, s1, s2, pf);
+    if (K > 2 && px0 + 2 < a.Wo) step<(K > 2 ? 2 : 0)>(st, a, xb, ob, r0, px0 + 2, sc, sh, se, ak, obb, oak, s1, s2, pf);
+    if (K > 3 && px0 + 3 < a.Wo) step<(K > 3 ? 3 : 0)>(st, a, xb, ob, r0, px0 + 3, sc, sh, se, ak, obb, oak, s1, s2, pf);
+    if (K > 4 && px0 + 4 < a.Wo) step<(K > 4 ? 4 : 0)>(st, a, xb, ob, r0, px0 + 4, sc, sh, se, ak, obb, oak, s1, s2, pf);
+  }
+
+  // `Sink::stat(b, which, c, value)` receives the per-sample sums of one item
+  template <class Sink>
+  static __host__ __device__ void thread_main(const DwcFwdArgs& a, int c, int il, Sink& sink) {
+    const T* x = reinterpret_cast<const T*>(a.x);
+    T* y = reinterpret_cast<T*>(a.y);
+    State st;
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) st.wt[t] = dwc_ldc<CPT>(a.w_taps + (size_t)t * a.C + c);
+#pragma unroll
+    for (int ai = 0; ai < NAI; ++ai)
+#pragma unroll
+      for (int e = 0; e < S; ++e) st.rx[ai][e] = Io::zero();
+    V sc, sh, obb;
+    dv_set(sc, 1.f); dv_set(sh, 0.f); dv_set(obb, 0.f);
+    if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
+    if (a.out_bias) obb = dwc_ldc<CPT>(a.out_bias + c);
+    const DwcAct ak = dwc_make_act(a.act), oak = dwc_make_act(a.out_act);
+    const bool pf_lane = a.pf_dist > 0 && ((size_t)c * sizeof(T)) % 128 == 0;
+    for (int item = il; item < a.n_items; item += a.item_lanes) {
+      const int b = item / a.n_bands, band = item - b * a.n_bands;
+      const int r0 = band * R;
+      V se;
+      dv_set(se, 1.f);
+      if (a.se) se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+      const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
+      T* ob = y + (size_t)b * a.Ho * a.Wo * a.C + c;
+      V s1, s2;
+      dv_set(s1, 0.f); dv_set(s2, 0.f);
+      prefetch(st, a, xb, r0, PXB, pf_lane);
+      for (int px0 = PXB; px0 < a.Wo; px0 += K) run_phases(st, a, xb, ob, r0, px0, sc, sh, se, ak, obb, oak, s1, s2, pf_lane);
+      if (a.stats) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          sink.stat(b, 0, c + i, dv_get(s1, i));
+          sink.stat(b, 1, c + i, dv_get(s2, i));
+        }
+      }
+    }
+  }
+};
+
 }  // namespace td3d

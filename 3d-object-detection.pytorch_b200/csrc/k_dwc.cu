@@ -124,6 +124,68 @@ int dwc_dispatch(const DwBwdArgs& b, cudaStream_t st) {
   return TD3D_EINVAL;
 }
 
+
+// ---- forward -----------------------------------------------------------------------------------------------------
+struct GlobalStatSink {
+  float* stats; int C;
+  __device__ __forceinline__ void stat(int b, int which, int c, float v) { atomicAdd(&stats[((size_t)b * 2 + which) * C + c], v); }
+};
+
+template <typename T, int K, int S, int R, int CPT>
+__global__ void __launch_bounds__(256, 2) dwc_fwd_kernel(DwcFwdArgs a) {
+  const int chunk = blockIdx.x % a.n_cchunks, ib = blockIdx.x / a.n_cchunks;
+  const int ncg = a.C / CPT;
+  const int cg0 = chunk * a.cw;
+  const int cw_here = min(a.cw, ncg - cg0);
+  const int cgl = threadIdx.x % a.cw, ilb = threadIdx.x / a.cw;
+  const int il = ib * a.ilb + ilb;
+  if (cgl < cw_here && ilb < a.ilb && il < a.item_lanes) {
+    GlobalStatSink sink = {a.stats, a.C};
+    DwcFwd<T, K, S, R, CPT>::thread_main(a, (cg0 + cgl) * CPT, il, sink);
+  }
+}
+
+template <typename T, int K, int S, int R, int CPT>
+int dwc_fwd_launch(const DwArgs& b, cudaStream_t st) {
+  DwcFwdArgs a;
+  a.x = b.x; a.scale = b.xf.scale; a.shift = b.xf.shift; a.se = b.xf.se; a.act = b.xf.act;
+  a.w_taps = b.w_taps; a.out_bias = b.out_bias; a.out_act = b.out_act; a.y = b.y; a.stats = b.stats;
+  a.B = b.B; a.H = b.H; a.W = b.W; a.C = b.C;
+  a.Ho = (b.H - 1) / S + 1; a.Wo = (b.W - 1) / S + 1;
+  a.pf_dist = pf_dist();
+  a.n_bands = ceil_div(a.Ho, R);
+  a.n_items = a.B * a.n_bands;
+  const int ncg = a.C / CPT;
+  a.n_cchunks = ceil_div(ncg, 256);
+  a.cw = ceil_div(ceil_div(ncg, a.n_cchunks), 8) * 8;
+  if (a.cw > ncg) a.cw = ncg;
+  a.n_cchunks = ceil_div(ncg, a.cw);
+  a.ilb = 256 / a.cw;
+  if (a.ilb < 1) a.ilb = 1;
+  const int threads = ceil_div(a.cw * a.ilb, 32) * 32;
+  int ib_max = ceil_div(a.n_items, a.ilb);
+  int ib = (sm_count() * 8) / a.n_cchunks;      // no per-thread sums to amortise beyond an item: more, shorter lanes balance better
+  if (ib < 1) ib = 1;
+  if (ib > ib_max) ib = ib_max;
+  a.item_lanes = ib * a.ilb;
+  if (a.item_lanes > a.n_items) a.item_lanes = a.n_items;
+  dwc_fwd_kernel<T, K, S, R, CPT><<<ib * a.n_cchunks, threads, 0, st>>>(a);
+  TD3D_LAUNCH_CHECK();
+  return TD3D_OK;
+}
+
+template <typename T>
+int dwc_fwd_dispatch(const DwArgs& b, cudaStream_t st) {
+  const int Ho = (b.H - 1) / b.stride + 1;
+  const bool tall = Ho >= 28;
+  if (b.k == 3 && b.stride == 1) return tall ? dwc_fwd_launch<T, 3, 1, 4, 2>(b, st) : dwc_fwd_launch<T, 3, 1, 2, 2>(b, st);
+  if (b.k == 3 && b.stride == 2) return tall ? dwc_fwd_launch<T, 3, 2, 2, 2>(b, st) : dwc_fwd_launch<T, 3, 2, 1, 2>(b, st);
+  if (b.k == 5 && b.stride == 1) return dwc_fwd_launch<T, 5, 1, 2, 1>(b, st);
+  if (b.k == 5 && b.stride == 2) return tall ? dwc_fwd_launch<T, 5, 2, 2, 1>(b, st) : dwc_fwd_launch<T, 5, 2, 1, 1>(b, st);
+  set_last_error("dw_fwd: unsupported kernel/stride %d/%d", b.k, b.stride);
+  return TD3D_EINVAL;
+}
+
 }  // namespace
 
 int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st) {
@@ -131,4 +193,11 @@ int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   return dtype == TD3D_BF16 ? dwc_dispatch<bf16>(a, st) : dwc_dispatch<float>(a, st);
 }
 
+}  // namespace td3d
+
+namespace td3d {
+int launch_dw_fwd_cw(const DwArgs& a, int dtype, cudaStream_t st) {
+  TD3D_REQUIRE(a.C % 8 == 0 && a.B > 0 && a.H > 0 && a.W > 0 && a.y, "dw_fwd_cw: bad arguments");
+  return dtype == TD3D_BF16 ? dwc_fwd_dispatch<bf16>(a, st) : dwc_fwd_dispatch<float>(a, st);
+}
 }  // namespace td3d

@@ -194,6 +194,7 @@ struct TcNtParams {
   bf16* y; float* yf;
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
+  int act;              // epilogue activation after the bias (TD3D_ACT_*), before the addend
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
   int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
@@ -330,6 +331,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int et = (threadIdx.x - 32 * (1 + TC_MMA_WARPS)) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
+    const ActK eak = make_actk(p.act);
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
@@ -368,6 +370,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               loadf8(p.bias + n, bb);
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += bb[i];
+            }
+            if (p.act != TD3D_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = actk_fwd(x[i], eak);
             }
             const size_t off = (size_t)m * p.N + n;
             if (p.addend) {
@@ -656,6 +662,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.yf = g.out_f32 ? (float*)g.y : nullptr;
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
+  p.act = g.act;
   p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
   p.dbg = env_int("TD3D_TC_DBG", 0);
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but

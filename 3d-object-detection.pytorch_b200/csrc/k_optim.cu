@@ -114,11 +114,12 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const __grid_constant__
   const PackSeg sg = t.seg[blockIdx.y];
   const int64_t n = (int64_t)sg.rows * sg.cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = sg.src[i];
+    float v = sg.src[i];
     int64_t o = i;
-    if (sg.transpose) {
+    if (sg.transpose || sg.row_scale) {
       const int r = (int)(i / sg.cols), c = (int)(i % sg.cols);
-      o = (int64_t)c * sg.rows + r;
+      if (sg.transpose) o = (int64_t)c * sg.rows + r;
+      if (sg.row_scale) v *= sg.row_scale[r];
     }
     if (sg.out_dtype == TD3D_BF16) reinterpret_cast<bf16*>(sg.dst)[o] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(sg.dst)[o] = v;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(128) bn_fold_table_kernel(const __grid_constan
     float invstd = 1.f / sqrtf(sg.rv[c] + eps);
     float sc = sg.gamma[c] * invstd;
     sg.scale[c] = sc;
-    sg.shift[c] = sg.beta[c] - sg.rm[c] * sc;
+    sg.shift[c] = sg.beta[c] - sg.rm[c] * sc + (sg.lin_bias ? sg.lin_bias[c] * sc : 0.f);
   }
 }
 int launch_pack_table(const PackTable& t, cudaStream_t st) {

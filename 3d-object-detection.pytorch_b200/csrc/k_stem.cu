@@ -32,7 +32,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float v[32]) {
 template <typename T>
 __global__ void __launch_bounds__(ST_TH * ST_TW)
 stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* __restrict__ y,
-                float* __restrict__ stats, int H, int W, int Ho, int Wo) {
+                float* __restrict__ stats, int H, int W, int Ho, int Wo, const float* __restrict__ out_bias, int out_act) {
   __shared__ float s_in[3][ST_IH][ST_IW + 1];
   __shared__ float s_w[27 * ST_C];
   __shared__ float s_acc[2 * ST_C];
@@ -66,6 +66,10 @@ stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* _
 #pragma unroll
         for (int c = 0; c < ST_C; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
       }
+  if (out_bias) {      // inference: BatchNorm folded into w / out_bias, activation before the single store
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) acc[c] = act_fwd(acc[c] + __ldg(out_bias + c), out_act);
+  }
   float red[32];
   if (valid) {
     T* yo = y + (((size_t)b * Ho + oy) * Wo + ox) * ST_C;
@@ -92,14 +96,14 @@ stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* _
 }
 
 int launch_stem_fwd(const float* img, const float* w27xC, void* y, float* stats, int B, int H, int W, int C,
-                    int dtype, cudaStream_t st) {
+                    int dtype, cudaStream_t st, const float* out_bias, int out_act) {
   TD3D_REQUIRE(C == ST_C, "stem: only %d output channels supported (got %d)", ST_C, C);
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   dim3 grid(ceil_div(Wo, ST_TW), ceil_div(Ho, ST_TH), B);
   if (dtype == TD3D_BF16)
-    stem_fwd_kernel<bf16><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (bf16*)y, stats, H, W, Ho, Wo);
+    stem_fwd_kernel<bf16><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (bf16*)y, stats, H, W, Ho, Wo, out_bias, out_act);
   else
-    stem_fwd_kernel<float><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (float*)y, stats, H, W, Ho, Wo);
+    stem_fwd_kernel<float><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (float*)y, stats, H, W, Ho, Wo, out_bias, out_act);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

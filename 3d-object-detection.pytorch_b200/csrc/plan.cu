@@ -53,6 +53,7 @@ struct Block {
   int64_t se_w1 = -1, se_b1 = -1, se_w2 = -1, se_b2 = -1;
   size_t pw1 = 0, pw1t = 0, pdw = 0, pw3 = 0, pw3t = 0;   // packed offsets
   size_t pse_w1t = 0, pse_w2t = 0;                        // fp32 transposed SE weights
+  size_t pi1 = 0, pidw = 0, pi3 = 0;                      // inference copies: eval-mode BatchNorm folded into the weights
   size_t y1 = 0, y2 = 0, h = 0, h2 = 0, y3 = 0, out = 0;  // workspace activations (T)
   size_t hstats = 0, hbstats = 0;       // dw-first + SE: pool sums of H and their backward twin
   size_t zbar = 0, hid = 0, pre = 0, gate = 0;
@@ -97,6 +98,7 @@ struct td3d_plan {
   int64_t w_stem, w_last, w_fc, b_fc, w_reg0, w_cls, b_cls;
   int64_t head_stride;
   size_t p_stem, p_last, p_lastt, p_fc, p_fct;
+  size_t pi_stem, pi_last, pi_fc;        // inference copies (BatchNorm folded)
   size_t y0, x0, yc, pooled, yfc, feat, kp_saved, logits_saved, pool_stats, pool_bstats_unused;
   int Hl, Wl;                            // final resolution
   int64_t first_param_tail;
@@ -119,6 +121,7 @@ struct td3d_plan {
   bool side_pending[2] = {false, false};
   int overlap = 1;
   td3d::PackTable pack_table;
+  td3d::PackTable pack_table_eval;       // weights * eval-mode BatchNorm scale (rebuilt with the fold, td3d_pack_weights)
   td3d::BnFoldTable fold_table;
 };
 
@@ -250,6 +253,14 @@ static int build(td3d_plan* pl) {
     bn.escale = pk.take(sizeof(float) * bn.C);
     bn.eshift = pk.take(sizeof(float) * bn.C);
   }
+  pl->pi_stem = pk.take(sizeof(float) * 27 * n.stem_ch);
+  for (auto& b : pl->blocks) {
+    if (b.expand) b.pi1 = pk.take(e * b.d.exp_ch * b.d.in_ch);
+    b.pidw = pk.take(sizeof(float) * b.d.kernel * b.d.kernel * b.d.exp_ch);
+    b.pi3 = pk.take(e * b.d.out_ch * b.d.exp_ch);
+  }
+  pl->pi_last = pk.take(e * n.last_ch * cin);
+  pl->pi_fc = pk.take(e * n.head_ch * n.last_ch);
   pl->packed_bytes = pk.off;
 
   // ---- workspace ----
@@ -574,6 +585,89 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   return TD3D_OK;
 }
 
+// ---- inference forward (eval mode): BatchNorm folded into the weights, activation / residual in the producer's
+// epilogue -- every layer reads its input once and writes its activated output once (SURVEY.md 8d forward bytes).
+// Only SE blocks keep one extra pass: the gate needs the whole plane's squeeze before act(gate * z) can be applied.
+// Replaces eval-mode ModelWrapper.forward / forward_to_onnx (model_builder.py:112-146) over MobileNetV3.extract_features
+// + classifier (mobilenetv3.py:188-203) with running-statistic BatchNorm.
+static int forward_infer(const Ctx& c, const float* img, const void** feat_out) {
+  td3d_plan* pl = c.pl;
+  const td3d_net_desc& n = pl->net;
+  const int B = pl->B, dt = pl->dtype;
+  auto eshift = [&](int bn_idx) { return (const float*)c.pkf(pl->bns[bn_idx].eshift); };
+  pl->prof.tag = 0;
+  TD3D_K(PK_STEM_FWD, (double)B * 3 * pl->H * pl->W * 4 + (double)B * pl->H1 * pl->W1 * n.stem_ch * c.esz(),
+         launch_stem_fwd(img, c.pkf(pl->pi_stem), c.ws(pl->x0), nullptr, B, pl->H, pl->W, n.stem_ch, dt, c.st,
+                         eshift(pl->bn_stem), TD3D_ACT_HSWISH));
+  const void* cur = c.ws(pl->x0);
+  for (auto& b : pl->blocks) {
+    pl->prof.tag = (int)(&b - pl->blocks.data()) + 1;
+    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
+    const int Mi = B * HWi, Mo = B * HWo;
+    const int E = b.d.exp_ch;
+    DwArgs dw;
+    dw.xf = xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE);
+    if (b.expand) {
+      GemmNT g = {};
+      g.a = cur; g.w = c.pk(b.pi1); g.y = c.ws(b.y1); g.bias = eshift(b.bn1); g.act = act;
+      g.M = Mi; g.N = E; g.K = b.d.in_ch;
+      TD3D_TRY(gemm_nt(c, g));
+      dw.x = c.ws(b.y1);
+    } else {
+      dw.x = cur;
+    }
+    float* sq = c.wsf(pl->bns[b.bn2].fstats);          // per-sample sums of the depthwise output: the SE squeeze
+    if (b.d.use_se) TD3D_CUDA(cudaMemsetAsync(sq, 0, sizeof(float) * 2 * (size_t)B * E, c.st));
+    // dw-first layout is BN -> act -> SE (mobilenetv3.py:137-140), expanded layout BN -> SE -> act (:153-156)
+    const bool act_in_dw = !b.d.use_se || !b.expand;
+    dw.w_taps = c.pkf(b.pidw); dw.y = c.ws(b.d.use_se ? b.y2 : b.h2); dw.stats = b.d.use_se ? sq : nullptr;
+    dw.out_bias = eshift(b.bn2); dw.out_act = act_in_dw ? act : TD3D_ACT_NONE;
+    dw.B = B; dw.H = b.Hin; dw.W = b.Win; dw.C = E; dw.k = b.d.kernel; dw.stride = b.d.stride;
+    {
+      double in = (double)B * HWi * E, out = (double)B * HWo * E;
+      TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd_cw(dw, dt, c.st));
+    }
+    if (b.d.use_se) {
+      SeArgs s;
+      s.w1 = c.P(b.se_w1); s.b1 = c.P(b.se_b1); s.w2 = c.P(b.se_w2); s.b2 = c.P(b.se_b2);
+      s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
+      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
+      s.pool_stats = sq; s.scale = nullptr; s.shift = nullptr;
+      TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+      TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(nullptr, nullptr, s.gate, act_in_dw ? TD3D_ACT_NONE : act), nullptr, c.ws(b.h2),
+                       nullptr, B, HWo, E, dt, c.st));
+    }
+    GemmNT g = {};
+    g.a = c.ws(b.h2); g.w = c.pk(b.pi3); g.y = c.ws(b.out); g.bias = eshift(b.bn3);
+    g.addend = b.residual ? cur : nullptr;
+    g.M = Mo; g.N = b.d.out_ch; g.K = E;
+    TD3D_TRY(gemm_nt(c, g));
+    cur = c.ws(b.out);
+  }
+  pl->prof.tag = (int)pl->blocks.size() + 1;
+  const int HWl = pl->Hl * pl->Wl, Ml = B * HWl;
+  const int Cl = pl->blocks.back().d.out_ch;
+  {
+    GemmNT g = {};
+    g.a = cur; g.w = c.pk(pl->pi_last); g.y = c.ws(pl->yc); g.bias = eshift(pl->bn_last); g.act = TD3D_ACT_HSWISH;
+    g.M = Ml; g.N = n.last_ch; g.K = Cl;
+    TD3D_TRY(gemm_nt(c, g));
+    TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->pool_stats), 0, sizeof(float) * 2 * (size_t)B * n.last_ch, c.st));
+    TD3D_TRY(p_xform(c, c.ws(pl->yc), xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), nullptr, nullptr,
+                     c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
+    TD3D_K(PK_POOL, 8.0 * B * n.last_ch, launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
+  }
+  {
+    GemmNT g = {};
+    g.a = c.ws(pl->pooled); g.w = c.pk(pl->pi_fc); g.y = c.ws(pl->feat); g.bias = eshift(pl->bn_fc); g.act = TD3D_ACT_HSWISH;
+    g.M = B; g.N = n.head_ch; g.K = n.last_ch;
+    TD3D_TRY(gemm_nt(c, g));
+  }
+  *feat_out = c.ws(pl->feat);
+  return TD3D_OK;
+}
+
 static HeadsArgs heads_args(const Ctx& c, const void* feat, const int64_t* cats, const float* keep, uint64_t seed,
                             int training) {
   td3d_plan* pl = c.pl;
@@ -818,10 +912,12 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
   return TD3D_OK;
 }
 
-static int add_seg(PackTable& t, const float* src, void* dst, int rows, int cols, int transpose, int out_dtype) {
+static int add_seg(PackTable& t, const float* src, void* dst, int rows, int cols, int transpose, int out_dtype,
+                   const float* row_scale = nullptr) {
   TD3D_REQUIRE(t.n < 160, "pack table overflow");
   PackSeg& sg = t.seg[t.n++];
   sg.src = src; sg.dst = dst; sg.rows = rows; sg.cols = cols; sg.transpose = transpose; sg.out_dtype = out_dtype;
+  sg.row_scale = row_scale;
   return TD3D_OK;
 }
 
@@ -860,14 +956,31 @@ static int build_tables(td3d_plan* pl) {
     sg.gamma = c.P(bn.gamma); sg.beta = c.P(bn.beta);
     sg.rm = pl->BNB + bn.rm; sg.rv = pl->BNB + bn.rm + bn.C;
     sg.scale = c.pkf(bn.escale); sg.shift = c.pkf(bn.eshift); sg.C = bn.C;
+    sg.lin_bias = (&bn - pl->bns.data()) == pl->bn_fc ? c.P(pl->b_fc) : nullptr;   // classifier Linear bias rides in the folded shift
   }
+  // inference weights: W'[n][k] = W[n][k] * escale[n]; the consumer's bias is the BatchNorm's eshift
+  PackTable& te = pl->pack_table_eval;
+  te.n = 0;
+  auto esc = [&](int bn_idx) { return (const float*)c.pkf(pl->bns[bn_idx].escale); };
+  TD3D_TRY(add_seg(te, c.P(pl->w_stem), c.pk(pl->pi_stem), n.stem_ch, 27, 1, TD3D_F32, esc(pl->bn_stem)));
+  for (auto& b : pl->blocks) {
+    const int E = b.d.exp_ch, kk = b.d.kernel * b.d.kernel;
+    if (b.expand) TD3D_TRY(add_seg(te, c.P(b.w1), c.pk(b.pi1), E, b.d.in_ch, 0, dt, esc(b.bn1)));
+    TD3D_TRY(add_seg(te, c.P(b.wdw), c.pk(b.pidw), E, kk, 1, TD3D_F32, esc(b.bn2)));
+    TD3D_TRY(add_seg(te, c.P(b.w3), c.pk(b.pi3), b.d.out_ch, E, 0, dt, esc(b.bn3)));
+  }
+  TD3D_TRY(add_seg(te, c.P(pl->w_last), c.pk(pl->pi_last), n.last_ch, Cl, 0, dt, esc(pl->bn_last)));
+  TD3D_TRY(add_seg(te, c.P(pl->w_fc), c.pk(pl->pi_fc), n.head_ch, n.last_ch, 0, dt, esc(pl->bn_fc)));
   return TD3D_OK;
 }
 
 // weights only (every optimizer step) / weights + eval-mode BN fold (explicit td3d_pack_weights)
 static int pack_impl(const Ctx& c, bool with_bn_fold) {
   TD3D_TRY(launch_pack_table(c.pl->pack_table, c.st));
-  if (with_bn_fold) TD3D_TRY(launch_bn_fold_table(c.pl->fold_table, BN_EPS, c.st));
+  if (with_bn_fold) {
+    TD3D_TRY(launch_bn_fold_table(c.pl->fold_table, BN_EPS, c.st));
+    TD3D_TRY(launch_pack_table(c.pl->pack_table_eval, c.st));
+  }
   return TD3D_OK;
 }
 
@@ -1024,7 +1137,8 @@ int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const flo
   TD3D_REQUIRE(img && cats && kp && logits, "forward: null argument");
   Ctx c = {pl, (cudaStream_t)stream};
   const void* feat = nullptr;
-  TD3D_TRY(forward_backbone(c, img, training, &feat));
+  if (training) TD3D_TRY(forward_backbone(c, img, 1, &feat));
+  else TD3D_TRY(forward_infer(c, img, &feat));
   HeadsArgs h = heads_args(c, feat, cats, dropout_keep, seed, training);
   TD3D_K(PK_HEADS, 4.0 * pl->B * pl->net.head_ch, launch_heads_fwd(h, pl->dtype, c.st));
   TD3D_CUDA(cudaMemcpyAsync(kp, h.kp, sizeof(float) * pl->B * pl->net.num_points, cudaMemcpyDeviceToDevice, c.st));
@@ -1040,7 +1154,7 @@ int td3d_forward_export(td3d_plan* pl, const float* img, float* kp_all, float* l
   TD3D_REQUIRE(!select || (kp_sel && labels), "forward_export: select needs kp_sel and labels");
   Ctx c = {pl, (cudaStream_t)stream};
   const void* feat = nullptr;
-  TD3D_TRY(forward_backbone(c, img, 0, &feat));
+  TD3D_TRY(forward_infer(c, img, &feat));
   HeadsArgs h = heads_args(c, feat, nullptr, nullptr, 0, 0);
   h.logits = logits;
   TD3D_TRY(launch_heads_all(h, kp_all, pl->dtype, c.st));

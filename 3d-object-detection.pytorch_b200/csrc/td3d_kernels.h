@@ -58,8 +58,9 @@ struct SeBwdArgs {
 int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st);
 
 // ---- k_stem.cu ----
+// out_bias != null (inference): y = out_act(conv + out_bias[c]) with BatchNorm folded into w27xC / out_bias
 int launch_stem_fwd(const float* img, const float* w27xC, void* y, float* stats, int B, int H, int W, int C,
-                    int dtype, cudaStream_t st);
+                    int dtype, cudaStream_t st, const float* out_bias = nullptr, int out_act = TD3D_ACT_NONE);
 // dW[C,3,3,3] (reference layout) += sum_pixels gy[p,c] * patch ; gy = alpha*g + beta*y + gamma
 int launch_stem_wgrad(const float* img, const void* g, const void* y, const float* alpha, const float* beta,
                       const float* gamma, float* dw, int B, int H, int W, int C, int dtype, cudaStream_t st);
@@ -70,6 +71,8 @@ struct DwArgs {
   const float* w_taps;              // [k*k][C] fp32
   void* y; float* stats;            // output raw [B,Ho,Wo,C]; stats [B][2][C] (sum, sumsq) or null
   int B, H, W, C, k, stride;
+  const float* out_bias = nullptr;  // inference (BatchNorm folded into taps + bias): y = out_act(dw(...) + out_bias[c])
+  int out_act = TD3D_ACT_NONE;      //   (column-walker kernel only)
 };
 int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st);
 struct DwBwdArgs {
@@ -90,7 +93,8 @@ int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st);
 bool dw_walker_supported(int H, int W, int C, int k, int stride);       // k_dww.cu: small planes (W <= 32), stride 1
 int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st);
 int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st);
-int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);   // k_dwc.cu: one pass (data + weight gradient + sums)
+int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);
+int launch_dw_fwd_cw(const DwArgs& a, int dtype, cudaStream_t st);        // k_dwc.cu: column walker (optional bias + activation epilogue)   // k_dwc.cu: one pass (data + weight gradient + sums)
 
 // ---- k_gemm_simple.cu / k_gemm_tc.cu ----
 struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m,n])
@@ -101,7 +105,7 @@ struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m
   float* stats; int slots;   // [slots][2][N] or null
   int M, N, K;
   int out_f32;               // write Y as float regardless of dtype
-  int relu;                  // SIMT kernel only: y = max(y, 0) before the store
+  int act;                   // TD3D_ACT_*: y = act(acc + bias) (+ addend)   (inference: BatchNorm folded into w / bias)
 };
 int launch_gemm_nt_simt(const GemmNT& g, int dtype, cudaStream_t st);
 int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st);       // bf16 only
@@ -152,9 +156,11 @@ struct OptimArgs {
   int32_t* steps; const int32_t* present;
 };
 int launch_optim(const OptimArgs& a, cudaStream_t st);
-struct PackSeg { const float* src; void* dst; int rows, cols; int transpose; int out_dtype; };
+struct PackSeg { const float* src; void* dst; int rows, cols; int transpose; int out_dtype;
+                 const float* row_scale; };   // optional [rows]: dst = src[r][c] * row_scale[r] (eval-mode BatchNorm folded into the weights)
 struct PackTable { int n; PackSeg seg[160]; };
-struct BnFoldSeg { const float *gamma, *beta, *rm, *rv; float *scale, *shift; int C; };
+struct BnFoldSeg { const float *gamma, *beta, *rm, *rv; float *scale, *shift; int C;
+                   const float* lin_bias; };     // optional [C]: bias of the Linear in front of this BatchNorm, folded into shift
 struct BnFoldTable { int n; BnFoldSeg seg[128]; };
 int launch_pack_table(const PackTable& t, cudaStream_t st);
 int launch_bn_fold_table(const BnFoldTable& t, float eps, cudaStream_t st);

@@ -94,6 +94,7 @@ class Regressor(nn.Module):
         self._eval_fold_stale = True
         self._dropout_calls = 0
         self.dropout_seed = 0x5DEECE66D
+        self.infer_chunk = 512            # forward_to_onnx micro-batch (crops)
         self.present = None              # device i32[9]: heads that received a gradient (last backward)
 
         probe = _Plan(self, 1, 32, 32)   # shape-independent: parameter / BN tables
@@ -296,9 +297,11 @@ class Regressor(nn.Module):
         """All nine heads (model_builder.py:112-124). With select=True also applies the deployment
         consumer (utils/ie_wrappers.py:138-142) on device: returns (kp_sel[B,9,2], labels[B], logits)."""
         x = x.contiguous().float()
+        B = x.shape[0]
+        if B > self.infer_chunk:
+            return self._export_chunked(x, select)
         plan = self._plan_for(x)
         self.pack(plan, for_eval=True)
-        B = x.shape[0]
         kp_all = torch.empty(MAX_CLASSES, B, NUM_POINTS // 2, 2, device=x.device)
         logits = torch.empty(B, self.num_classes, device=x.device)
         kp_sel = torch.empty(B, NUM_POINTS // 2, 2, device=x.device) if select else None
@@ -311,6 +314,15 @@ class Regressor(nn.Module):
         if self.num_classes > 1:
             return kp_all, logits
         return kp_all, torch.zeros(B, device=x.device)
+
+    def _export_chunked(self, x, select):
+        """Large batches (BASELINE config 4: 4096 crops) run as micro-batches of `infer_chunk` crops through one plan:
+        activations of a micro-batch stay L2/HBM friendly and tensors stay below the kernels' 2^31-element index range."""
+        B, n = x.shape[0], self.infer_chunk
+        outs = [self.forward_to_onnx(x[c0:min(B, c0 + n)], select=select) for c0 in range(0, B, n)]
+        if select:
+            return tuple(torch.cat([o[i] for o in outs], dim=0) for i in range(3))
+        return torch.cat([o[0] for o in outs], dim=1), torch.cat([o[1] for o in outs], dim=0)
 
     def train(self, mode=True):
         super().train(mode)

@@ -138,40 +138,183 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def run_infer(args):
-    """Eval-mode forward with running-statistic BatchNorm, all nine heads + on-device argmax select
-    (forward_to_onnx + utils/ie_wrappers.py:138-142), inputs resident in HBM."""
-    from torchdet3d_b200 import _lib as L
+def forward_bytes_per_crop(esz):
+    """forward bytes = s(I+O) per conv/linear layer."""
+    from oracle import torch_port as tp
+    return sum(esz * (I + O) for kind, I, O, W, M in tp.layer_table(MODEL, RES))
+
+
+def cpu_reference_infer(batch, steps, warmup, threads):
+    """Reference export forward + consumer (model_builder.py:112-124, ie_wrappers.py:138-142) on host cores (oracle port)."""
+    from oracle import torch_port as tp
+    torch.set_num_threads(threads)
+    state = tp.synth_state(MODEL, seed=0)
+    imgs = torch.rand(batch, 3, RES, RES, generator=torch.Generator().manual_seed(1234))
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            kp_all, logits = tp.forward_export(state, MODEL, imgs)
+            tp.select_by_argmax(kp_all, logits)
+            times.append(time.perf_counter() - t0)
+    t = times[warmup:]
+    return sum(t) / len(t)
+
+
+def run_infer(args, rank, world, local):
+    """BASELINE configs[3]: MobileNetV3-large inference, batch 4096 crops per GPU, eval BatchNorm folded, all nine heads +
+    on-device arg-max select.  N > 1: replicas only (no communication), each rank its own 4096 crops."""
+    from torchdet3d_b200 import _lib as L, InferSession
     from torchdet3d_b200.builders import build_model
     from torchdet3d_b200.utils import Dict
     from oracle import torch_port as tp
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     L.require_b200()
     cfg = Dict(model=dict(name=MODEL, pretrained=False, num_classes=9), b200=dict(dtype=args.dtype, gemm=args.gemm))
     m = build_model(cfg)
     m.load_state_dict(tp.synth_state(MODEL, seed=0))
     m = m.to(dev).eval()
     IB = args.infer_batch
-    xs = [torch.rand(IB, 3, RES, RES, device=dev) for _ in range(2)]      # 2 x 154 MB at 256 crops: beyond the 126 MB L2
-    for i in range(4):
-        m.forward_to_onnx(xs[i & 1], select=True)
-    torch.cuda.synchronize(dev)
+    sess = InferSession(m, IB, RES, RES, chunk=args.infer_chunk, use_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(1234 + rank)
+    imgs_h = torch.rand(IB, 3, RES, RES, generator=g).pin_memory()           # 2.47 GB at 4096 crops: far beyond the 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sess.load(imgs_h)
+    for _ in range(args.warmup):
+        sess.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_it = 20
     e0.record()
-    for i in range(n_it):
-        m.forward_to_onnx(xs[i & 1], select=True)
+    for _ in range(args.steps):
+        sess.run()
     e1.record()
-    torch.cuda.synchronize(dev)
-    ims = e0.elapsed_time(e1) / n_it
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * IB / (ms_step / 1e3)
+
+    # end to end: pinned host crops -> H2D -> graph -> D2H of keypoints + labels, every step
+    kp_h = torch.zeros(IB, 9, 2).pin_memory()
+    lab_h = torch.zeros(IB, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        sess.load(imgs_h)
+        kp, labels, _ = sess.run()
+        kp_h.copy_(kp, non_blocking=True)
+        lab_h.copy_(labels, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, args.steps // 2)
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * IB / (t.item() / n_e2e / 1e3)
+
+    peak, peak_src = peaks()
     esz = 2 if args.dtype == "bf16" else 4
-    peak, _ = peaks()
-    fwd_bytes = algorithmic_bytes_per_crop(esz) / 3.0                     # forward = s(I+O) = one third of the train figure
-    out = {"value": IB / (ims / 1e3), "unit": "crops/s", "batch": IB, "ms_per_batch": ims,
-           "workload": f"{MODEL} eval forward (running-stat BN), 9 heads + argmax select, {args.dtype}, inputs resident in HBM, eager launches",
-           "roofline_frac": (fwd_bytes * IB / (peak * 1e9) * 1e3) / ims}
-    print("INFER " + json.dumps(out))
+    roofline, kinds, launches = None, {}, None
+    if rank == 0 and not args.skip_profile:
+        lib = L.lib()
+        plan = m._last_plan
+        x = sess.imgs[:sess.chunk]
+        m.forward_to_onnx(x, select=True)
+        torch.cuda.synchronize(dev)
+        L.check(lib.td3d_plan_profile(plan.handle, 1))
+        nprof = 3
+        for _ in range(nprof):
+            m.forward_to_onnx(x, select=True)
+        torch.cuda.synchronize(dev)
+        k, tot_ms = 0, 0.0
+        while True:
+            name = C.create_string_buffer(64)
+            ms_k, by_k, n_k = C.c_double(), C.c_double(), C.c_int64()
+            if lib.td3d_plan_profile_read(plan.handle, k, name, 64, C.byref(ms_k), C.byref(by_k), C.byref(n_k)) != 0:
+                break
+            if n_k.value:
+                kinds[name.value.decode()] = dict(ms_per_chunk=ms_k.value / nprof, launches_per_chunk=n_k.value / nprof,
+                                                  gbytes_per_chunk=by_k.value / nprof / 1e9,
+                                                  gbs=by_k.value / 1e6 / max(ms_k.value, 1e-9))
+                tot_ms += ms_k.value / nprof
+            k += 1
+        L.check(lib.td3d_plan_profile(plan.handle, 0))
+        for v in kinds.values():
+            v["share"] = v["ms_per_chunk"] / tot_ms
+        launches = int(sum(v["launches_per_chunk"] for v in kinds.values())) * ((IB + sess.chunk - 1) // sess.chunk)
+        top = max(kinds.items(), key=lambda kv: kv[1]["ms_per_chunk"])
+        roofline = {"bound": "hbm", "kernel": top[0], "achieved": top[1]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": top[1]["gbs"] / peak, "traffic": None, "peak_source": peak_src, "share_of_step": top[1]["share"],
+                    "how": "CUDA events around every launch of this kernel kind on the launching stream, eager pass over one micro-batch"}
+    step_bytes = forward_bytes_per_crop(esz) * IB
+    step_roof_ms = step_bytes / (peak * 1e9) * 1e3
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        sec = cpu_reference_infer(64, 2, 1, threads)
+        cpu = {"value": 64 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"2 x 64 crops of the same {MODEL} export forward + arg-max select, fp32, oracle/torch_port.py"}
+    if rank == 0:
+        line = {
+            "metric": "infer_crops_per_s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": f"{MODEL} regressor inference (eval BatchNorm folded, 9 heads + arg-max select), batch {IB}/GPU in "
+                                   f"micro-batches of {sess.chunk}, {RES}x{RES} synthetic crops (BASELINE configs[3])",
+                       "per_gpu_batch": IB, "parallelism": f"replicas x{world}", "cuda_graph": not args.no_graph,
+                       "l2": "inputs (2.47 GB fp32 crops per step) exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": imgs_h.numel() * 4,
+                    "d2h_bytes_per_step": kp_h.numel() * 4 + lab_h.numel() * 8},
+            "gpu_launches": (launches or 0) * args.steps,
+            "roofline": roofline,
+            "step_roofline": {"algorithmic_gbytes_per_step": step_bytes / 1e9, "roofline_ms": step_roof_ms,
+                              "frac": step_roof_ms / ms_step, "peak_gbs": peak, "peak_source": peak_src},
+            "kernel_kinds": kinds, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        sess._graph = None
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+def run_reference_infer(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 64
+    sec = cpu_reference_infer(batch, args.steps, args.warmup, threads)
+    v = batch / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "infer_crops_per_s", "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL} export forward + arg-max select, {RES}x{RES} crops, CPU sample of {batch} crops/step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} crops, oracle/torch_port.py"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
@@ -187,10 +330,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
     ap.add_argument("--skip-infer", action="store_true")
-    ap.add_argument("--infer-only", action="store_true", help="(internal) run only the inference leg and print 'INFER {json}'")
-    ap.add_argument("--infer-batch", type=int, default=256,
-                    help="inference leg batch (BASELINE configs[3] says 4096; the depthwise kernels use 32-bit element offsets, which "
-                         "caps the widest layer at 2048 crops per launch, and batches above the 256 exercised by the tests are unverified)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1] (default, the driver's line); infer = BASELINE configs[3]")
+    ap.add_argument("--infer-batch", type=int, default=4096, help="inference batch per GPU (BASELINE configs[3]: 4096 crops)")
+    ap.add_argument("--infer-chunk", type=int, default=256, help="micro-batch the inference session runs the batch in")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch profile (kind, layer tag, ms, GB/s) as CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -199,10 +342,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.mode == "infer":
+            run_reference_infer(args, rank)
+        else:
+            run_reference(args, rank, world)
         return
-    if args.infer_only:
-        run_infer(args)
+    if args.mode == "infer":
+        run_infer(args, rank, world, local)
         return
 
     from torchdet3d_b200 import _lib as L
@@ -390,10 +536,16 @@ def main():
     if rank == 0 and world == 1 and not args.skip_infer:
         import subprocess
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--infer-only", "--infer-batch", str(args.infer_batch),
-                                "--dtype", args.dtype, "--gemm", args.gemm], capture_output=True, text=True, timeout=600)
-            lines = [l for l in p.stdout.splitlines() if l.startswith("INFER ")]
-            infer = json.loads(lines[-1][6:]) if lines else {"error": (p.stderr or "no output")[-300:]}
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "infer", "--infer-batch", str(args.infer_batch),
+                                "--infer-chunk", str(args.infer_chunk), "--dtype", args.dtype, "--gemm", args.gemm, "--steps", "5",
+                                "--warmup", "3", "--skip-cpu"], capture_output=True, text=True, timeout=600, env=env)
+            lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            if lines:
+                full = json.loads(lines[-1])
+                infer = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "step_roofline")}
+            else:
+                infer = {"error": (p.stderr or "no output")[-300:]}
         except Exception as ex:
             infer = {"error": str(ex)[:300]}
 

@@ -16,6 +16,18 @@ for k,v in sorted(d['kernel_kinds'].items(), key=lambda kv:-kv[1]['ms_per_step']
 PY
 done
 grep dw_bwd gpurun_out/launches_pf6.csv
+timeout 900 python -m pytest tests/test_gpu_infer.py -q 2>&1 | tail -30 > gpurun_out/t_infer.log; tail -n 20 gpurun_out/t_infer.log | cut -c1-400
+timeout 600 python bench.py --mode infer --steps 10 --warmup 3 > gpurun_out/bench_infer.json 2> gpurun_out/bench_infer.err; echo "infer rc=$?"; tail -n 3 gpurun_out/bench_infer.err | cut -c1-400
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_infer.json').read().strip().splitlines()[-1])
+    print('infer', d['value'], d['ms_per_step'], d['e2e'], d['step_roofline'], d['cpu_baseline'])
+    for k,v in sorted(d['kernel_kinds'].items(), key=lambda kv:-kv[1]['ms_per_chunk']):
+        print(f"  {k:16s} {v['ms_per_chunk']:8.3f} ms  n={v['launches_per_chunk']:5.0f}  {v['gbs']:8.1f} GB/s")
+except Exception as e:
+    print('infer parse failed', e)
+PY
 for b in 512 1024; do
   CUDA_LAUNCH_BLOCKING=1 timeout 600 python tests/export_bigb.py $b > gpurun_out/bigb_$b.log 2>&1; echo "bigb $b rc=$?"; tail -n 4 gpurun_out/bigb_$b.log | cut -c1-600
 done

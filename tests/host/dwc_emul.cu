@@ -136,9 +136,92 @@ static int run_all() {
   return bad;
 }
 
+
+// ---- forward ----------------------------------------------------------------------------------------------------
+struct HostFwdSink {
+  std::vector<double>* st; int C;
+  void stat(int b, int which, int c, float v) { (*st)[((size_t)b * 2 + which) * C + c] += v; }
+};
+
+template <typename T, int K, int S, int R, int CPT>
+static int run_fwd_case(int B, int H, int W, int C, int act, bool with_xf, int out_act, bool with_bias, int lanes_req) {
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1, KK = K * K, PAD = (K - 1) / 2;
+  std::vector<T> x((size_t)B * H * W * C), y((size_t)B * Ho * Wo * C);
+  std::vector<float> scale(C), shift(C), se(B * C), taps(KK * C), bias(C);
+  for (auto& v : x) v = cvt<T>(frand() * 3);
+  for (auto& v : scale) v = (float)(frand() * 0.5 + 1.0);
+  for (auto& v : shift) v = (float)frand() * 0.5f;
+  for (auto& v : se) v = (float)(frand() * 0.25 + 0.75);
+  for (auto& v : taps) v = (float)frand() * 0.3f;
+  for (auto& v : bias) v = (float)frand();
+  for (auto& v : y) v = cvt<T>(777.0);
+  DwcFwdArgs a;
+  a.x = x.data(); a.scale = with_xf ? scale.data() : nullptr; a.shift = with_xf ? shift.data() : nullptr;
+  a.se = with_xf ? se.data() : nullptr; a.act = act; a.w_taps = taps.data();
+  a.out_bias = with_bias ? bias.data() : nullptr; a.out_act = out_act; a.y = y.data();
+  std::vector<float> dummy(1);
+  a.stats = dummy.data();
+  a.B = B; a.H = H; a.W = W; a.C = C; a.Ho = Ho; a.Wo = Wo;
+  a.n_bands = (Ho + R - 1) / R; a.n_items = B * a.n_bands;
+  a.item_lanes = lanes_req < a.n_items ? lanes_req : a.n_items;
+  a.cw = 0; a.n_cchunks = 0; a.ilb = 0; a.pf_dist = 0;
+  std::vector<double> st((size_t)B * 2 * C, 0.0), rst((size_t)B * 2 * C, 0.0);
+  HostFwdSink sink = {&st, C};
+  for (int c = 0; c < C; c += CPT)
+    for (int il = 0; il < a.item_lanes; ++il) DwcFwd<T, K, S, R, CPT>::thread_main(a, c, il, sink);
+  double err = 0, mx = 0;
+  for (int b = 0; b < B; ++b)
+    for (int py = 0; py < Ho; ++py)
+      for (int px = 0; px < Wo; ++px)
+        for (int c = 0; c < C; ++c) {
+          double acc = with_bias ? bias[c] : 0.0;
+          for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) {
+              int qy = S * py + i - PAD, qx = S * px + j - PAD;
+              if (qy < 0 || qx < 0 || qy >= H || qx >= W) continue;
+              double xr = tof(x[(((size_t)b * H + qy) * W + qx) * C + c]);
+              double t = with_xf ? (double)se[b * C + c] * ((double)scale[c] * xr + shift[c]) : xr;
+              acc += (double)taps[(i * K + j) * C + c] * act_ref(t, act);
+            }
+          double ref = act_ref(acc, out_act);
+          double got = tof(y[(((size_t)b * Ho + py) * Wo + px) * C + c]);
+          err = fmax(err, fabs(got - ref)); mx = fmax(mx, fabs(ref));
+          rst[((size_t)b * 2) * C + c] += got;
+          rst[((size_t)b * 2 + 1) * C + c] += got * got;
+        }
+  double err_st = 0, max_st = 0;
+  for (size_t i = 0; i < st.size(); ++i) { err_st = fmax(err_st, fabs(st[i] - rst[i])); max_st = fmax(max_st, fabs(rst[i])); }
+  const bool is_bf = sizeof(T) == 2;
+  const bool ok = err / mx < (is_bf ? 6e-3 : 2e-5) && err_st / fmax(max_st, 1e-9) < 2e-4;
+  printf("%s FWD T=%s K=%d S=%d R=%d CPT=%d B=%d %dx%d C=%d act=%d xf=%d oact=%d bias=%d lanes=%d: y %.2e st %.2e\n", ok ? "ok  " : "FAIL",
+         is_bf ? "bf16" : "f32", K, S, R, CPT, B, H, W, C, act, (int)with_xf, out_act, (int)with_bias, a.item_lanes, err / mx,
+         err_st / fmax(max_st, 1e-9));
+  return ok ? 0 : 1;
+}
+
+template <typename T>
+static int run_all_fwd() {
+  int bad = 0;
+  const int shapes[][4] = {{2, 14, 14, 16}, {3, 7, 7, 24}, {2, 29, 23, 8}, {1, 56, 56, 8}, {2, 1, 5, 16}, {3, 2, 3, 8}, {1, 8, 8, 8}, {2, 5, 1, 8}};
+  for (auto& s : shapes) {
+    for (int v = 0; v < 3; ++v) {
+      const int act = v, oact = v == 0 ? 2 : 0;
+      const bool xf = v != 0, bias = v == 0;
+      bad += run_fwd_case<T, 3, 1, 4, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 5);
+      bad += run_fwd_case<T, 3, 1, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 1000);
+      bad += run_fwd_case<T, 3, 2, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 3);
+      bad += run_fwd_case<T, 3, 2, 1, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 1000);
+      bad += run_fwd_case<T, 5, 1, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 4);
+      bad += run_fwd_case<T, 5, 2, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 1000);
+      bad += run_fwd_case<T, 5, 2, 1, 1>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 7);
+    }
+  }
+  return bad;
+}
+
 int main() {
   srand(1234);
-  int bad = run_all<float>() + run_all<bf16>();
+  int bad = run_all<float>() + run_all<bf16>() + run_all_fwd<float>() + run_all_fwd<bf16>();
   printf("%s (%d failing cases)\n", bad ? "DWC_EMUL FAILED" : "DWC_EMUL OK", bad);
   return bad ? 1 : 0;
 }

@@ -1,0 +1,74 @@
+"""Inference path (BASELINE config 4): eval-mode BatchNorm folded into the weights, activations in the producers'
+epilogues, micro-batched + CUDA-graph `InferSession`, against the CPU oracle's forward_export + select_by_argmax
+(= ModelWrapper.forward_to_onnx, model_builder.py:112-124, + utils/ie_wrappers.py:138-142)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_port as tp                                   # noqa: E402
+from test_gpu_model import make_model, t2n, rel, DEV                  # noqa: E402
+from torchdet3d_b200 import InferSession                              # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["mobilenetv3_small", "mobilenetv3_large"])
+def test_infer_session_fp32_matches_oracle_bit_exact_labels(name):
+    case = dict(model=name, optim=dict(name="adam"), loss=None)
+    _, model = make_model(case)
+    B, res = 40, 96
+    x = torch.rand(B, 3, res, res, generator=torch.Generator().manual_seed(3))
+    kp_all_ref, logits_ref = tp.forward_export(tp.synth_state(name, seed=0), name, x)
+    ref_sel, ref_lab = tp.select_by_argmax(kp_all_ref, logits_ref)
+    sess = InferSession(model, B, res, res, chunk=16)          # 16 + 16 + 8: a partial last micro-batch
+    for it in range(3):                                        # eager, capture, replay
+        kp, labels, logits = sess(x)
+        torch.cuda.synchronize()
+        assert np.array_equal(labels.cpu().numpy(), ref_lab.numpy()), it          # arg-max class bit-exact
+        assert rel(t2n(kp), ref_sel.numpy()) < 1e-3 and rel(t2n(logits), logits_ref.numpy()) < 1e-3, it
+    assert sess._graph is not None
+    # the eager public call takes the same micro-batched route above `infer_chunk`
+    model.infer_chunk = 16
+    kp_all, lg = model.forward_to_onnx(x.to(DEV))
+    assert kp_all.shape == (9, B, 9, 2)
+    assert rel(t2n(kp_all), kp_all_ref.numpy()) < 1e-3 and rel(t2n(lg), logits_ref.numpy()) < 1e-3
+    kp2, lab2, _ = model.forward_to_onnx(x.to(DEV), select=True)
+    assert np.array_equal(lab2.cpu().numpy(), ref_lab.numpy()) and rel(t2n(kp2), ref_sel.numpy()) < 1e-3
+
+
+def test_infer_session_weights_refresh_without_recapture():
+    case = dict(model="mobilenetv3_small", optim=dict(name="adam"), loss=None)
+    _, model = make_model(case)
+    x = torch.rand(8, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    sess = InferSession(model, 8, 64, 64, chunk=8)
+    for _ in range(3):
+        kp0 = sess(x)[0].clone()
+    state = tp.synth_state("mobilenetv3_small", seed=1)
+    model.load_state_dict(state)                               # new weights + running statistics, same arenas
+    kp1 = sess(x)[0].clone()
+    ref = tp.select_by_argmax(*tp.forward_export(state, "mobilenetv3_small", x))[0]
+    assert rel(t2n(kp1), ref.numpy()) < 1e-3 and not torch.allclose(kp0, kp1)
+
+
+def test_config4_large_batch_bf16_subsample_vs_oracle():
+    """MobileNetV3-large, 224x224, bf16/tcgen05, 1100 crops (> the 1024 that aborted in round 1) in micro-batches of 256.
+    Stated bf16 bounds: keypoints <= 1e-2 abs (eval), arg-max agreement >= 85 % (near-ties flip in bf16)."""
+    name = "mobilenetv3_large"
+    case = dict(model=name, optim=dict(name="adam"), loss=None)
+    _, model = make_model(case, "bf16", "auto")
+    B = 1100
+    x = torch.rand(B, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    sess = InferSession(model, B, 224, 224, chunk=256)
+    for _ in range(2):
+        kp, labels, logits = sess(x)
+    torch.cuda.synchronize()
+    idx = torch.linspace(0, B - 1, 24).long()
+    kp_all_ref, logits_ref = tp.forward_export(tp.synth_state(name, seed=0), name, x[idx])
+    ref_sel, ref_lab = tp.select_by_argmax(kp_all_ref, logits_ref)
+    got_lab = labels[idx.to(DEV)].cpu()
+    agree = (got_lab == ref_lab).float().mean().item()
+    assert agree >= 0.85, agree
+    same = got_lab == ref_lab                                   # keypoints compared where the same head was selected
+    err = (kp[idx.to(DEV)].cpu()[same] - ref_sel[same]).abs().max().item()
+    assert err < 1e-2, err
+    assert rel(t2n(logits[idx.to(DEV)]), logits_ref.numpy()) < 3e-2
