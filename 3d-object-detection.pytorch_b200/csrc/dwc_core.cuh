@@ -19,6 +19,7 @@
 //
 // The per-thread body is __host__ __device__ so tests/host/dwc_emul.cu can run the exact index logic on the CPU.
 #pragma once
+#include <math.h>
 #include <string.h>
 
 #include "td3d_common.cuh"
@@ -74,7 +75,7 @@ __host__ __device__ __forceinline__ float dv_get(const float2& v, int i) { retur
 __host__ __device__ __forceinline__ float dv_get(const float& v, int) { return v; }
 
 // activation constants: act(u) = u * sat(a*u + b);  act'(u) = u <= lo ? 0 : (u >= hi ? 1 : da*u + db)
-struct DwcAct { float a, b, da, db, lo, hi; };
+struct DwcAct { float a, b, da, db, lo, hi; int silu; };
 __host__ __device__ inline DwcAct dwc_make_act(int act) {
   DwcAct k;
   const bool hs = act == TD3D_ACT_HSWISH, re = act == TD3D_ACT_RELU;
@@ -84,11 +85,23 @@ __host__ __device__ inline DwcAct dwc_make_act(int act) {
   k.db = hs ? 0.5f : 1.f;
   k.lo = hs ? -3.f : (re ? 0.f : -3.0e38f);
   k.hi = hs ? 3.f : 3.0e38f;
+  k.silu = act == TD3D_ACT_SILU;
   return k;
 }
 __host__ __device__ __forceinline__ float dwc_sat(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
-__host__ __device__ __forceinline__ float dwc_act1(float u, const DwcAct& k) { return u * dwc_sat(u * k.a + k.b); }
+__host__ __device__ __forceinline__ float dwc_sigmoid(float u) {
+#ifdef __CUDA_ARCH__
+  return 1.f / (1.f + __expf(-u));
+#else
+  return 1.f / (1.f + expf(-u));
+#endif
+}
+__host__ __device__ __forceinline__ float dwc_act1(float u, const DwcAct& k) {
+  if (k.silu) return u * dwc_sigmoid(u);
+  return u * dwc_sat(u * k.a + k.b);
+}
 __host__ __device__ __forceinline__ float dwc_actd1(float u, const DwcAct& k) {
+  if (k.silu) { const float s = dwc_sigmoid(u); return s * (1.f + u * (1.f - s)); }
   float d = u * k.da + k.db;
   d = u >= k.hi ? 1.f : d;
   return u <= k.lo ? 0.f : d;

@@ -9,9 +9,21 @@
 
 namespace td3d {
 
+// TD3D_DW_FWD_CW=1 (A/B measurements) routes every forward depthwise conv through the column walker.
+static int dw_fwd_cw() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TD3D_DW_FWD_CW");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw fwd: C=%d must be a multiple of 8", a.C);
   TD3D_REQUIRE((a.k == 3 || a.k == 5) && (a.stride == 1 || a.stride == 2), "dw fwd: unsupported kernel=%d stride=%d", a.k, a.stride);
+  // SiLU inputs (EfficientNet) and the bias + activation epilogue of inference exist only in the column walker
+  if (a.xf.act == TD3D_ACT_SILU || a.out_bias || a.out_act != TD3D_ACT_NONE || dw_fwd_cw()) return launch_dw_fwd_cw(a, dtype, st);
   if (dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return launch_dw_fwd_walker(a, dtype, st);
   return launch_dw_fwd_v2(a, dtype, st);
 }

@@ -32,15 +32,14 @@ __device__ __forceinline__ float warp_transpose_sum32(float v[32]) {
 template <typename T>
 __global__ void __launch_bounds__(ST_TH * ST_TW)
 stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* __restrict__ y,
-                float* __restrict__ stats, int H, int W, int Ho, int Wo, const float* __restrict__ out_bias, int out_act) {
+                float* __restrict__ stats, int H, int W, int Ho, int Wo, int C, const float* __restrict__ out_bias,
+                int out_act) {
   __shared__ float s_in[3][ST_IH][ST_IW + 1];
   __shared__ float s_w[27 * ST_C];
   __shared__ float s_acc[2 * ST_C];
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
   const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-  for (int i = threadIdx.x; i < 27 * ST_C; i += blockDim.x) s_w[i] = w[i];
-  if (threadIdx.x < 2 * ST_C) s_acc[threadIdx.x] = 0.f;
   for (int i = threadIdx.x; i < 3 * ST_IH * ST_IW; i += blockDim.x) {
     int ci = i / (ST_IH * ST_IW), r = (i / ST_IW) % ST_IH, c = i % ST_IW;
     int iy = iy0 + r, ix = ix0 + c;
@@ -48,62 +47,73 @@ stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* _
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix);
     s_in[ci][r][c] = v;
   }
-  __syncthreads();
   const int ty = threadIdx.x / ST_TW, tx = threadIdx.x % ST_TW;
   const int oy = oy0 + ty, ox = ox0 + tx;
   const bool valid = oy < Ho && ox < Wo;
-  float acc[ST_C];
-#pragma unroll
-  for (int c = 0; c < ST_C; ++c) acc[c] = 0.f;
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float x = s_in[ci][2 * ty + ky][2 * tx + kx];
-        const float* wr = s_w + ((ci * 3 + ky) * 3 + kx) * ST_C;
-#pragma unroll
-        for (int c = 0; c < ST_C; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
-      }
-  if (out_bias) {      // inference: BatchNorm folded into w / out_bias, activation before the single store
-#pragma unroll
-    for (int c = 0; c < ST_C; ++c) acc[c] = act_fwd(acc[c] + __ldg(out_bias + c), out_act);
-  }
-  float red[32];
-  if (valid) {
-    T* yo = y + (((size_t)b * Ho + oy) * Wo + ox) * ST_C;
-    store8(yo, acc);
-    store8(yo + 8, acc + 8);
-    // statistics are taken on the values as stored (bf16-rounded in bf16 mode), i.e. exactly the
-    // tensor the consumer will normalise
-#pragma unroll
-    for (int c = 0; c < ST_C; ++c) {
-      float v = to_f(from_f<T>(acc[c]));
-      red[c] = v;
-      red[ST_C + c] = v * v;
+  // the image tile is staged once; the C output channels (16 for MobileNetV3, 32 / 40 for EfficientNet-B0 / B3) are
+  // produced in slices of ST_C
+  for (int c0 = 0; c0 < C; c0 += ST_C) {
+    __syncthreads();                         // s_in ready (first slice) / previous slice done with s_w, s_acc
+    for (int i = threadIdx.x; i < 27 * ST_C; i += blockDim.x) {
+      const int c = c0 + i % ST_C;
+      s_w[i] = c < C ? w[(i / ST_C) * C + c] : 0.f;
     }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) red[c] = 0.f;
-  }
-  if (stats) {
-    float tot = warp_transpose_sum32(red);
-    atomicAdd(&s_acc[threadIdx.x & 31], tot);
+    if (threadIdx.x < 2 * ST_C) s_acc[threadIdx.x] = 0.f;
     __syncthreads();
-    if (threadIdx.x < 2 * ST_C) atomicAdd(&stats[(size_t)b * 2 * ST_C + threadIdx.x], s_acc[threadIdx.x]);
+    float acc[ST_C];
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float x = s_in[ci][2 * ty + ky][2 * tx + kx];
+          const float* wr = s_w + ((ci * 3 + ky) * 3 + kx) * ST_C;
+#pragma unroll
+          for (int c = 0; c < ST_C; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+        }
+    if (out_bias) {      // inference: BatchNorm folded into w / out_bias, activation before the single store
+#pragma unroll
+      for (int c = 0; c < ST_C; ++c) acc[c] = c0 + c < C ? act_fwd(acc[c] + __ldg(out_bias + c0 + c), out_act) : 0.f;
+    }
+    float red[32];
+    if (valid) {
+      T* yo = y + (((size_t)b * Ho + oy) * Wo + ox) * C + c0;
+      store8(yo, acc);
+      if (c0 + 8 < C) store8(yo + 8, acc + 8);
+      // statistics are taken on the values as stored (bf16-rounded in bf16 mode), i.e. exactly the
+      // tensor the consumer will normalise
+#pragma unroll
+      for (int c = 0; c < ST_C; ++c) {
+        float v = to_f(from_f<T>(acc[c]));
+        red[c] = v;
+        red[ST_C + c] = v * v;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) red[c] = 0.f;
+    }
+    if (stats) {
+      float tot = warp_transpose_sum32(red);
+      atomicAdd(&s_acc[threadIdx.x & 31], tot);
+      __syncthreads();
+      if (threadIdx.x < 2 * ST_C && c0 + (threadIdx.x % ST_C) < C)
+        atomicAdd(&stats[((size_t)b * 2 + threadIdx.x / ST_C) * C + c0 + threadIdx.x % ST_C], s_acc[threadIdx.x]);
+    }
   }
 }
 
 int launch_stem_fwd(const float* img, const float* w27xC, void* y, float* stats, int B, int H, int W, int C,
                     int dtype, cudaStream_t st, const float* out_bias, int out_act) {
-  TD3D_REQUIRE(C == ST_C, "stem: only %d output channels supported (got %d)", ST_C, C);
+  TD3D_REQUIRE(C % 8 == 0 && C >= 8 && C <= 64, "stem: output channels must be a multiple of 8 in 8..64 (got %d)", C);
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   dim3 grid(ceil_div(Wo, ST_TW), ceil_div(Ho, ST_TH), B);
   if (dtype == TD3D_BF16)
-    stem_fwd_kernel<bf16><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (bf16*)y, stats, H, W, Ho, Wo, out_bias, out_act);
+    stem_fwd_kernel<bf16><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (bf16*)y, stats, H, W, Ho, Wo, C, out_bias, out_act);
   else
-    stem_fwd_kernel<float><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (float*)y, stats, H, W, Ho, Wo, out_bias, out_act);
+    stem_fwd_kernel<float><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (float*)y, stats, H, W, Ho, Wo, C, out_bias, out_act);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -151,7 +161,7 @@ template <typename T>
 __global__ void __launch_bounds__(SW_THREADS, 2)
 stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const T* __restrict__ y,
                   const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gamma,
-                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int tiles_per_cta) {
+                  float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int tiles_per_cta, int C) {
   __shared__ float s_in[3 * ST_IH * ST_IW];      // [ci][row][col], odd row stride
   __shared__ __align__(16) float s_gy[ST_TH * ST_TW][SW_GS];
   __shared__ float s_al[ST_C], s_be[ST_C], s_ga[ST_C];
@@ -163,7 +173,9 @@ stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const 
   const int ci = warp / 3, ky = warp % 3;
   const bool has_gy = tid < ST_TH * ST_TW * 2;
   const int gp = tid >> 1, ghalf = tid & 1;      // (pixel, 8-channel half) of the staged gy vector
-  if (tid < ST_C) s_be[tid] = beta[tid];
+  const int c0 = blockIdx.y * ST_C;              // this CTA's 16-channel slice of the C output channels
+  const bool half_ok = c0 + ghalf * 8 < C;
+  if (tid < ST_C) s_be[tid] = c0 + tid < C ? beta[c0 + tid] : 0.f;
   float acc[3][ST_C];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -193,8 +205,8 @@ stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const 
     r_live = false;
     if (has_gy) {
       const int oy = oy0 + gp / ST_TW, ox = ox0 + gp % ST_TW;
-      if (oy < Ho && ox < Wo) {
-        const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * ST_C + ghalf * 8;
+      if (oy < Ho && ox < Wo && half_ok) {
+        const size_t off = (((size_t)b * Ho + oy) * Wo + ox) * C + c0 + ghalf * 8;
         r_gy.load(g + off, y + off);
         r_live = true;
       }
@@ -207,8 +219,8 @@ stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const 
     const int b = tile / (tiles_x * tiles_y);
     if (b != cur_b) {           // CTA-uniform; the previous readers of s_al/s_ga are two barriers behind
       if (tid < ST_C) {
-        s_al[tid] = alpha[(size_t)b * ST_C + tid];
-        s_ga[tid] = gamma[(size_t)b * ST_C + tid];
+        s_al[tid] = c0 + tid < C ? alpha[(size_t)b * C + c0 + tid] : 0.f;
+        s_ga[tid] = c0 + tid < C ? gamma[(size_t)b * C + c0 + tid] : 0.f;
       }
       cur_b = b;
       __syncthreads();
@@ -260,22 +272,22 @@ stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const 
 #pragma unroll
     for (int c = 0; c < ST_C; ++c) {
       const float r = warp_sum(acc[k][c]);
-      if (lane == 0) atomicAdd(&dw[c * 27 + ci * 9 + ky * 3 + k], r);
+      if (lane == 0 && c0 + c < C) atomicAdd(&dw[(c0 + c) * 27 + ci * 9 + ky * 3 + k], r);
     }
 }
 
 int launch_stem_wgrad(const float* img, const void* g, const void* y, const float* alpha, const float* beta,
                       const float* gamma, float* dw, int B, int H, int W, int C, int dtype, cudaStream_t st) {
-  TD3D_REQUIRE(C == ST_C, "stem wgrad: only %d output channels supported", ST_C);
+  TD3D_REQUIRE(C % 8 == 0 && C >= 8 && C <= 64, "stem wgrad: output channels must be a multiple of 8 in 8..64 (got %d)", C);
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   int n_tiles = B * ceil_div(Wo, ST_TW) * ceil_div(Ho, ST_TH);
   int ctas = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
   int per = ceil_div(n_tiles, ctas);
-  int grid = ceil_div(n_tiles, per);
+  dim3 grid(ceil_div(n_tiles, per), ceil_div(C, ST_C));
   if (dtype == TD3D_BF16)
-    stem_wgrad_kernel<bf16><<<grid, SW_THREADS, 0, st>>>(img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per);
+    stem_wgrad_kernel<bf16><<<grid, SW_THREADS, 0, st>>>(img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C);
   else
-    stem_wgrad_kernel<float><<<grid, SW_THREADS, 0, st>>>(img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per);
+    stem_wgrad_kernel<float><<<grid, SW_THREADS, 0, st>>>(img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -47,6 +47,8 @@ struct Bn {
 struct Block {
   td3d_block_desc d;
   bool expand, residual;
+  bool se_post;                         // SE after the activation (dw-first MobileNetV3 block; every EfficientNet block)
+  int act;                              // TD3D_ACT_* of this block
   int Hin, Win, Hout, Wout;
   int bn1, bn2, bn3;                    // indices into bns (-1 if absent)
   int64_t w1 = -1, wdw = -1, w3 = -1;   // param offsets
@@ -94,6 +96,8 @@ struct td3d_plan {
   size_t packed_bytes = 0, ws_bytes = 0;
   // stem / tail
   int H1, W1;                            // stem output resolution
+  int stem_act, se_kind;                 // stem / last-conv activation; 0 = h_sigmoid/ReLU SE (k_se.cu), 1 = sigmoid/SiLU SE (k_se_gen.cu)
+  bool has_fc;                           // classifier Linear + BatchNorm1d (MobileNetV3 only, model_builder.py:117-118)
   int bn_stem, bn_last, bn_fc;
   int64_t w_stem, w_last, w_fc, b_fc, w_reg0, w_cls, b_cls;
   int64_t head_stride;
@@ -172,51 +176,91 @@ static int build(td3d_plan* pl) {
   pl->H1 = (pl->H - 1) / 2 + 1;
   pl->W1 = (pl->W - 1) / 2 + 1;
   // ---- parameter table in reference state_dict order ----
+  const bool eff = n.arch == TD3D_ARCH_EFFICIENTNET;
+  pl->stem_act = eff ? TD3D_ACT_SILU : TD3D_ACT_HSWISH;
+  pl->se_kind = eff ? 1 : 0;
+  pl->has_fc = !eff;
   pl->w_stem = add_param(pl, "features.0.0.weight", {n.stem_ch, 3, 3, 3});
   pl->bn_stem = add_bn(pl, "features.0.1", n.stem_ch);
   int h = pl->H1, w = pl->W1;
   int cin = n.stem_ch;
+  int last_stage = 0;
   for (int i = 0; i < n.n_blocks; ++i) {
     Block b;
     b.d = pl->block_descs[i];
     TD3D_REQUIRE(b.d.in_ch == cin, "block %d: in_ch=%d does not chain from %d", i, b.d.in_ch, cin);
     TD3D_REQUIRE(b.d.in_ch % 8 == 0 && b.d.exp_ch % 8 == 0 && b.d.out_ch % 8 == 0, "block %d: channels must be multiples of 8", i);
     TD3D_REQUIRE((b.d.kernel == 3 || b.d.kernel == 5) && (b.d.stride == 1 || b.d.stride == 2), "block %d: bad kernel/stride", i);
+    TD3D_REQUIRE(b.d.use_hs >= 0 && b.d.use_hs <= 2, "block %d: bad activation code %d", i, b.d.use_hs);
     b.expand = b.d.in_ch != b.d.exp_ch;
     b.residual = b.d.stride == 1 && b.d.in_ch == b.d.out_ch;
+    b.act = b.d.use_hs == 2 ? TD3D_ACT_SILU : (b.d.use_hs == 1 ? TD3D_ACT_HSWISH : TD3D_ACT_RELU);
+    b.se_post = b.d.use_se && (eff || !b.expand);
     b.Hin = h; b.Win = w;
     b.Hout = (h - 1) / b.d.stride + 1; b.Wout = (w - 1) / b.d.stride + 1;
-    std::string pre = "features." + std::to_string(i + 1) + ".conv.";
     b.first_param = pl->param_floats;
     b.bn1 = -1;
-    int j = 0;
-    if (b.expand) {
-      b.w1 = add_param(pl, pre + "0.weight", {b.d.exp_ch, b.d.in_ch, 1, 1});
-      b.bn1 = add_bn(pl, pre + "1", b.d.exp_ch);
-      j = 3;
+    if (!eff) {
+      // torchdet3d/models/mobilenetv3.py:133-160: features.<i+1>.conv.<j>
+      std::string pre = "features." + std::to_string(i + 1) + ".conv.";
+      int j = 0;
+      if (b.expand) {
+        b.w1 = add_param(pl, pre + "0.weight", {b.d.exp_ch, b.d.in_ch, 1, 1});
+        b.bn1 = add_bn(pl, pre + "1", b.d.exp_ch);
+        j = 3;
+      }
+      b.wdw = add_param(pl, pre + std::to_string(j) + ".weight", {b.d.exp_ch, 1, b.d.kernel, b.d.kernel});
+      b.bn2 = add_bn(pl, pre + std::to_string(j + 1), b.d.exp_ch);
+      int se_idx = b.expand ? j + 2 : j + 3, pw_idx = b.expand ? 7 : 4;
+      if (b.d.use_se) {
+        std::string sp = pre + std::to_string(se_idx) + ".fc.";
+        b.se_w1 = add_param(pl, sp + "0.weight", {b.d.se_hidden, b.d.exp_ch});
+        b.se_b1 = add_param(pl, sp + "0.bias", {b.d.se_hidden});
+        b.se_w2 = add_param(pl, sp + "2.weight", {b.d.exp_ch, b.d.se_hidden});
+        b.se_b2 = add_param(pl, sp + "2.bias", {b.d.exp_ch});
+      }
+      b.w3 = add_param(pl, pre + std::to_string(pw_idx) + ".weight", {b.d.out_ch, b.d.exp_ch, 1, 1});
+      b.bn3 = add_bn(pl, pre + std::to_string(pw_idx + 1), b.d.out_ch);
+    } else {
+      // torchvision MBConv: features.<stage>.<index>.block.<k> = [expand Conv2dNormActivation], depthwise
+      // Conv2dNormActivation, SqueezeExcitation (fc1 / fc2 are 1x1 convs), project Conv2dNormActivation
+      TD3D_REQUIRE(b.d.use_se && b.d.se_hidden >= 1, "block %d: EfficientNet blocks carry an SE layer", i);
+      std::string pre = "features." + std::to_string(b.d.name_stage) + "." + std::to_string(b.d.name_index) + ".block.";
+      int k = 0;
+      if (b.expand) {
+        b.w1 = add_param(pl, pre + "0.0.weight", {b.d.exp_ch, b.d.in_ch, 1, 1});
+        b.bn1 = add_bn(pl, pre + "0.1", b.d.exp_ch);
+        k = 1;
+      }
+      b.wdw = add_param(pl, pre + std::to_string(k) + ".0.weight", {b.d.exp_ch, 1, b.d.kernel, b.d.kernel});
+      b.bn2 = add_bn(pl, pre + std::to_string(k) + ".1", b.d.exp_ch);
+      std::string sp = pre + std::to_string(k + 1) + ".";
+      b.se_w1 = add_param(pl, sp + "fc1.weight", {b.d.se_hidden, b.d.exp_ch, 1, 1});
+      b.se_b1 = add_param(pl, sp + "fc1.bias", {b.d.se_hidden});
+      b.se_w2 = add_param(pl, sp + "fc2.weight", {b.d.exp_ch, b.d.se_hidden, 1, 1});
+      b.se_b2 = add_param(pl, sp + "fc2.bias", {b.d.exp_ch});
+      b.w3 = add_param(pl, pre + std::to_string(k + 2) + ".0.weight", {b.d.out_ch, b.d.exp_ch, 1, 1});
+      b.bn3 = add_bn(pl, pre + std::to_string(k + 2) + ".1", b.d.out_ch);
+      if (b.d.name_stage > last_stage) last_stage = b.d.name_stage;
     }
-    b.wdw = add_param(pl, pre + std::to_string(j) + ".weight", {b.d.exp_ch, 1, b.d.kernel, b.d.kernel});
-    b.bn2 = add_bn(pl, pre + std::to_string(j + 1), b.d.exp_ch);
-    int se_idx = b.expand ? j + 2 : j + 3, pw_idx = b.expand ? 7 : 4;
-    if (b.d.use_se) {
-      std::string sp = pre + std::to_string(se_idx) + ".fc.";
-      b.se_w1 = add_param(pl, sp + "0.weight", {b.d.se_hidden, b.d.exp_ch});
-      b.se_b1 = add_param(pl, sp + "0.bias", {b.d.se_hidden});
-      b.se_w2 = add_param(pl, sp + "2.weight", {b.d.exp_ch, b.d.se_hidden});
-      b.se_b2 = add_param(pl, sp + "2.bias", {b.d.exp_ch});
-    }
-    b.w3 = add_param(pl, pre + std::to_string(pw_idx) + ".weight", {b.d.out_ch, b.d.exp_ch, 1, 1});
-    b.bn3 = add_bn(pl, pre + std::to_string(pw_idx + 1), b.d.out_ch);
     pl->blocks.push_back(b);
     h = b.Hout; w = b.Wout; cin = b.d.out_ch;
   }
   pl->Hl = h; pl->Wl = w;
   pl->first_param_tail = pl->param_floats;
-  pl->w_last = add_param(pl, "conv.0.weight", {n.last_ch, cin, 1, 1});
-  pl->bn_last = add_bn(pl, "conv.1", n.last_ch);
-  pl->w_fc = add_param(pl, "classifier.0.weight", {n.head_ch, n.last_ch});
-  pl->b_fc = add_param(pl, "classifier.0.bias", {n.head_ch});
-  pl->bn_fc = add_bn(pl, "classifier.1", n.head_ch);
+  pl->w_fc = pl->b_fc = -1; pl->bn_fc = -1;
+  if (!eff) {
+    pl->w_last = add_param(pl, "conv.0.weight", {n.last_ch, cin, 1, 1});
+    pl->bn_last = add_bn(pl, "conv.1", n.last_ch);
+    pl->w_fc = add_param(pl, "classifier.0.weight", {n.head_ch, n.last_ch});
+    pl->b_fc = add_param(pl, "classifier.0.bias", {n.head_ch});
+    pl->bn_fc = add_bn(pl, "classifier.1", n.head_ch);
+  } else {
+    TD3D_REQUIRE(n.head_ch == n.last_ch, "EfficientNet: the heads read the pooled last conv (head_ch %d != last_ch %d)", n.head_ch, n.last_ch);
+    std::string pre = "features." + std::to_string(last_stage + 1) + ".";
+    pl->w_last = add_param(pl, pre + "0.weight", {n.last_ch, cin, 1, 1});
+    pl->bn_last = add_bn(pl, pre + "1", n.last_ch);
+  }
   pl->head_stride = 0;
   for (int k = 0; k < n.max_classes; ++k) {
     int64_t wo = add_param(pl, "regressors." + std::to_string(k) + ".0.weight", {n.num_points, n.head_ch});
@@ -247,8 +291,11 @@ static int build(td3d_plan* pl) {
   }
   pl->p_last = pk.take(e * n.last_ch * cin);
   pl->p_lastt = pk.take(e * n.last_ch * cin);
-  pl->p_fc = pk.take(e * n.head_ch * n.last_ch);
-  pl->p_fct = pk.take(e * n.head_ch * n.last_ch);
+  pl->p_fc = pl->p_fct = 0;
+  if (pl->has_fc) {
+    pl->p_fc = pk.take(e * n.head_ch * n.last_ch);
+    pl->p_fct = pk.take(e * n.head_ch * n.last_ch);
+  }
   for (auto& bn : pl->bns) {
     bn.escale = pk.take(sizeof(float) * bn.C);
     bn.eshift = pk.take(sizeof(float) * bn.C);
@@ -260,7 +307,7 @@ static int build(td3d_plan* pl) {
     b.pi3 = pk.take(e * b.d.out_ch * b.d.exp_ch);
   }
   pl->pi_last = pk.take(e * n.last_ch * cin);
-  pl->pi_fc = pk.take(e * n.head_ch * n.last_ch);
+  pl->pi_fc = pl->has_fc ? pk.take(e * n.head_ch * n.last_ch) : 0;
   pl->packed_bytes = pk.off;
 
   // ---- workspace ----
@@ -271,13 +318,13 @@ static int build(td3d_plan* pl) {
   pl->fstats_begin = ws.off;
   for (auto& bn : pl->bns) bn.fstats = f32((int64_t)B * 2 * bn.C);
   for (auto& b : pl->blocks)
-    if (!b.expand && b.d.use_se) b.hstats = f32((int64_t)B * 2 * b.d.exp_ch);
+    if (b.se_post) b.hstats = f32((int64_t)B * 2 * b.d.exp_ch);
   pl->pool_stats = f32((int64_t)B * 2 * n.last_ch);
   pl->fstats_end = ws.off;
   pl->bstats_begin = ws.off;
   for (auto& bn : pl->bns) bn.bstats = f32((int64_t)B * 2 * bn.C);
   for (auto& b : pl->blocks)
-    if (!b.expand && b.d.use_se) b.hbstats = f32((int64_t)B * 2 * b.d.exp_ch);
+    if (b.se_post) b.hbstats = f32((int64_t)B * 2 * b.d.exp_ch);
   pl->bstats_end = ws.off;
   for (auto& bn : pl->bns) {
     bn.scale = f32(bn.C); bn.shift = f32(bn.C); bn.mean = f32(bn.C); bn.invstd = f32(bn.C);
@@ -291,7 +338,7 @@ static int build(td3d_plan* pl) {
     const int64_t Mi = (int64_t)B * b.Hin * b.Win, Mo = (int64_t)B * b.Hout * b.Wout;
     if (b.expand) b.y1 = act(Mi, b.d.exp_ch);
     b.y2 = act(Mo, b.d.exp_ch);
-    if (!b.expand && b.d.use_se) b.h = act(Mo, b.d.exp_ch);
+    if (b.se_post) b.h = act(Mo, b.d.exp_ch);
     b.h2 = act(Mo, b.d.exp_ch);
     b.y3 = act(Mo, b.d.out_ch);
     b.out = act(Mo, b.d.out_ch);
@@ -308,7 +355,7 @@ static int build(td3d_plan* pl) {
   pl->yc = act(Ml, n.last_ch);
   pl->pooled = act(B, n.last_ch);
   pl->yfc = act(B, n.head_ch);
-  pl->feat = act(B, n.head_ch);
+  pl->feat = pl->has_fc ? act(B, n.head_ch) : pl->pooled;     // no classifier: the heads read the pooled last conv
   pl->kp_saved = f32((int64_t)B * n.num_points);
   pl->logits_saved = f32((int64_t)B * n.num_classes);
   if (Ml * n.last_ch > max_wide) max_wide = Ml * n.last_ch;
@@ -486,6 +533,13 @@ static int bn_forward(const Ctx& c, int idx, double count, int training, const f
   return TD3D_OK;
 }
 
+static int se_forward(const Ctx& c, const SeArgs& s) {
+  return c.pl->se_kind ? launch_se_gen_fwd(s, c.st) : launch_se_fwd(s, c.st);
+}
+static int se_backward(const Ctx& c, const SeBwdArgs& s) {
+  return c.pl->se_kind ? launch_se_gen_bwd(s, c.st) : launch_se_bwd(s, c.st);
+}
+
 static XForm xf_make(const float* scale, const float* shift, const float* se, int act) {
   XForm x; x.scale = scale; x.shift = shift; x.se = se; x.act = act;
   return x;
@@ -502,12 +556,12 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   Bn& b0 = pl->bns[pl->bn_stem];
   TD3D_K(PK_STEM_FWD, (double)B * 3 * pl->H * pl->W * 4 + (double)B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_fwd(img, c.pkf(pl->p_stem), c.ws(pl->y0), c.wsf(b0.fstats), B, pl->H, pl->W, n.stem_ch, dt, c.st));
   TD3D_TRY(bn_forward(c, pl->bn_stem, (double)B * pl->H1 * pl->W1, training, &sc, &sh));
-  TD3D_TRY(p_xform(c, c.ws(pl->y0), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, c.ws(pl->x0), nullptr,
+  TD3D_TRY(p_xform(c, c.ws(pl->y0), xf_make(sc, sh, nullptr, pl->stem_act), nullptr, c.ws(pl->x0), nullptr,
                               B, pl->H1 * pl->W1, n.stem_ch, dt, c.st));
   const void* cur = c.ws(pl->x0);
   for (auto& b : pl->blocks) {
     pl->prof.tag = (int)(&b - pl->blocks.data()) + 1;
-    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int act = b.act;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
     const int E = b.d.exp_ch;
@@ -532,14 +586,14 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
       s.w1 = c.P(b.se_w1); s.b1 = c.P(b.se_b1); s.w2 = c.P(b.se_w2); s.b2 = c.P(b.se_b2);
       s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
       s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
-      if (b.expand) {      // BN -> SE -> act (mobilenetv3.py:153-156): squeeze from the dw epilogue sums
+      if (!b.se_post) {    // BN -> SE -> act (mobilenetv3.py:153-156): squeeze from the dw epilogue sums
         s.pool_stats = c.wsf(pl->bns[b.bn2].fstats); s.scale = sc; s.shift = sh;
-        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
         TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, s.gate, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
-      } else {             // BN -> act -> SE (mobilenetv3.py:137-140)
+      } else {             // BN -> act -> SE (mobilenetv3.py:137-140; every torchvision MBConv)
         TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h), c.wsf(b.hstats), B, HWo, E, dt, c.st));
         s.pool_stats = c.wsf(b.hstats); s.scale = nullptr; s.shift = nullptr;
-        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+        TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
         TD3D_TRY(p_xform(c, c.ws(b.h), xf_make(nullptr, nullptr, s.gate, TD3D_ACT_NONE), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
       }
     } else {
@@ -566,12 +620,13 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     g.M = Ml; g.N = n.last_ch; g.K = Cl;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, pl->bn_last, (double)Ml, training, &sc, &sh));
-    TD3D_TRY(p_xform(c, c.ws(pl->yc), xf_make(sc, sh, nullptr, TD3D_ACT_HSWISH), nullptr, nullptr,
+    TD3D_TRY(p_xform(c, c.ws(pl->yc), xf_make(sc, sh, nullptr, pl->stem_act), nullptr, nullptr,
                                 c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
     TD3D_K(PK_POOL, 8.0 * B * n.last_ch, launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
   }
-  // classifier: Linear -> BatchNorm1d -> h_swish (mobilenetv3.py:191-195)
-  {
+  // classifier: Linear -> BatchNorm1d -> h_swish (mobilenetv3.py:191-195; applied only when the backbone is the in-repo
+  // MobileNetV3, model_builder.py:117-118,130-131 -- otherwise the heads read the pooled features)
+  if (pl->has_fc) {
     GemmNT g = {};
     g.a = c.ws(pl->pooled); g.w = c.pk(pl->p_fc); g.y = c.ws(pl->yfc); g.bias = c.P(pl->b_fc);
     g.stats = c.wsf(pl->bns[pl->bn_fc].fstats); g.slots = B;
@@ -598,11 +653,11 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
   pl->prof.tag = 0;
   TD3D_K(PK_STEM_FWD, (double)B * 3 * pl->H * pl->W * 4 + (double)B * pl->H1 * pl->W1 * n.stem_ch * c.esz(),
          launch_stem_fwd(img, c.pkf(pl->pi_stem), c.ws(pl->x0), nullptr, B, pl->H, pl->W, n.stem_ch, dt, c.st,
-                         eshift(pl->bn_stem), TD3D_ACT_HSWISH));
+                         eshift(pl->bn_stem), pl->stem_act));
   const void* cur = c.ws(pl->x0);
   for (auto& b : pl->blocks) {
     pl->prof.tag = (int)(&b - pl->blocks.data()) + 1;
-    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int act = b.act;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
     const int E = b.d.exp_ch;
@@ -620,7 +675,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
     float* sq = c.wsf(pl->bns[b.bn2].fstats);          // per-sample sums of the depthwise output: the SE squeeze
     if (b.d.use_se) TD3D_CUDA(cudaMemsetAsync(sq, 0, sizeof(float) * 2 * (size_t)B * E, c.st));
     // dw-first layout is BN -> act -> SE (mobilenetv3.py:137-140), expanded layout BN -> SE -> act (:153-156)
-    const bool act_in_dw = !b.d.use_se || !b.expand;
+    const bool act_in_dw = !b.d.use_se || b.se_post;
     dw.w_taps = c.pkf(b.pidw); dw.y = c.ws(b.d.use_se ? b.y2 : b.h2); dw.stats = b.d.use_se ? sq : nullptr;
     dw.out_bias = eshift(b.bn2); dw.out_act = act_in_dw ? act : TD3D_ACT_NONE;
     dw.B = B; dw.H = b.Hin; dw.W = b.Win; dw.C = E; dw.k = b.d.kernel; dw.stride = b.d.stride;
@@ -634,7 +689,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
       s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
       s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
       s.pool_stats = sq; s.scale = nullptr; s.shift = nullptr;
-      TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, launch_se_fwd(s, c.st));
+      TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
       TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(nullptr, nullptr, s.gate, act_in_dw ? TD3D_ACT_NONE : act), nullptr, c.ws(b.h2),
                        nullptr, B, HWo, E, dt, c.st));
     }
@@ -650,7 +705,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
   const int Cl = pl->blocks.back().d.out_ch;
   {
     GemmNT g = {};
-    g.a = cur; g.w = c.pk(pl->pi_last); g.y = c.ws(pl->yc); g.bias = eshift(pl->bn_last); g.act = TD3D_ACT_HSWISH;
+    g.a = cur; g.w = c.pk(pl->pi_last); g.y = c.ws(pl->yc); g.bias = eshift(pl->bn_last); g.act = pl->stem_act;
     g.M = Ml; g.N = n.last_ch; g.K = Cl;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->pool_stats), 0, sizeof(float) * 2 * (size_t)B * n.last_ch, c.st));
@@ -658,7 +713,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
                      c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
     TD3D_K(PK_POOL, 8.0 * B * n.last_ch, launch_pool_finalize(c.wsf(pl->pool_stats), 1.f / (float)HWl, c.ws(pl->pooled), B, n.last_ch, dt, c.st));
   }
-  {
+  if (pl->has_fc) {
     GemmNT g = {};
     g.a = c.ws(pl->pooled); g.w = c.pk(pl->pi_fc); g.y = c.ws(pl->feat); g.bias = eshift(pl->bn_fc); g.act = TD3D_ACT_HSWISH;
     g.M = B; g.N = n.head_ch; g.K = n.last_ch;
@@ -748,6 +803,8 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     hb.dw_reg = c.G(pl->w_reg0); hb.dw_cls = c.G(pl->w_cls); hb.db_cls = c.G(pl->b_cls);
     hb.present = present;
     TD3D_K(PK_HEADS, 8.0 * B * n.head_ch, launch_heads_bwd(hb, dt, c.st));
+    const float* g_pooled = c.wsf(pl->g_feat);          // no classifier: the heads' input gradient IS the pooled gradient
+    if (pl->has_fc) {
     // classifier: feat = h_swish(BN1d(yfc))
     Bn& bfc = pl->bns[pl->bn_fc];
     XForm xfc = xf_make(c.wsf(bfc.scale), c.wsf(bfc.shift), nullptr, TD3D_ACT_HSWISH);
@@ -768,10 +825,12 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
     TD3D_TRY(side_join(c, 0));        // the classifier weight-gradient GEMM reads g_wide_a, rewritten next
-    // avg-pool backward + h_swish + BN of the final conv
+    g_pooled = c.wsf(pl->g_pool_f);
+    }
+    // avg-pool backward + activation + BN of the final conv
     Bn& bl = pl->bns[pl->bn_last];
-    XForm xl = xf_make(c.wsf(bl.scale), c.wsf(bl.shift), nullptr, TD3D_ACT_HSWISH);
-    TD3D_TRY(p_actbwd(c, nullptr, c.wsf(pl->g_pool_f), 1.f / (float)HWl, c.ws(pl->yc), xl, c.ws(pl->g_wide_a),
+    XForm xl = xf_make(c.wsf(bl.scale), c.wsf(bl.shift), nullptr, pl->stem_act);
+    TD3D_TRY(p_actbwd(c, nullptr, g_pooled, 1.f / (float)HWl, c.ws(pl->yc), xl, c.ws(pl->g_wide_a),
                                   c.wsf(bl.bstats), B, HWl, n.last_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_last, HWl, nullptr, nullptr, nullptr));
     TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_a), c.ws(pl->yc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
@@ -793,7 +852,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     Block& b = pl->blocks[i];
     pl->prof.tag = 1000 + i + 1;
     TD3D_TRY(side_join(c, 0));        // weight-gradient GEMMs of the previous stage read g_wide_a/b and g_y3, rewritten below
-    const int act = b.d.use_hs ? TD3D_ACT_HSWISH : TD3D_ACT_RELU;
+    const int act = b.act;
     const int HWi = b.Hin * b.Win, HWo = b.Hout * b.Wout;
     const int Mi = B * HWi, Mo = B * HWo;
     const int E = b.d.exp_ch;
@@ -816,36 +875,29 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     const float* sc2 = c.wsf(bn2.scale);
     const float* sh2 = c.wsf(bn2.shift);
     void* gw = c.ws(pl->g_wide_a);
-    if (b.expand) {
-      const float* gate = b.d.use_se ? c.wsf(b.gate) : nullptr;
+    auto se_bwd_args = [&](const float* stats, const float* scale, const float* shift) {
+      SeBwdArgs s;
+      s.bwd_stats = stats; s.scale = scale; s.shift = shift; s.inv_hw = 1.f / (float)HWo;
+      s.w1t = c.pkf(b.pse_w1t); s.w2t = c.pkf(b.pse_w2t); s.w1 = c.P(b.se_w1);
+      s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
+      s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
+      s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
+      s.B = B; s.C = E; s.Ch = b.d.se_hidden;
+      return s;
+    };
+    if (b.d.use_se && !b.se_post) {
+      // x = act(gate * BN(y2)): the gate sits inside the activation (mobilenetv3.py:153-156)
+      const float* gate = c.wsf(b.gate);
       TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, gate, act), gw, c.wsf(bn2.bstats), B, HWo,
                                     E, dt, c.st));
-      if (b.d.use_se) {
-        SeBwdArgs s;
-        s.bwd_stats = c.wsf(bn2.bstats); s.scale = sc2; s.shift = sh2; s.inv_hw = 1.f / (float)HWo;
-        s.w1t = c.pkf(b.pse_w1t); s.w2t = c.pkf(b.pse_w2t);
-        s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
-        s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
-        s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
-        s.B = B; s.C = E; s.Ch = b.d.se_hidden;
-        TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, launch_se_bwd(s, c.st));
-        TD3D_TRY(bn_backward(c, b.bn2, HWo, gate, c.wsf(pl->se_gpool), c.wsf(bn2.fstats)));
-      } else {
-        TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
-      }
+      TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, se_backward(c, se_bwd_args(c.wsf(bn2.bstats), sc2, sh2)));
+      TD3D_TRY(bn_backward(c, b.bn2, HWo, gate, c.wsf(pl->se_gpool), c.wsf(bn2.fstats)));
     } else {
       if (b.d.use_se) {
         // x = H * gate with H = act(BN(y2)):  g_H = gate*g_x + g_pool/HW
         TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.h), xf_make(nullptr, nullptr, c.wsf(b.gate), TD3D_ACT_NONE), gw,
                                       c.wsf(b.hbstats), B, HWo, E, dt, c.st));
-        SeBwdArgs s;
-        s.bwd_stats = c.wsf(b.hbstats); s.scale = nullptr; s.shift = nullptr; s.inv_hw = 1.f / (float)HWo;
-        s.w1t = c.pkf(b.pse_w1t); s.w2t = c.pkf(b.pse_w2t);
-        s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre);
-        s.g_pre = c.wsf(pl->se_gpre); s.g_hid = c.wsf(pl->se_ghid); s.g_pool = c.wsf(pl->se_gpool);
-        s.dw1 = c.G(b.se_w1); s.db1 = c.G(b.se_b1); s.dw2 = c.G(b.se_w2); s.db2 = c.G(b.se_b2);
-        s.B = B; s.C = E; s.Ch = b.d.se_hidden;
-        TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, launch_se_bwd(s, c.st));
+        TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, se_backward(c, se_bwd_args(c.wsf(b.hbstats), nullptr, nullptr)));
         scale_kernel<<<ceil_div(B * E, 256), 256, 0, c.st>>>(c.wsf(pl->se_gpool), 1.f / (float)HWo, c.wsf(pl->se_gpool_scaled), B * E);
         TD3D_LAUNCH_CHECK();
         TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->zeros_c), 0, sizeof(float) * E, c.st));
@@ -901,7 +953,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     Bn& b0 = pl->bns[pl->bn_stem];
     const int HW1 = pl->H1 * pl->W1;
     void* g0 = c.ws(pl->g_narrow[0]);
-    TD3D_TRY(p_actbwd(c, g0, nullptr, 1.f, c.ws(pl->y0), xf_make(c.wsf(b0.scale), c.wsf(b0.shift), nullptr, TD3D_ACT_HSWISH),
+    TD3D_TRY(p_actbwd(c, g0, nullptr, 1.f, c.ws(pl->y0), xf_make(c.wsf(b0.scale), c.wsf(b0.shift), nullptr, pl->stem_act),
                                   g0, c.wsf(b0.bstats), B, HW1, n.stem_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_stem, HW1, nullptr, nullptr, nullptr));
     TD3D_K(PK_STEM_WGRAD, (double)B * 3 * pl->H * pl->W * 4 + 2.0 * B * pl->H1 * pl->W1 * n.stem_ch * c.esz(), launch_stem_wgrad(pl->last_img, g0, c.ws(pl->y0), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
@@ -946,8 +998,10 @@ static int build_tables(td3d_plan* pl) {
   const int Cl = pl->blocks.back().d.out_ch;
   TD3D_TRY(add_seg(t, c.P(pl->w_last), c.pk(pl->p_last), n.last_ch, Cl, 0, dt));
   TD3D_TRY(add_seg(t, c.P(pl->w_last), c.pk(pl->p_lastt), n.last_ch, Cl, 1, dt));
-  TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fc), n.head_ch, n.last_ch, 0, dt));
-  TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fct), n.head_ch, n.last_ch, 1, dt));
+  if (pl->has_fc) {
+    TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fc), n.head_ch, n.last_ch, 0, dt));
+    TD3D_TRY(add_seg(t, c.P(pl->w_fc), c.pk(pl->p_fct), n.head_ch, n.last_ch, 1, dt));
+  }
   BnFoldTable& f = pl->fold_table;
   f.n = 0;
   TD3D_REQUIRE(pl->bns.size() <= 128, "too many BatchNorm layers for the fold table");
@@ -956,7 +1010,7 @@ static int build_tables(td3d_plan* pl) {
     sg.gamma = c.P(bn.gamma); sg.beta = c.P(bn.beta);
     sg.rm = pl->BNB + bn.rm; sg.rv = pl->BNB + bn.rm + bn.C;
     sg.scale = c.pkf(bn.escale); sg.shift = c.pkf(bn.eshift); sg.C = bn.C;
-    sg.lin_bias = (&bn - pl->bns.data()) == pl->bn_fc ? c.P(pl->b_fc) : nullptr;   // classifier Linear bias rides in the folded shift
+    sg.lin_bias = (pl->has_fc && (&bn - pl->bns.data()) == pl->bn_fc) ? c.P(pl->b_fc) : nullptr;   // classifier Linear bias rides in the folded shift
   }
   // inference weights: W'[n][k] = W[n][k] * escale[n]; the consumer's bias is the BatchNorm's eshift
   PackTable& te = pl->pack_table_eval;
@@ -970,7 +1024,7 @@ static int build_tables(td3d_plan* pl) {
     TD3D_TRY(add_seg(te, c.P(b.w3), c.pk(b.pi3), b.d.out_ch, E, 0, dt, esc(b.bn3)));
   }
   TD3D_TRY(add_seg(te, c.P(pl->w_last), c.pk(pl->pi_last), n.last_ch, Cl, 0, dt, esc(pl->bn_last)));
-  TD3D_TRY(add_seg(te, c.P(pl->w_fc), c.pk(pl->pi_fc), n.head_ch, n.last_ch, 0, dt, esc(pl->bn_fc)));
+  if (pl->has_fc) TD3D_TRY(add_seg(te, c.P(pl->w_fc), c.pk(pl->pi_fc), n.head_ch, n.last_ch, 0, dt, esc(pl->bn_fc)));
   return TD3D_OK;
 }
 
@@ -1011,7 +1065,8 @@ int td3d_plan_create(const td3d_net_desc* net, int batch, int height, int width,
   TD3D_REQUIRE(batch > 0 && batch <= 65535 && height >= 8 && width >= 8, "plan_create: bad batch/resolution %d %dx%d", batch, height, width);
   TD3D_REQUIRE(dtype == TD3D_F32 || dtype == TD3D_BF16, "plan_create: bad dtype %d", dtype);
   TD3D_REQUIRE(net->n_blocks > 0 && net->blocks, "plan_create: no blocks");
-  TD3D_REQUIRE(net->stem_ch == 16, "plan_create: stem_ch must be 16");
+  TD3D_REQUIRE(net->stem_ch >= 16 && net->stem_ch <= 48 && net->stem_ch % 8 == 0, "plan_create: stem_ch must be 16..48 in steps of 8");
+  TD3D_REQUIRE(net->arch == TD3D_ARCH_MOBILENETV3 || net->arch == TD3D_ARCH_EFFICIENTNET, "plan_create: unknown arch %d", net->arch);
   TD3D_REQUIRE(net->num_points == 18, "plan_create: num_points must be 18 (9 keypoints)");
   TD3D_REQUIRE(net->num_classes >= 1 && net->num_classes <= 32 && net->max_classes >= 1 && net->max_classes <= 32, "plan_create: bad class counts");
   TD3D_REQUIRE(net->last_ch % 8 == 0 && net->head_ch % 8 == 0, "plan_create: widths must be multiples of 8");

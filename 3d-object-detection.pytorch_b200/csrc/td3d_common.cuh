@@ -58,19 +58,21 @@ struct XForm {
 __device__ __forceinline__ float act_fwd(float u, int act) {
   if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
   if (act == TD3D_ACT_HSWISH) return u * fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  if (act == TD3D_ACT_SILU) return u / (1.f + __expf(-u));
   return u;
 }
 // d act(u) / du, matching autograd of x*relu6(x+3)/6 (hardtanh grad is 0 at both clamp points)
 __device__ __forceinline__ float act_bwd(float u, int act) {
   if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
   if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) * (1.f / 6.f));
+  if (act == TD3D_ACT_SILU) { const float s = 1.f / (1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
   return 1.f;
 }
 // Branch-free activations from per-kernel uniform constants (set up once with make_actk): the `act` switch of
 // act_fwd/act_bwd costs two uniform compare+branch pairs PER ELEMENT when it sits in an inner loop (ncu: 30 % of
 // the issued instructions of apply_xform).  act(u) = u * sat(a*u + b):  none a=0,b=1 | relu a=2^100,b=0 |
 // h_swish a=1/6,b=1/2.   act'(u) = u <= lo ? 0 : (u >= hi ? 1 : da*u + db).
-struct ActK { float a, b, da, db, lo, hi; };
+struct ActK { float a, b, da, db, lo, hi; int silu; };   // silu: x*sigmoid(x) has no clamp form -> one uniform branch
 __device__ __forceinline__ ActK make_actk(int act) {
   ActK k;
   const bool hs = act == TD3D_ACT_HSWISH, re = act == TD3D_ACT_RELU;
@@ -80,10 +82,15 @@ __device__ __forceinline__ ActK make_actk(int act) {
   k.db = hs ? 0.5f : 1.f;
   k.lo = hs ? -3.f : (re ? 0.f : -__int_as_float(0x7f800000));
   k.hi = hs ? 3.f : __int_as_float(0x7f800000);
+  k.silu = act == TD3D_ACT_SILU;
   return k;
 }
-__device__ __forceinline__ float actk_fwd(float u, const ActK& k) { return u * __saturatef(fmaf(k.a, u, k.b)); }
+__device__ __forceinline__ float actk_fwd(float u, const ActK& k) {
+  if (k.silu) return u / (1.f + __expf(-u));
+  return u * __saturatef(fmaf(k.a, u, k.b));
+}
 __device__ __forceinline__ float actk_bwd(float u, const ActK& k) {
+  if (k.silu) { const float s = 1.f / (1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
   float d = fmaf(u, k.da, k.db);
   d = u >= k.hi ? 1.f : d;
   return u <= k.lo ? 0.f : d;

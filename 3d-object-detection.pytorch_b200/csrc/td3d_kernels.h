@@ -45,6 +45,7 @@ struct SeArgs {
   int B; int C; int Ch;
 };
 int launch_se_fwd(const SeArgs& a, cudaStream_t st);
+int launch_se_gen_fwd(const SeArgs& a, cudaStream_t st);   // k_se_gen.cu: sigmoid gate / SiLU hidden, any Ch (hid holds the hidden PRE-activation)
 struct SeBwdArgs {
   const float* bwd_stats;    // [B][2][C]: P1 = sum gu, P2 = sum gu*y
   const float* scale; const float* shift;   // gs = scale*P2 + shift*P1 (null: gs = P2)
@@ -54,8 +55,10 @@ struct SeBwdArgs {
   float* g_pre; float* g_hid; float* g_pool;           // [B,C] [B,Ch] [B,C]
   float* dw1; float* db1; float* dw2; float* db2;      // grads arena
   int B; int C; int Ch;
+  const float* w1 = nullptr;                           // general flavour only: W1 [Ch,C] as stored
 };
 int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st);
+int launch_se_gen_bwd(const SeBwdArgs& a, cudaStream_t st);
 
 // ---- k_stem.cu ----
 // out_bias != null (inference): y = out_act(conv + out_bias[c]) with BatchNorm folded into w27xC / out_bias

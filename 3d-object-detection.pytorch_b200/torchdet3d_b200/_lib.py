@@ -13,18 +13,18 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtd3d.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_HSWISH = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SILU = 0, 1, 2, 3
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 OPT_SGD, OPT_ADAMW, OPT_RMSPROP, OPT_ADADELTA = 0, 1, 2, 3
 
 
 class BlockDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("kernel", "stride", "in_ch", "exp_ch", "out_ch", "use_se", "se_hidden", "use_hs")]
+                ("kernel", "stride", "in_ch", "exp_ch", "out_ch", "use_se", "se_hidden", "use_hs", "name_stage", "name_index")]
 
 
 class NetDesc(C.Structure):
-    _fields_ = [("stem_ch", C.c_int), ("n_blocks", C.c_int), ("blocks", C.POINTER(BlockDesc)),
+    _fields_ = [("arch", C.c_int), ("stem_ch", C.c_int), ("n_blocks", C.c_int), ("blocks", C.POINTER(BlockDesc)),
                 ("last_ch", C.c_int), ("head_ch", C.c_int), ("num_classes", C.c_int),
                 ("max_classes", C.c_int), ("num_points", C.c_int)]
 

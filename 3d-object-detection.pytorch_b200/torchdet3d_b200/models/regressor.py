@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
-from .arch import blocks_for, AVAILABLE_MODELS
+from .arch import blocks_for, arch_of, AVAILABLE_MODELS
 
 MAX_CLASSES = 9      # model_builder.py:78
 NUM_POINTS = 18      # model_builder.py:73
@@ -85,7 +85,7 @@ class Regressor(nn.Module):
         stem, blocks, last_ch, head_ch = blocks_for(name)
         self._blocks_py = blocks
         self._block_array = (L.BlockDesc * len(blocks))(*[L.BlockDesc(**b) for b in blocks])
-        self._net_desc = L.NetDesc(stem, len(blocks), self._block_array, last_ch, head_ch, num_classes,
+        self._net_desc = L.NetDesc(arch_of(name), stem, len(blocks), self._block_array, last_ch, head_ch, num_classes,
                                    MAX_CLASSES, NUM_POINTS)
         self.head_ch = head_ch
         self._plans = {}

@@ -28,11 +28,14 @@
 extern "C" {
 #endif
 
-#define TD3D_ABI_VERSION 1
+#define TD3D_ABI_VERSION 2
 
 enum { TD3D_OK = 0, TD3D_EINVAL = -1, TD3D_ECUDA = -2, TD3D_ENOMEM = -3, TD3D_ESTATE = -4 };
 enum { TD3D_F32 = 0, TD3D_BF16 = 1 };                       /* activation / packed-weight dtype  */
-enum { TD3D_ACT_NONE = 0, TD3D_ACT_RELU = 1, TD3D_ACT_HSWISH = 2 };
+enum { TD3D_ACT_NONE = 0, TD3D_ACT_RELU = 1, TD3D_ACT_HSWISH = 2, TD3D_ACT_SILU = 3 };
+/* backbone family: parameter naming, SE flavour / position, tail */
+enum { TD3D_ARCH_MOBILENETV3 = 0,      /* torchdet3d/models/mobilenetv3.py: h_sigmoid/ReLU SE between BN and activation, classifier Linear+BN1d */
+       TD3D_ARCH_EFFICIENTNET = 1 };   /* torchvision efficientnet .features (BASELINE configs 3, 5): SiLU, sigmoid/SiLU SE after the activation, no classifier */
 enum { TD3D_GEMM_AUTO = 0, TD3D_GEMM_SIMT = 1, TD3D_GEMM_TCGEN05 = 2 };
 enum { TD3D_OPT_SGD = 0, TD3D_OPT_ADAMW = 1, TD3D_OPT_RMSPROP = 2, TD3D_OPT_ADADELTA = 3 };
 
@@ -44,18 +47,21 @@ typedef struct td3d_block_desc {
   int exp_ch;     /* hidden (expanded) channels               */
   int out_ch;     /* block output channels                    */
   int use_se;     /* SELayer present                          */
-  int se_hidden;  /* _make_divisible(exp_ch // 4, 8)          */
-  int use_hs;     /* 1: h_swish, 0: ReLU                      */
+  int se_hidden;  /* MobileNetV3: _make_divisible(exp_ch // 4, 8); EfficientNet: max(1, in_ch // 4) */
+  int use_hs;     /* activation: 0 ReLU, 1 h_swish, 2 SiLU    */
+  int name_stage; /* EfficientNet: features.<stage>.<index>.block.* parameter names (MobileNetV3: unused) */
+  int name_index;
 } td3d_block_desc;
 
 /* Whole regressor: MobileNetV3 backbone (mobilenetv3.py:169-203) + ModelWrapper heads
  * (model_builder.py:76-87). */
 typedef struct td3d_net_desc {
-  int stem_ch;            /* 16                                                   */
+  int arch;               /* TD3D_ARCH_*                                          */
+  int stem_ch;            /* 16 (MobileNetV3) / 32, 40 (EfficientNet-B0, B3)      */
   int n_blocks;
   const td3d_block_desc* blocks;
   int last_ch;            /* final 1x1 conv width (exp_size: 576 / 960)           */
-  int head_ch;            /* classifier width (1024 / 1280)                       */
+  int head_ch;            /* classifier width (1024 / 1280); EfficientNet: == last_ch (no classifier) */
   int num_classes;        /* cls_fc outputs                                       */
   int max_classes;        /* number of regressor heads (9)                        */
   int num_points;         /* outputs per head (18)                                */

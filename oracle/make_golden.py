@@ -206,6 +206,60 @@ def run_alwa_golden():
           [round(float(out[f"v1_i{i}_lam_cls"][0]), 4) for i in range(9)])
 
 
+def run_effnet_golden():
+    """torchvision efficientnet_b0 `.features` through the REFERENCE's own model_wrapper: pins
+    oracle/effnet_port.py (which restates the wrapper because /root/reference does not travel to the GPU box)."""
+    from torchdet3d.builders.model_builder import model_wrapper
+    from torchdet3d.builders import build_loss
+    from torchdet3d.losses import LossManager
+    from oracle import effnet_port as ep
+    name, B, res = "efficientnet_b0", 5, 64
+
+    class TVFeat(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = ep.features(name)
+
+        def extract_features(self, x):
+            return self.features(x)
+
+    net = model_wrapper(model_class=TVFeat, output_channels=1280, num_classes=9)
+    state = ep.synth_state(name, seed=0)
+    net.load_state_dict(state)
+    out = {}
+    imgs, gt_kp, cats, _ = tp.synth_batch(B, res=res, seed=77)
+    net.eval()
+    with torch.no_grad():
+        kp, logits = net(imgs, cats)
+        kp_all, elog = net.forward_to_onnx(imgs)
+    out["eval_kp"], out["eval_logits"] = kp.numpy(), logits.numpy()
+    out["export_kp_all"], out["export_logits"] = kp_all.numpy(), elog.numpy()
+    cfg = refshim.reference_config("mobilenetv3_small")
+    lm = LossManager(build_loss(cfg), cfg.loss.coeffs, cfg.loss.alwa)
+    net.train()
+    imgs, gt_kp, cats, _ = tp.synth_batch(B, res=res, seed=1000)
+    mask = dropout_mask_for(500, B, 1280)
+    torch.manual_seed(500)
+    kp, logits = net(imgs, cats)
+    loss = lm.parse_losses(kp, gt_kp, logits, cats, 0)
+    loss.backward()
+    out["s0_mask"] = np.packbits(mask.numpy().astype(np.uint8), axis=1)
+    out["s0_kp"], out["s0_logits"] = kp.detach().numpy(), logits.detach().numpy()
+    out["s0_loss"] = np.array([loss.item()], dtype=np.float64)
+    names = [n for n, _ in net.named_parameters()]
+    out["param_names"] = np.array(names)
+    out["s0_grad_none"] = np.array([p.grad is None for _, p in net.named_parameters()])
+    out["s0_grad_l2"] = np.array([0.0 if p.grad is None else p.grad.double().norm().item() for _, p in net.named_parameters()])
+    sd = net.state_dict()
+    for n in ["features.0.1.running_mean", "features.1.0.block.0.1.running_var", "features.8.1.running_var"]:
+        out["s0_buf/" + n] = sd[n].detach().numpy().copy()
+    for n in ["features.0.0.weight", "features.1.0.block.1.fc1.weight", "features.2.0.block.2.fc2.bias", "features.8.1.weight",
+              "cls_fc.1.weight"]:
+        out["s0_grad/" + n] = dict(net.named_parameters())[n].grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "effnet_b0.npz"), **out)
+    print("effnet_b0 ->", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
 def main():
     refshim.install()
     os.makedirs(OUT, exist_ok=True)
@@ -215,6 +269,8 @@ def main():
         run_alwa_golden()
     if only in (None, "loss"):
         run_loss_metric_golden()
+    if only in (None, "effnet"):
+        run_effnet_golden()
     for case in CASES:
         if only in (None, case[0]):
             run_case(*case)

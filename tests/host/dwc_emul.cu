@@ -26,11 +26,13 @@ struct HostSink {
 static double act_ref(double u, int act) {
   if (act == TD3D_ACT_RELU) return u > 0 ? u : 0;
   if (act == TD3D_ACT_HSWISH) { double r = u + 3; r = r < 0 ? 0 : (r > 6 ? 6 : r); return u * r / 6; }
+  if (act == TD3D_ACT_SILU) return u / (1 + exp(-u));
   return u;
 }
 static double actd_ref(double u, int act) {
   if (act == TD3D_ACT_RELU) return u > 0 ? 1 : 0;
   if (act == TD3D_ACT_HSWISH) return u <= -3 ? 0 : (u >= 3 ? 1 : (2 * u + 3) / 6);
+  if (act == TD3D_ACT_SILU) { double s = 1 / (1 + exp(-u)); return s * (1 + u * (1 - s)); }
   return 1;
 }
 
@@ -122,7 +124,7 @@ static int run_all() {
   int bad = 0;
   const int shapes[][4] = {{2, 14, 14, 16}, {3, 7, 7, 24}, {2, 29, 23, 8}, {1, 56, 56, 8}, {2, 1, 5, 16}, {3, 2, 3, 8}, {1, 8, 8, 8}, {2, 5, 1, 8}};
   for (auto& s : shapes) {
-    for (int act = 0; act < 3; ++act) {
+    for (int act = 0; act < 4; ++act) {
       const bool xf = act != 0;
       bad += run_case<T, 3, 1, 4, 2>(s[0], s[1], s[2], s[3], act, xf, 5);
       bad += run_case<T, 3, 1, 2, 2>(s[0], s[1], s[2], s[3], act, xf, 1000);
@@ -204,8 +206,8 @@ static int run_all_fwd() {
   int bad = 0;
   const int shapes[][4] = {{2, 14, 14, 16}, {3, 7, 7, 24}, {2, 29, 23, 8}, {1, 56, 56, 8}, {2, 1, 5, 16}, {3, 2, 3, 8}, {1, 8, 8, 8}, {2, 5, 1, 8}};
   for (auto& s : shapes) {
-    for (int v = 0; v < 3; ++v) {
-      const int act = v, oact = v == 0 ? 2 : 0;
+    for (int v = 0; v < 4; ++v) {
+      const int act = v, oact = v == 0 ? 2 : (v == 3 ? 3 : 0);
       const bool xf = v != 0, bias = v == 0;
       bad += run_fwd_case<T, 3, 1, 4, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 5);
       bad += run_fwd_case<T, 3, 1, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 1000);

@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(L.SYMBOLS) == declared, (set(L.SYMBOLS) ^ declared)
-    assert lib.td3d_abi_version() == 1
+    assert lib.td3d_abi_version() == 2
 
 
 @pytest.mark.parametrize("name", ["mobilenetv3_small", "mobilenetv3_large"])
@@ -46,6 +46,21 @@ def test_plan_param_table_matches_reference_state_dict(name):
     assert torch.equal(m._flat[off:off + m._param_table[3][2]].view(m._param_table[3][3]), st[m._param_table[3][0]])
 
 
+@pytest.mark.parametrize("name,n_params", [("efficientnet_b0", 4226599), ("efficientnet_b3", 10959059)])
+def test_plan_param_table_matches_torchvision_efficientnet_through_the_wrapper(name, n_params):
+    """BASELINE configs 3 / 5: keys, order and shapes of the torchvision `.features` state_dict + the reference wrapper's
+    heads (oracle/effnet_port.py)."""
+    from oracle import effnet_port as ep
+    m = Regressor(name, num_classes=9)
+    ref = ep.synth_state(name, seed=1)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
+    assert sum(p.numel() for p in m.parameters()) == n_params
+    m.load_state_dict(ref)
+    assert all(torch.equal(m.state_dict()[k], ref[k]) for k in ref)
+
+
 def test_no_cpu_fallback():
     m = Regressor("mobilenetv3_small")
     with pytest.raises(L.Td3dError):
@@ -60,8 +75,8 @@ def test_no_cpu_fallback():
 
 def test_plan_rejects_bad_descriptors():
     lib = L.lib()
-    blocks = (L.BlockDesc * 1)(L.BlockDesc(3, 1, 16, 20, 16, 0, 0, 0))     # exp_ch not a multiple of 8
-    net = L.NetDesc(16, 1, blocks, 96, 128, 9, 9, 18)
+    blocks = (L.BlockDesc * 1)(L.BlockDesc(3, 1, 16, 20, 16, 0, 0, 0, 0, 0))     # exp_ch not a multiple of 8
+    net = L.NetDesc(0, 16, 1, blocks, 96, 128, 9, 9, 18)
     h = C.c_void_p()
     assert lib.td3d_plan_create(C.byref(net), 4, 64, 64, 0, 0, C.byref(h)) != 0
     assert b"multiples of 8" in lib.td3d_last_error()

@@ -154,3 +154,35 @@ def test_live_reference_forward_and_rmsprop_adadelta():
             torch.nn.functional.linear(x, w, b).pow(2).sum().backward()
             tp.optim_step(st, {"w.weight": w.grad, "w.bias": b.grad}, ost, ocfg)
         _close(st["w.weight"], lin.weight.detach(), rtol=1e-5); _close(st["w.bias"], lin.bias.detach(), rtol=1e-5)
+
+
+def test_effnet_port_matches_reference_wrapper_over_torchvision_golden():
+    """oracle/effnet_port.py (restated wrapper over torchvision efficientnet_b0.features) against the golden produced by
+    the REFERENCE's own model_wrapper over the same features (oracle/make_golden.py effnet): BASELINE configs 3 / 5."""
+    from oracle import effnet_port as ep
+    g = load_golden("effnet_b0")
+    name, B, res = "efficientnet_b0", 5, 64
+    state = ep.synth_state(name, seed=0)
+    imgs, gt_kp, cats, _ = tp.synth_batch(B, res=res, seed=77)
+    m = ep.make(name, state).eval()
+    with torch.no_grad():
+        kp, logits = m(imgs, cats)
+        kp_all, elog = m.forward_export(imgs)
+    _close(kp, g["eval_kp"]); _close(logits, g["eval_logits"])
+    _close(kp_all, g["export_kp_all"]); _close(elog, g["export_logits"])
+    imgs, gt_kp, cats, _ = tp.synth_batch(B, res=res, seed=1000)
+    mask = torch.tensor(np.unpackbits(g["s0_mask"], axis=1)[:, :1280].astype(np.float32))
+    r = ep.train_step(state, name, {}, imgs, gt_kp, cats, mask, step_optimizer=False)
+    _close_rel(r["kp"], g["s0_kp"], 1e-4); _close_rel(r["logits"], g["s0_logits"], 1e-4)
+    assert abs(r["loss"] - g["s0_loss"][0]) <= 1e-5 * abs(g["s0_loss"][0])
+    names = [str(n) for n in g["param_names"]]
+    assert names == [k for k in state if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
+    assert np.array_equal(np.array([r["grads"][n] is None for n in names]), g["s0_grad_none"])
+    l2 = np.array([0.0 if r["grads"][n] is None else r["grads"][n].double().norm().item() for n in names])
+    big = g["s0_grad_l2"] > 1e-6
+    assert np.abs(l2[big] - g["s0_grad_l2"][big]).max() / g["s0_grad_l2"][big].max() < 1e-4
+    for key in g.files:
+        if key.startswith("s0_grad/"):
+            _close_rel(r["grads"][key[8:]], g[key], 1e-3)
+        elif key.startswith("s0_buf/"):
+            _close(state[key[7:]], g[key], rtol=1e-4, atol=1e-6)
