@@ -115,4 +115,6 @@ def act_ref(u, act):
         return torch.relu(u)
     if act == L.ACT_HSWISH:
         return u * torch.nn.functional.relu6(u + 3) / 6
+    if act == L.ACT_SILU:
+        return torch.nn.functional.silu(u)
     return u

@@ -30,7 +30,7 @@ def _seed():
 
 @pytest.mark.parametrize("code", CODES)
 @pytest.mark.parametrize("shape", [(3, 7, 7, 96), (2, 28, 28, 72), (5, 1, 1, 1024), (2, 56, 56, 16), (1, 5, 9, 2096)])
-@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_RELU, L.ACT_HSWISH])
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_RELU, L.ACT_HSWISH, L.ACT_SILU])
 def test_apply_xform_and_pool(code, shape, act):
     B, H, W, Cn = shape
     y = (torch.randn(shape, device=DEV) * 2).to(K.dt(code))
@@ -58,7 +58,7 @@ def test_affine2_and_act_bwd_stats(code, shape):
     torch.testing.assert_close(out.float(), ref, **tol(code))
     scale, shift = torch.rand(Cn, device=DEV) + 0.5, torch.randn(Cn, device=DEV)
     se = torch.rand(B, Cn, device=DEV) + 0.2
-    for act in (L.ACT_NONE, L.ACT_RELU, L.ACT_HSWISH):
+    for act in (L.ACT_NONE, L.ACT_RELU, L.ACT_HSWISH, L.ACT_SILU):
         gu, st = K.act_bwd_stats(g, y, scale, shift, se, act, code)
         u = (se[:, None, None] * (y.float() * scale + shift)).requires_grad_(True)
         K.act_ref(u, act).backward(g.float())
@@ -69,11 +69,12 @@ def test_affine2_and_act_bwd_stats(code, shape):
 
 @pytest.mark.parametrize("code", CODES)
 @pytest.mark.parametrize("hw", [(224, 224), (64, 64), (37, 51)])
-def test_stem(code, hw):
+@pytest.mark.parametrize("Cs", [16, 32, 40])          # MobileNetV3 / EfficientNet-B0 / EfficientNet-B3 stems
+def test_stem(code, hw, Cs):
     B = 3
     img = torch.rand(B, 3, *hw, device=DEV)
-    w = torch.randn(16, 3, 3, 3, device=DEV) * 0.3
-    w27 = w.reshape(16, 27).t().contiguous()
+    w = torch.randn(Cs, 3, 3, 3, device=DEV) * 0.3
+    w27 = w.reshape(Cs, 27).t().contiguous()
     y, st = K.stem_fwd(img, w27, code)
     ref = F.conv2d(img, w, stride=2, padding=1)
     assert rel_err(K.nchw(y), ref) < (1e-5 if code == L.F32 else 6e-3)
@@ -82,7 +83,7 @@ def test_stem(code, hw):
     torch.testing.assert_close(st[:, 1], (yf * yf).sum(dim=(1, 2)), rtol=1e-4, atol=1e-2)
     # weight gradient with a lazily applied affine (BN backward) on the incoming gradient
     g = torch.randn_like(yf).to(K.dt(code))
-    alpha, gamma, beta = torch.randn(B, 16, device=DEV), torch.randn(B, 16, device=DEV) * 0.1, torch.randn(16, device=DEV) * 0.1
+    alpha, gamma, beta = torch.randn(B, Cs, device=DEV), torch.randn(B, Cs, device=DEV) * 0.1, torch.randn(Cs, device=DEV) * 0.1
     dw = K.stem_wgrad(img, g, y, alpha, beta, gamma, code)
     gy = alpha[:, None, None] * g.float() + beta * yf + gamma[:, None, None]
     wr = w.clone().requires_grad_(True)
@@ -93,9 +94,8 @@ def test_stem(code, hw):
 @pytest.mark.parametrize("code", CODES)
 @pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1), (5, 2)])
 @pytest.mark.parametrize("shape", [(2, 14, 14, 240), (3, 7, 7, 96), (2, 29, 23, 16), (1, 56, 56, 72)])
-def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
+def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2, act=L.ACT_HSWISH):
     B, H, W, Cn = shape
-    act = L.ACT_HSWISH
     x = (torch.randn(shape, device=DEV) * 2).to(K.dt(code))
     scale, shift = torch.rand(Cn, device=DEV) + 0.5, torch.randn(Cn, device=DEV) * 0.5
     se = torch.rand(B, Cn, device=DEV) + 0.5
@@ -133,6 +133,14 @@ def test_depthwise(code, k, stride, shape, gx_tol_bf16=1e-2):
 @pytest.mark.parametrize("shape", [(5, 8, 8, 40), (3, 32, 32, 24), (2, 1, 5, 16), (9, 16, 16, 8), (300, 7, 7, 24), (2, 3, 31, 48)])
 def test_depthwise_walker_edges(code, k, shape):
     test_depthwise(code, k, 1, shape)
+
+
+# SiLU inputs (EfficientNet) take the column-walker forward kernel (k_dwc.cu) instead of the row walker / tiled kernels
+@pytest.mark.parametrize("code", CODES)
+@pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1), (5, 2)])
+@pytest.mark.parametrize("shape", [(2, 14, 14, 240), (3, 7, 7, 96), (2, 29, 23, 16), (1, 56, 56, 72), (2, 1, 5, 16), (3, 2, 3, 8)])
+def test_depthwise_silu_column_walker(code, k, stride, shape):
+    test_depthwise(code, k, stride, shape, act=L.ACT_SILU)
 
 
 GEMM_SHAPES = [(300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (5000, 16, 64),
