@@ -58,7 +58,7 @@ int pf_dist() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TD3D_DWC_PF");
-    v = e ? atoi(e) : 6;
+    v = e ? atoi(e) : 0;       // measured (r02 call B): 13.9 ms/step with 0 vs 14.5 ms with 6 or 12 -- off by default
   }
   return v;
 }

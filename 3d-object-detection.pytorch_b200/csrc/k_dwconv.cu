@@ -1,8 +1,8 @@
 // Depthwise k x k convolution dispatch (reference op: nn.Conv2d(hidden, hidden, k, s, (k-1)//2, groups=hidden) inside
 // InvertedResidual, torchdet3d/models/mobilenetv3.py:136,152).
 //   forward : row walker (k_dww.cu) for small stride-1 planes, tiled persistent kernels (k_dw2.cu) otherwise
-//   backward: one-pass column walker (k_dwc.cu / dwc_core.cuh): data gradient + weight gradient + BatchNorm sums
-//             from a single read of g, y_out and x
+//   backward: data- and weight-gradient kernels of k_dww.cu / k_dw2.cu (default), or the one-pass column walker
+//             (k_dwc.cu / dwc_core.cuh: both gradients + BatchNorm sums from a single read; SiLU layers)
 #include "td3d_kernels.h"
 
 #include <stdlib.h>
@@ -28,20 +28,25 @@ int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
   return launch_dw_fwd_v2(a, dtype, st);
 }
 
-// TD3D_DW_BWD_SPLIT=1 (A/B measurements only) selects the round-1 two-kernel backward.
-static int dw_bwd_split() {
+// Measured on B200 (r02 call B, MobileNetV3-large batch 256): the one-pass column walker is correct but SLOWER than the
+// two-kernel backward of round 1 (5.25 ms vs 3.85 ms per step over the 15 layers; it stalls on its one-step-ahead
+// register prefetch at 16 warps / SM), so it is used where only it applies -- SiLU (EfficientNet) -- and the split
+// kernels stay the default.  TD3D_DW_BWD_FUSED=1 forces the one-pass kernel everywhere (A/B measurements).
+static int dw_bwd_fused() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TD3D_DW_BWD_SPLIT");
+    const char* e = getenv("TD3D_DW_BWD_FUSED");
     v = e ? atoi(e) : 0;
   }
   return v;
 }
 
+bool dw_bwd_is_split(const DwBwdArgs& a) { return !(dw_bwd_fused() || a.xf.act == TD3D_ACT_SILU); }
+
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw bwd: C=%d must be a multiple of 8", a.C);
   TD3D_REQUIRE((a.k == 3 || a.k == 5) && (a.stride == 1 || a.stride == 2), "dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);
-  if (!dw_bwd_split()) return launch_dw_bwd_fused(a, dtype, st);
+  if (!dw_bwd_is_split(a)) return launch_dw_bwd_fused(a, dtype, st);
   if (dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return launch_dw_bwd_walker(a, dtype, st);
   return launch_dw_bwd_v2(a, dtype, st);
 }

@@ -471,11 +471,23 @@ static int p_dwf(const Ctx& c, const DwArgs& a, int dt, cudaStream_t st) {
   TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd(a, dt, st));
   return TD3D_OK;
 }
-static int p_dwb(const Ctx& c, const DwBwdArgs& a, int dt, cudaStream_t st) {
+static int p_dwb(const Ctx& c, const DwBwdArgs& a0, int dt, cudaStream_t st) {
+  DwBwdArgs a = a0;
   int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
   double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
-  // one pass: read g, y_out, x once; write gx once (data gradient, weight gradient and BatchNorm sums together)
+  // split backward: the weight-gradient kernel runs on side stream 1, concurrently with the data-gradient kernel (both
+  // read g, y_out, x: the second reader mostly hits L2); joined right after, because the next BatchNorm finalize
+  // overwrites the alpha/beta/gamma it reads.  The one-pass kernel (SiLU layers) needs no fork.
+  Ctx sc = c;
+  const bool split = dw_bwd_is_split(a);
+  if (split) TD3D_TRY(side_fork(c, 1, &sc));
+  a.wgrad_stream = sc.st != c.st ? (void*)sc.st : nullptr;
+  // algorithmic bytes = the fused ideal: read g, y_out, x once; write gx once
   TD3D_K(PK_DW_BWD, (2 * out + 2 * in) * c.esz(), launch_dw_bwd(a, dt, st));
+  if (a.wgrad_stream) {
+    TD3D_TRY(side_done(c, 1));
+    TD3D_TRY(side_join(c, 1));
+  }
   return TD3D_OK;
 }
 
@@ -966,7 +978,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
 
 static int add_seg(PackTable& t, const float* src, void* dst, int rows, int cols, int transpose, int out_dtype,
                    const float* row_scale = nullptr) {
-  TD3D_REQUIRE(t.n < 160, "pack table overflow");
+  TD3D_REQUIRE(t.n < 256, "pack table overflow");
   PackSeg& sg = t.seg[t.n++];
   sg.src = src; sg.dst = dst; sg.rows = rows; sg.cols = cols; sg.transpose = transpose; sg.out_dtype = out_dtype;
   sg.row_scale = row_scale;
@@ -1300,6 +1312,38 @@ int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const fl
   a.g = g; a.y_out = y_out; a.alpha = alpha; a.beta = beta; a.gamma = gamma;
   a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.gx = gx; a.stats = stats; a.dw = dw;
   a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
+  return launch_dw_bwd(a, dtype, (cudaStream_t)stream);
+}
+int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
+                     const float* out_bias, int out_act, void* y, float* stats, int B, int H, int W, int C, int k, int stride,
+                     int dtype, int impl, void* stream) {
+  DwArgs a;
+  a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.y = y; a.stats = stats;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride; a.out_bias = out_bias; a.out_act = out_act;
+  TD3D_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2) && C % 8 == 0, "dw_fwd_ex: bad kernel/stride/channels");
+  if (impl == 2) return launch_dw_fwd_cw(a, dtype, (cudaStream_t)stream);
+  if (impl == 1) {
+    TD3D_REQUIRE(!out_bias && out_act == TD3D_ACT_NONE && act != TD3D_ACT_SILU, "dw_fwd_ex: epilogue / SiLU need the column walker");
+    if (dw_walker_supported(H, W, C, k, stride)) return launch_dw_fwd_walker(a, dtype, (cudaStream_t)stream);
+    return launch_dw_fwd_v2(a, dtype, (cudaStream_t)stream);
+  }
+  return launch_dw_fwd(a, dtype, (cudaStream_t)stream);
+}
+int td3d_k_dw_bwd_ex(const void* g, const void* y_out, const float* alpha, const float* beta, const float* gamma,
+                     const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
+                     void* gx, float* dw, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, int impl,
+                     void* stream) {
+  DwBwdArgs a;
+  a.g = g; a.y_out = y_out; a.alpha = alpha; a.beta = beta; a.gamma = gamma;
+  a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.gx = gx; a.stats = stats; a.dw = dw;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
+  TD3D_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2) && C % 8 == 0, "dw_bwd_ex: bad kernel/stride/channels");
+  if (impl == 2) return launch_dw_bwd_fused(a, dtype, (cudaStream_t)stream);
+  if (impl == 1) {
+    TD3D_REQUIRE(act != TD3D_ACT_SILU, "dw_bwd_ex: SiLU needs the column walker");
+    if (dw_walker_supported(H, W, C, k, stride)) return launch_dw_bwd_walker(a, dtype, (cudaStream_t)stream);
+    return launch_dw_bwd_v2(a, dtype, (cudaStream_t)stream);
+  }
   return launch_dw_bwd(a, dtype, (cudaStream_t)stream);
 }
 int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias, const void* ysaved,

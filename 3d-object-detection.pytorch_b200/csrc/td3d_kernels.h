@@ -91,6 +91,7 @@ struct DwBwdArgs {
                                                     // the caller orders it against the launching stream with events
 };
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
+bool dw_bwd_is_split(const DwBwdArgs& a);   // true: separate weight-gradient kernel (may run on wgrad_stream)
 int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu (default)
 int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st);
 bool dw_walker_supported(int H, int W, int C, int k, int stride);       // k_dww.cu: small planes (W <= 32), stride 1
@@ -161,7 +162,7 @@ struct OptimArgs {
 int launch_optim(const OptimArgs& a, cudaStream_t st);
 struct PackSeg { const float* src; void* dst; int rows, cols; int transpose; int out_dtype;
                  const float* row_scale; };   // optional [rows]: dst = src[r][c] * row_scale[r] (eval-mode BatchNorm folded into the weights)
-struct PackTable { int n; PackSeg seg[160]; };
+struct PackTable { int n; PackSeg seg[256]; };     // EfficientNet-B3: 26 blocks x 7 segments + 3
 struct BnFoldSeg { const float *gamma, *beta, *rm, *rv; float *scale, *shift; int C;
                    const float* lin_bias; };     // optional [C]: bias of the Linear in front of this BatchNorm, folded into shift
 struct BnFoldTable { int n; BnFoldSeg seg[128]; };

@@ -36,6 +36,32 @@ MODEL = "mobilenetv3_large"
 RES = 224
 METRIC = "train_crops_per_s"
 UNIT = "crops/s"
+# BASELINE.json configs: [1] (default, the driver's line), [2] and [4] by --workload
+WORKLOADS = {"mnv3_large": ("mobilenetv3_large", 224, 256, "BASELINE configs[1]"),
+             "effnet_b0": ("efficientnet_b0", 224, 512, "BASELINE configs[2]"),
+             "effnet_b3": ("efficientnet_b3", 320, 256, "BASELINE configs[4]")}
+
+
+def oracle_mod():
+    """(module with synth_state / train_step / layer_table for MODEL)."""
+    if MODEL.startswith("efficientnet"):
+        from oracle import effnet_port as ep
+        return ep
+    from oracle import torch_port as tp
+    return tp
+
+
+def layer_rows():
+    o = oracle_mod()
+    return o.layer_table(MODEL, RES)
+
+
+def head_width():
+    if MODEL.startswith("efficientnet"):
+        from oracle import effnet_port as ep
+        return ep.MODELS[MODEL]
+    from oracle import torch_port as tp
+    return tp.block_table(MODEL)["head"]
 
 
 def peaks():
@@ -89,9 +115,8 @@ class ClockSampler:
 
 def algorithmic_bytes_per_crop(esz):
     """train bytes = s(3I+3O) + 2sW/B per conv/linear layer (B large -> W term ~0)."""
-    from oracle import torch_port as tp
     tot = 0.0
-    for kind, I, O, W, M in tp.layer_table(MODEL, RES):
+    for kind, I, O, W, M in layer_rows():
         tot += esz * (3 * I + 3 * O)
     return tot
 
@@ -99,15 +124,16 @@ def algorithmic_bytes_per_crop(esz):
 def cpu_reference_step(batch, steps, warmup, threads):
     """The reference algorithm (oracle port) on host cores: trainer/train.py:46-55 per step."""
     from oracle import torch_port as tp
+    o = oracle_mod()
     torch.set_num_threads(threads)
-    state = tp.synth_state(MODEL, seed=0)
+    state = o.synth_state(MODEL, seed=0)
     opt_state = {}
     imgs, gt_kp, cats, keep = tp.synth_batch(batch, res=RES, seed=1234, all_classes=True)
-    keep = keep[:, :tp.block_table(MODEL)["head"]].contiguous()
+    keep = keep[:, :head_width()].contiguous()
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        tp.train_step(state, MODEL, opt_state, imgs, gt_kp, cats, keep)
+        o.train_step(state, MODEL, opt_state, imgs, gt_kp, cats, keep)
         times.append(time.perf_counter() - t0)
     t = times[warmup:]
     return sum(t) / len(t)
@@ -141,7 +167,7 @@ def run_reference(args, rank, world):
 def forward_bytes_per_crop(esz):
     """forward bytes = s(I+O) per conv/linear layer."""
     from oracle import torch_port as tp
-    return sum(esz * (I + O) for kind, I, O, W, M in tp.layer_table(MODEL, RES))
+    return sum(esz * (I + O) for kind, I, O, W, M in layer_rows())
 
 
 def cpu_reference_infer(batch, steps, warmup, threads):
@@ -323,7 +349,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's BASELINE batch)")
+    ap.add_argument("--workload", default="mnv3_large", choices=sorted(WORKLOADS),
+                    help="mnv3_large = BASELINE configs[1] (default); effnet_b0 = configs[2] (batch 512/GPU); effnet_b3 = configs[4] (320x320, batch 256/GPU)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-graph", action="store_true")
@@ -337,6 +365,10 @@ def main():
     ap.add_argument("--dump-launches", default=None, help="write the per-launch profile (kind, layer tag, ms, GB/s) as CSV")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global MODEL, RES
+    MODEL, RES, dflt_batch, cfg_name = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        args.batch = dflt_batch
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -371,7 +403,7 @@ def main():
                b200=dict(dtype=args.dtype, gemm=args.gemm))
     cfg.loss.coeffs = (list(tp.DEFAULT_LOSS["coeffs"][0]), list(tp.DEFAULT_LOSS["coeffs"][1]))
     model = build_model(cfg)
-    model.load_state_dict(tp.synth_state(MODEL, seed=0))     # identical replicas on every rank
+    model.load_state_dict(oracle_mod().synth_state(MODEL, seed=0))     # identical replicas on every rank
     model = model.to(dev).train()
     lm = LossManager(build_loss(cfg), cfg.loss.coeffs, cfg.loss.alwa)
     opt = build_optimizer(cfg, model)
@@ -533,7 +565,7 @@ def main():
 
     # ---- inference leg (BASELINE configs[3]) in a CHILD process: a failure there can never take the train line down ----
     infer = None
-    if rank == 0 and world == 1 and not args.skip_infer:
+    if rank == 0 and world == 1 and not args.skip_infer and args.workload == "mnv3_large":
         import subprocess
         try:
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
@@ -555,9 +587,9 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{MODEL} regressor train step (fwd+loss+bwd+AdamW+metrics), batch {B}/GPU, "
-                                   f"{RES}x{RES} synthetic crops, 9 classes (BASELINE configs[1])",
+                                   f"{RES}x{RES} synthetic crops, 9 classes ({cfg_name})",
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "inputs (154 MB fp32 images/step) and per-step activations (>2 GB) exceed the 126 MB L2",
+                       "l2": f"inputs ({B * 3 * RES * RES * 4 / 1e6:.0f} MB fp32 images/step) and per-step activations (>2 GB) exceed the 126 MB L2",
                        "cuda_graph": not args.no_graph, "gemm": args.gemm},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -81,6 +81,27 @@ def dw_fwd(x, scale, shift, se, act, w_taps, k, stride, code):
     return y, st
 
 
+def dw_fwd_ex(x, scale, shift, se, act, w_taps, k, stride, code, impl, out_bias=None, out_act=0):
+    B, H, W, Cn = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty(B, Ho, Wo, Cn, device=x.device, dtype=dt(code))
+    st = stats_buf(B, Cn, x.device)
+    L.check(L.lib().td3d_k_dw_fwd_ex(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(se), act, L.ptr(w_taps), L.ptr(out_bias),
+                                     out_act, L.ptr(y), L.ptr(st), B, H, W, Cn, k, stride, code, impl, L.stream()))
+    return y, st
+
+
+def dw_bwd_ex(g, y_out, alpha, beta, gamma, x, scale, shift, se, act, w_taps, k, stride, code, impl):
+    B, H, W, Cn = x.shape
+    gx = torch.empty_like(x)
+    dw = torch.zeros(Cn, 1, k, k, device=x.device)
+    st = stats_buf(B, Cn, x.device)
+    L.check(L.lib().td3d_k_dw_bwd_ex(L.ptr(g), L.ptr(y_out), L.ptr(alpha), L.ptr(beta), L.ptr(gamma), L.ptr(x), L.ptr(scale),
+                                     L.ptr(shift), L.ptr(se), act, L.ptr(w_taps), L.ptr(gx), L.ptr(dw), L.ptr(st), B, H, W, Cn,
+                                     k, stride, code, impl, L.stream()))
+    return gx, dw, st
+
+
 def dw_bwd(g, y_out, alpha, beta, gamma, x, scale, shift, se, act, w_taps, k, stride, code):
     B, H, W, Cn = x.shape
     gx = torch.empty_like(x)
