@@ -17,6 +17,11 @@
 // (it loops over many (sample, band) items), g / y_out / x are each loaded once per band (halo rows come from
 // L1/L2), and no shared memory or barrier is used in the main loop.
 //
+// Inner-loop hygiene (the first version spent ~250 SASS instructions per output element, most of them 64-bit address
+// arithmetic, row/column predicates with divergence barriers and an inlined SiLU slow path): per item the row offsets are
+// computed ONCE as clamped 32-bit element offsets with a 0/1 float mask per row, a step adds one clamped column offset,
+// out-of-range taps are loaded from the clamped (valid) address and multiplied by the mask -- no branches in the walk.
+//
 // The per-thread body is __host__ __device__ so tests/host/dwc_emul.cu can run the exact index logic on the CPU.
 #pragma once
 #include <math.h>
@@ -43,7 +48,6 @@ struct DwcArgs {
   int cw;                                     // channel groups (of CPT channels) per block column chunk
   int n_cchunks;                              // ceil((C / CPT) / cw)
   int ilb;                                    // item lanes per block
-  int pf_dist;                                // L2 prefetch distance in walk steps (0 = off)
 };
 
 // ---- CPT-wide fp32 vectors -------------------------------------------------------------------------------------
@@ -71,6 +75,8 @@ __host__ __device__ __forceinline__ float2 dv_add(float2 a, float2 b) { return m
 __host__ __device__ __forceinline__ float dv_add(float a, float b) { return a + b; }
 __host__ __device__ __forceinline__ void dv_set(float2& v, float s) { v = make_float2(s, s); }
 __host__ __device__ __forceinline__ void dv_set(float& v, float s) { v = s; }
+__host__ __device__ __forceinline__ float2 dv_scale(float2 a, float m) { return make_float2(a.x * m, a.y * m); }
+__host__ __device__ __forceinline__ float dv_scale(float a, float m) { return a * m; }
 __host__ __device__ __forceinline__ float dv_get(const float2& v, int i) { return i ? v.y : v.x; }
 __host__ __device__ __forceinline__ float dv_get(const float& v, int) { return v; }
 
@@ -91,7 +97,7 @@ __host__ __device__ inline DwcAct dwc_make_act(int act) {
 __host__ __device__ __forceinline__ float dwc_sat(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 __host__ __device__ __forceinline__ float dwc_sigmoid(float u) {
 #ifdef __CUDA_ARCH__
-  return 1.f / (1.f + __expf(-u));
+  return __fdividef(1.f, 1.f + __expf(-u));
 #else
   return 1.f / (1.f + expf(-u));
 #endif
@@ -204,6 +210,8 @@ template <> __host__ __device__ __forceinline__ float dwc_ldc<1>(const float* p)
 // One thread's whole life.  `c` = first of its CPT channels, `il` = item lane.  `Sink` receives the final sums:
 //   sink.dw(c + i, tap, value), sink.stat(which, c + i, value)
 // ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int dwc_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 template <typename T, int K, int S, int R, int CPT>
 struct DwcBwd {
   typedef typename DwcVec<CPT>::V V;
@@ -223,81 +231,40 @@ struct DwcBwd {
     V s1, s2;           // sum gx, sum gx * x
     Raw rg[NA], ry[NA]; // prefetched raw gradient column
     Raw rx[RI][S];      // prefetched raw input pixels of the next step
+    uint32_t og[NA];    // per item: clamped element offset of gradient row ar (row * Wo * C)
+    uint32_t ox[RI];    // ... of input row ey
+    float mg[NA];       // 1 inside the output plane, 0 outside
+    float mx[RI];
   };
 
-  // prefetch the raw data step `px` needs: gradient column px + HI, input columns S*px .. S*px + S-1
+  // raw loads step `px` needs: gradient column px + HI, input columns S*px .. S*px + S-1 (clamped addresses: always valid)
   static __host__ __device__ __forceinline__ void prefetch(State& st, const DwcArgs& a, const T* gb, const T* yb,
-                                                           const T* xb, int r0, int px, bool pf_lane) {
-    const int cg = px + HI;
-    const bool col_ok = cg >= 0 && cg < a.Wo;
+                                                           const T* xb, int px) {
+    const uint32_t cgo = (uint32_t)(dwc_clampi(px + HI, 0, a.Wo - 1) * a.C);
 #pragma unroll
     for (int ar = 0; ar < NA; ++ar) {
-      const int py = r0 + ar - LO;
-      const bool ok = col_ok && py >= 0 && py < a.Ho;
-      st.rg[ar] = Io::zero(); st.ry[ar] = Io::zero();
-      if (ok) {
-        const size_t off = ((size_t)py * a.Wo + cg) * a.C;
-        st.rg[ar] = Io::ld(gb + off);
-        st.ry[ar] = Io::ld(yb + off);
-      }
+      st.rg[ar] = Io::ld(gb + (st.og[ar] + cgo));
+      st.ry[ar] = Io::ld(yb + (st.og[ar] + cgo));
     }
-    if (px >= 0) {
 #pragma unroll
-      for (int ey = 0; ey < RI; ++ey) {
-        const int qy = S * r0 + ey;
+    for (int ex = 0; ex < S; ++ex) {
+      const uint32_t cxo = (uint32_t)(dwc_clampi(S * px + ex, 0, a.W - 1) * a.C);
 #pragma unroll
-        for (int ex = 0; ex < S; ++ex) {
-          const int qx = S * px + ex;
-          st.rx[ey][ex] = Io::zero();
-          if (qy < a.H && qx < a.W) st.rx[ey][ex] = Io::ld(xb + ((size_t)qy * a.W + qx) * a.C);
-        }
-      }
+      for (int ey = 0; ey < RI; ++ey) st.rx[ey][ex] = Io::ld(xb + (st.ox[ey] + cxo));
     }
-#ifdef __CUDA_ARCH__
-    // The register prefetch above runs one step ahead (a few hundred ns): too short for a DRAM round trip.  One lane
-    // per 128-byte line therefore asks L2 for the lines `pf_dist` steps further along the walk; they cost no registers.
-    if (pf_lane) {
-      const int cg2 = cg + a.pf_dist;
-      if (cg2 < a.Wo) {
-#pragma unroll
-        for (int ar = 0; ar < NA; ++ar) {
-          const int py = r0 + ar - LO;
-          if (py >= 0 && py < a.Ho) {
-            const size_t off = ((size_t)py * a.Wo + cg2) * a.C;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gb + off));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + off));
-          }
-        }
-      }
-      const int qx2 = S * (px + a.pf_dist);
-      if (qx2 < a.W) {
-#pragma unroll
-        for (int ey = 0; ey < RI; ++ey) {
-          const int qy = S * r0 + ey;
-          if (qy < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + ((size_t)qy * a.W + qx2) * a.C));
-        }
-      }
-    }
-#endif
   }
 
   template <int PH>
   static __host__ __device__ __forceinline__ void step(State& st, const DwcArgs& a, const T* gb, const T* yb, const T* xb,
-                                                       T* ob, int r0, int px, V al, V be, V ga, V sc, V sh, V se,
-                                                       const DwcAct& ak, bool want_stats, bool pf_lane) {
-    // 1. the prefetched gradient column enters the window (slot of column px + HI)
+                                                       T* ob, int px, V al, V be, V ga, V sc, V sh, V se, const DwcAct& ak) {
+    // 1. the prefetched gradient column enters the window (slot of column px + HI), zero outside the plane
     constexpr int SLOT_NEW = (NB - 1 + PH) % NB;
     {
       const int cg = px + HI;
-      const bool col_ok = cg >= 0 && cg < a.Wo;
+      const float cm = (cg >= 0 && cg < a.Wo) ? 1.f : 0.f;
 #pragma unroll
-      for (int ar = 0; ar < NA; ++ar) {
-        const int py = r0 + ar - LO;
-        const bool ok = col_ok && py >= 0 && py < a.Ho;
-        V v = dv_fma(al, Io::cvt(st.rg[ar]), dv_fma(be, Io::cvt(st.ry[ar]), ga));
-        if (!ok) dv_set(v, 0.f);
-        st.G[ar][SLOT_NEW] = v;
-      }
+      for (int ar = 0; ar < NA; ++ar)
+        st.G[ar][SLOT_NEW] = dv_scale(dv_fma(al, Io::cvt(st.rg[ar]), dv_fma(be, Io::cvt(st.ry[ar]), ga)), st.mg[ar] * cm);
     }
     V xv[RI][S];
 #pragma unroll
@@ -305,21 +272,21 @@ struct DwcBwd {
 #pragma unroll
       for (int ex = 0; ex < S; ++ex) xv[ey][ex] = Io::cvt(st.rx[ey][ex]);
     // 2. next step's loads go out before this step's math
-    prefetch(st, a, gb, yb, xb, r0, px + 1, pf_lane);
+    prefetch(st, a, gb, yb, xb, px + 1);
     if (px < 0) return;
-    // 3. every input pixel of this step: S*r0 + ey, S*px + ex
+    // 3. every input pixel of this step: row S*r0 + ey, column S*px + ex
 #pragma unroll
-    for (int ey = 0; ey < RI; ++ey) {
-      const int qy = S * r0 + ey;
-      if (qy >= a.H) continue;
+    for (int ex = 0; ex < S; ++ex) {
+      const int qx = S * px + ex;
+      const bool col_ok = qx < a.W;
+      const uint32_t cxo = (uint32_t)(dwc_clampi(qx, 0, a.W - 1) * a.C);
 #pragma unroll
-      for (int ex = 0; ex < S; ++ex) {
-        const int qx = S * px + ex;
-        if (qx >= a.W) continue;
+      for (int ey = 0; ey < RI; ++ey) {
+        const float vm = col_ok ? st.mx[ey] : 0.f;
         const V xr = xv[ey][ex];
         const V t = dv_mul(se, dv_fma(sc, xr, sh));
-        const V xa = dwc_act(t, ak);
-        const V da = dwc_actd(t, ak);
+        const V xa = dv_scale(dwc_act(t, ak), vm);
+        const V da = dv_scale(dwc_actd(t, ak), vm);
         V acc;
         dv_set(acc, 0.f);
         const int r = ey / S, e = ey % S;
@@ -336,13 +303,23 @@ struct DwcBwd {
             st.dwa[i * K + j] = dv_fma(xa, gv, st.dwa[i * K + j]);
           }
         }
-        const V gxr = Io::st(ob + ((size_t)qy * a.W + qx) * a.C, dv_mul(acc, da));
-        if (want_stats) {
-          st.s1 = dv_add(st.s1, gxr);
-          st.s2 = dv_fma(gxr, xr, st.s2);
-        }
+        const V gxv = dv_mul(acc, da);
+        V gxr = gxv;
+        if (vm != 0.f) gxr = Io::st(ob + (st.ox[ey] + cxo), gxv);
+        st.s1 = dv_add(st.s1, gxr);
+        st.s2 = dv_fma(gxr, xr, st.s2);
       }
     }
+  }
+
+  static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcArgs& a, const T* gb, const T* yb,
+                                                             const T* xb, T* ob, int px0, int px_end, V al, V be,
+                                                             V ga, V sc, V sh, V se, const DwcAct& ak) {
+    if (px0 + 0 < px_end) step<0>(st, a, gb, yb, xb, ob, px0 + 0, al, be, ga, sc, sh, se, ak);
+    if (NB > 1 && px0 + 1 < px_end) step<(NB > 1 ? 1 : 0)>(st, a, gb, yb, xb, ob, px0 + 1, al, be, ga, sc, sh, se, ak);
+    if (NB > 2 && px0 + 2 < px_end) step<(NB > 2 ? 2 : 0)>(st, a, gb, yb, xb, ob, px0 + 2, al, be, ga, sc, sh, se, ak);
+    if (NB > 3 && px0 + 3 < px_end) step<(NB > 3 ? 3 : 0)>(st, a, gb, yb, xb, ob, px0 + 3, al, be, ga, sc, sh, se, ak);
+    if (NB > 4 && px0 + 4 < px_end) step<(NB > 4 ? 4 : 0)>(st, a, gb, yb, xb, ob, px0 + 4, al, be, ga, sc, sh, se, ak);
   }
 
   template <class Sink>
@@ -358,16 +335,10 @@ struct DwcBwd {
       dv_set(st.dwa[t], 0.f);
     }
     dv_set(st.s1, 0.f); dv_set(st.s2, 0.f);
-#pragma unroll
-    for (int ey = 0; ey < RI; ++ey)
-#pragma unroll
-      for (int ex = 0; ex < S; ++ex) st.rx[ey][ex] = Io::zero();
     V be = dwc_ldc<CPT>(a.beta + c), sc, sh;
     dv_set(sc, 1.f); dv_set(sh, 0.f);
     if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
     const DwcAct ak = dwc_make_act(a.act);
-    const bool want_stats = a.stats != nullptr;
-    const bool pf_lane = a.pf_dist > 0 && ((size_t)c * sizeof(T)) % 128 == 0;
     for (int item = il; item < a.n_items; item += a.item_lanes) {
       const int b = item / a.n_bands, band = item - b * a.n_bands;
       const int r0 = band * R;
@@ -379,19 +350,30 @@ struct DwcBwd {
       const T* yb = y + (size_t)b * a.Ho * a.Wo * a.C + c;
       const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
       T* ob = gx + (size_t)b * a.H * a.W * a.C + c;
+#pragma unroll
+      for (int ar = 0; ar < NA; ++ar) {
+        const int py = r0 + ar - LO;
+        st.og[ar] = (uint32_t)(dwc_clampi(py, 0, a.Ho - 1) * a.Wo * a.C);
+        st.mg[ar] = (py >= 0 && py < a.Ho) ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int ey = 0; ey < RI; ++ey) {
+        const int qy = S * r0 + ey;
+        st.ox[ey] = (uint32_t)(dwc_clampi(qy, 0, a.H - 1) * a.W * a.C);
+        st.mx[ey] = qy < a.H ? 1.f : 0.f;
+      }
       // window fill: steps px = -(LO+HI) .. -1 only shift columns in; compute starts at px = 0
       const int px_begin = -(LO + HI);
-      prefetch(st, a, gb, yb, xb, r0, px_begin, pf_lane);
-      for (int px0 = px_begin; px0 < a.Wo; px0 += NB) {
-        // NB phases with compile-time window slots (no register moves when the window slides)
-        run_phases(st, a, gb, yb, xb, ob, r0, px0, a.Wo, al, be, ga, sc, sh, se, ak, want_stats, pf_lane);
-      }
+      prefetch(st, a, gb, yb, xb, px_begin);
+#pragma unroll 1
+      for (int px0 = px_begin; px0 < a.Wo; px0 += NB)      // NB phases with compile-time window slots (no register moves)
+        run_phases(st, a, gb, yb, xb, ob, px0, a.Wo, al, be, ga, sc, sh, se, ak);
     }
 #pragma unroll
     for (int t = 0; t < K * K; ++t)
 #pragma unroll
       for (int i = 0; i < CPT; ++i) sink.dw(c + i, t, dv_get(st.dwa[t], i));
-    if (want_stats) {
+    if (a.stats != nullptr) {
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
         sink.stat(0, c + i, dv_get(st.s1, i));
@@ -399,18 +381,7 @@ struct DwcBwd {
       }
     }
   }
-
-  static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcArgs& a, const T* gb, const T* yb,
-                                                             const T* xb, T* ob, int r0, int px0, int px_end, V al, V be,
-                                                             V ga, V sc, V sh, V se, const DwcAct& ak, bool ws, bool pf) {
-    if (px0 + 0 < px_end) step<0>(st, a, gb, yb, xb, ob, r0, px0 + 0, al, be, ga, sc, sh, se, ak, ws, pf);
-    if (NB > 1 && px0 + 1 < px_end) step<(NB > 1 ? 1 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 1, al, be, ga, sc, sh, se, ak, ws, pf);
-    if (NB > 2 && px0 + 2 < px_end) step<(NB > 2 ? 2 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 2, al, be, ga, sc, sh, se, ak, ws, pf);
-    if (NB > 3 && px0 + 3 < px_end) step<(NB > 3 ? 3 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 3, al, be, ga, sc, sh, se, ak, ws, pf);
-    if (NB > 4 && px0 + 4 < px_end) step<(NB > 4 ? 4 : 0)>(st, a, gb, yb, xb, ob, r0, px0 + 4, al, be, ga, sc, sh, se, ak, ws, pf);
-  }
 };
-
 
 // =================================================================================================================
 // FORWARD column walker:  y = out_act( dw(act(se*(scale*x+shift))) + out_bias )   (+ per-sample sums of y, y^2)
@@ -432,7 +403,6 @@ struct DwcFwdArgs {
   int B, H, W, C, Ho, Wo;
   int n_bands, n_items, item_lanes;
   int cw, n_cchunks, ilb;
-  int pf_dist;
 };
 
 template <typename T, int K, int S, int R, int CPT>
@@ -443,84 +413,65 @@ struct DwcFwd {
   static constexpr int PAD = (K - 1) / 2;
   static constexpr int NAI = S * (R - 1) + K;        // input rows of a band
   static constexpr int PXB = -((K - 1) / S);         // first (fill) step: every window column of step 0 has entered by then
-  static constexpr int QX0 = S * PXB + PAD - S + 1;  // first input column that ever enters the window
 
   struct State {
     V Wn[NAI][K];       // transformed input window
     V wt[K * K];
     Raw rx[NAI][S];     // prefetched raw input columns of the next step
+    uint32_t ox[NAI];   // per item: clamped element offset of input row ai
+    uint32_t oy[R];     // ... of output row r
+    float mx[NAI];      // 1 inside the image, 0 in the padding
   };
 
-  static __host__ __device__ __forceinline__ void prefetch(State& st, const DwcFwdArgs& a, const T* xb, int r0, int px,
-                                                           bool pf_lane) {
+  static __host__ __device__ __forceinline__ void prefetch(State& st, const DwcFwdArgs& a, const T* xb, int px) {
 #pragma unroll
     for (int e = 0; e < S; ++e) {
-      const int qx = S * px + PAD - S + 1 + e;
-      const bool col_ok = qx >= 0 && qx < a.W;
+      const uint32_t cxo = (uint32_t)(dwc_clampi(S * px + PAD - S + 1 + e, 0, a.W - 1) * a.C);
 #pragma unroll
-      for (int ai = 0; ai < NAI; ++ai) {
-        const int qy = S * r0 - PAD + ai;
-        st.rx[ai][e] = Io::zero();
-        if (col_ok && qy >= 0 && qy < a.H) st.rx[ai][e] = Io::ld(xb + ((size_t)qy * a.W + qx) * a.C);
-      }
+      for (int ai = 0; ai < NAI; ++ai) st.rx[ai][e] = Io::ld(xb + (st.ox[ai] + cxo));
     }
-#ifdef __CUDA_ARCH__
-    if (pf_lane) {
-      const int qx2 = S * (px + a.pf_dist) + PAD;
-      if (qx2 < a.W) {
-#pragma unroll
-        for (int ai = 0; ai < NAI; ++ai) {
-          const int qy = S * r0 - PAD + ai;
-          if (qy >= 0 && qy < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + ((size_t)qy * a.W + qx2) * a.C));
-        }
-      }
-    }
-#endif
   }
 
   template <int PH>
   static __host__ __device__ __forceinline__ void step(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0, int px,
                                                        V sc, V sh, V se, const DwcAct& ak, V ob_bias, const DwcAct& oak,
-                                                       V& s1, V& s2, bool pf_lane) {
+                                                       V& s1, V& s2) {
     // 1. the prefetched columns enter the window, transformed once (zero outside the image: conv padding)
 #pragma unroll
     for (int e = 0; e < S; ++e) {
       const int qx = S * px + PAD - S + 1 + e;
-      const bool col_ok = qx >= 0 && qx < a.W;
+      const float cm = (qx >= 0 && qx < a.W) ? 1.f : 0.f;
 #pragma unroll
-      for (int ai = 0; ai < NAI; ++ai) {
-        const int qy = S * r0 - PAD + ai;
-        V v = dwc_act(dv_mul(se, dv_fma(sc, Io::cvt(st.rx[ai][e]), sh)), ak);
-        if (!(col_ok && qy >= 0 && qy < a.H)) dv_set(v, 0.f);
-        st.Wn[ai][(S * PH + e) % K] = v;
-      }
+      for (int ai = 0; ai < NAI; ++ai)
+        st.Wn[ai][(S * PH + e) % K] = dv_scale(dwc_act(dv_mul(se, dv_fma(sc, Io::cvt(st.rx[ai][e]), sh)), ak), st.mx[ai] * cm);
     }
-    prefetch(st, a, xb, r0, px + 1, pf_lane);
+    prefetch(st, a, xb, px + 1);
     if (px < 0) return;
     // 2. R outputs of this column
+    const uint32_t cyo = (uint32_t)(px * a.C);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int py = r0 + r;
-      if (py >= a.Ho) continue;
       V acc = ob_bias;
 #pragma unroll
       for (int i = 0; i < K; ++i)
 #pragma unroll
         for (int j = 0; j < K; ++j) acc = dv_fma(st.wt[i * K + j], st.Wn[S * r + i][(S * PH + j + S) % K], acc);
-      const V yr = Io::st(ob + ((size_t)py * a.Wo + px) * a.C, dwc_act(acc, oak));
-      s1 = dv_add(s1, yr);
-      s2 = dv_fma(yr, yr, s2);
+      if (r0 + r < a.Ho) {
+        const V yr = Io::st(ob + (st.oy[r] + cyo), dwc_act(acc, oak));
+        s1 = dv_add(s1, yr);
+        s2 = dv_fma(yr, yr, s2);
+      }
     }
   }
 
   static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0,
                                                              int px0, V sc, V sh, V se, const DwcAct& ak, V obb,
-                                                             const DwcAct& oak, V& s1, V& s2, bool pf) {
-    if (px0 + 0 < a.Wo) step<0>(st, a, xb, ob, r0, px0 + 0, sc, sh, se, ak, obb, oak, s1, s2, pf);
-    if (K > 1 && px0 + 1 < a.Wo) step<(K > 1 ? 1 : 0)>(st, a, xb, ob, r0, px0 + 1, sc, sh, se, ak, obb, oak, s1, s2, pf);
-    if (K > 2 && px0 + 2 < a.Wo) step<(K > 2 ? 2 : 0)>(st, a, xb, ob, r0, px0 + 2, sc, sh, se, ak, obb, oak, s1, s2, pf);
-    if (K > 3 && px0 + 3 < a.Wo) step<(K > 3 ? 3 : 0)>(st, a, xb, ob, r0, px0 + 3, sc, sh, se, ak, obb, oak, s1, s2, pf);
-    if (K > 4 && px0 + 4 < a.Wo) step<(K > 4 ? 4 : 0)>(st, a, xb, ob, r0, px0 + 4, sc, sh, se, ak, obb, oak, s1, s2, pf);
+                                                             const DwcAct& oak, V& s1, V& s2) {
+    if (px0 + 0 < a.Wo) step<0>(st, a, xb, ob, r0, px0 + 0, sc, sh, se, ak, obb, oak, s1, s2);
+    if (K > 1 && px0 + 1 < a.Wo) step<(K > 1 ? 1 : 0)>(st, a, xb, ob, r0, px0 + 1, sc, sh, se, ak, obb, oak, s1, s2);
+    if (K > 2 && px0 + 2 < a.Wo) step<(K > 2 ? 2 : 0)>(st, a, xb, ob, r0, px0 + 2, sc, sh, se, ak, obb, oak, s1, s2);
+    if (K > 3 && px0 + 3 < a.Wo) step<(K > 3 ? 3 : 0)>(st, a, xb, ob, r0, px0 + 3, sc, sh, se, ak, obb, oak, s1, s2);
+    if (K > 4 && px0 + 4 < a.Wo) step<(K > 4 ? 4 : 0)>(st, a, xb, ob, r0, px0 + 4, sc, sh, se, ak, obb, oak, s1, s2);
   }
 
   // `Sink::stat(b, which, c, value)` receives the per-sample sums of one item
@@ -531,16 +482,11 @@ struct DwcFwd {
     State st;
 #pragma unroll
     for (int t = 0; t < K * K; ++t) st.wt[t] = dwc_ldc<CPT>(a.w_taps + (size_t)t * a.C + c);
-#pragma unroll
-    for (int ai = 0; ai < NAI; ++ai)
-#pragma unroll
-      for (int e = 0; e < S; ++e) st.rx[ai][e] = Io::zero();
     V sc, sh, obb;
     dv_set(sc, 1.f); dv_set(sh, 0.f); dv_set(obb, 0.f);
     if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
     if (a.out_bias) obb = dwc_ldc<CPT>(a.out_bias + c);
     const DwcAct ak = dwc_make_act(a.act), oak = dwc_make_act(a.out_act);
-    const bool pf_lane = a.pf_dist > 0 && ((size_t)c * sizeof(T)) % 128 == 0;
     for (int item = il; item < a.n_items; item += a.item_lanes) {
       const int b = item / a.n_bands, band = item - b * a.n_bands;
       const int r0 = band * R;
@@ -549,10 +495,19 @@ struct DwcFwd {
       if (a.se) se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
       const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
       T* ob = y + (size_t)b * a.Ho * a.Wo * a.C + c;
+#pragma unroll
+      for (int ai = 0; ai < NAI; ++ai) {
+        const int qy = S * r0 - PAD + ai;
+        st.ox[ai] = (uint32_t)(dwc_clampi(qy, 0, a.H - 1) * a.W * a.C);
+        st.mx[ai] = (qy >= 0 && qy < a.H) ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) st.oy[r] = (uint32_t)(dwc_clampi(r0 + r, 0, a.Ho - 1) * a.Wo * a.C);
       V s1, s2;
       dv_set(s1, 0.f); dv_set(s2, 0.f);
-      prefetch(st, a, xb, r0, PXB, pf_lane);
-      for (int px0 = PXB; px0 < a.Wo; px0 += K) run_phases(st, a, xb, ob, r0, px0, sc, sh, se, ak, obb, oak, s1, s2, pf_lane);
+      prefetch(st, a, xb, PXB);
+#pragma unroll 1
+      for (int px0 = PXB; px0 < a.Wo; px0 += K) run_phases(st, a, xb, ob, r0, px0, sc, sh, se, ak, obb, oak, s1, s2);
       if (a.stats) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {

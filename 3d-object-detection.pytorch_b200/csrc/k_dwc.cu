@@ -53,12 +53,12 @@ __global__ void __launch_bounds__(256, 2) dwc_bwd_kernel(DwcArgs a) {
   }
 }
 
-// TD3D_DWC_PF: L2 prefetch distance in walk steps (tuning; 0 disables)
-int pf_dist() {
+// TD3D_DWC_TALL=0 (tuning): 2-row bands also on tall planes (fewer registers, no spills, more halo re-reads)
+int tall_bands() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TD3D_DWC_PF");
-    v = e ? atoi(e) : 0;       // measured (r02 call B): 13.9 ms/step with 0 vs 14.5 ms with 6 or 12 -- off by default
+    const char* e = getenv("TD3D_DWC_TALL");
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
@@ -83,7 +83,6 @@ int dwc_launch(const DwBwdArgs& b, cudaStream_t st) {
   a.B = b.B; a.H = b.H; a.W = b.W; a.C = b.C;
   a.Ho = (b.H - 1) / S + 1; a.Wo = (b.W - 1) / S + 1;
   a.slots = b.B;
-  a.pf_dist = pf_dist();
   a.n_bands = ceil_div(a.Ho, R);
   a.n_items = a.B * a.n_bands;
   const int ncg = a.C / CPT;
@@ -115,7 +114,7 @@ template <typename T>
 int dwc_dispatch(const DwBwdArgs& b, cudaStream_t st) {
   const int Ho = (b.H - 1) / b.stride + 1;
   // R output rows per band: tall planes take 4 (less halo), short ones 2 (more items to spread)
-  const bool tall = Ho >= 28;
+  const bool tall = Ho >= 28 && tall_bands();
   if (b.k == 3 && b.stride == 1) return tall ? dwc_launch<T, 3, 1, 4, 2>(b, st) : dwc_launch<T, 3, 1, 2, 2>(b, st);
   if (b.k == 3 && b.stride == 2) return tall ? dwc_launch<T, 3, 2, 2, 2>(b, st) : dwc_launch<T, 3, 2, 1, 2>(b, st);
   if (b.k == 5 && b.stride == 1) return dwc_launch<T, 5, 1, 2, 1>(b, st);
@@ -152,7 +151,6 @@ int dwc_fwd_launch(const DwArgs& b, cudaStream_t st) {
   a.w_taps = b.w_taps; a.out_bias = b.out_bias; a.out_act = b.out_act; a.y = b.y; a.stats = b.stats;
   a.B = b.B; a.H = b.H; a.W = b.W; a.C = b.C;
   a.Ho = (b.H - 1) / S + 1; a.Wo = (b.W - 1) / S + 1;
-  a.pf_dist = pf_dist();
   a.n_bands = ceil_div(a.Ho, R);
   a.n_items = a.B * a.n_bands;
   const int ncg = a.C / CPT;
@@ -177,7 +175,7 @@ int dwc_fwd_launch(const DwArgs& b, cudaStream_t st) {
 template <typename T>
 int dwc_fwd_dispatch(const DwArgs& b, cudaStream_t st) {
   const int Ho = (b.H - 1) / b.stride + 1;
-  const bool tall = Ho >= 28;
+  const bool tall = Ho >= 28 && tall_bands();
   if (b.k == 3 && b.stride == 1) return tall ? dwc_fwd_launch<T, 3, 1, 4, 2>(b, st) : dwc_fwd_launch<T, 3, 1, 2, 2>(b, st);
   if (b.k == 3 && b.stride == 2) return tall ? dwc_fwd_launch<T, 3, 2, 2, 2>(b, st) : dwc_fwd_launch<T, 3, 2, 1, 2>(b, st);
   if (b.k == 5 && b.stride == 1) return dwc_fwd_launch<T, 5, 1, 2, 1>(b, st);

@@ -1289,6 +1289,13 @@ int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, f
   return TD3D_OK;
 }
 
+int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n_boxes,
+                         int out_h, int out_w, const float* mean255, const float* inv_std255, int swap_rb, float* out,
+                         void* stream) {
+  return launch_roi_crop_resize(frames, n_frames, frame_h, frame_w, boxes, n_boxes, out_h, out_w, mean255, inv_std255, swap_rb,
+                                out, (cudaStream_t)stream);
+}
+
 // ---- per-kernel entry points ----------------------------------------------------------------
 int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W, int C, int dtype,
                     void* stream) {

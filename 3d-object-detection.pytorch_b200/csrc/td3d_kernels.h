@@ -121,6 +121,10 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st);       // bf16 only
 bool tc_gemm_supported(int M, int N, int K);
 int tc_timeline_read(unsigned long long* out, int n);   // debug: pipeline event times of CTA 0 (TD3D_TC_DBG & 32)
 
+// ---- k_roi.cu ----
+int launch_roi_crop_resize(const uint8_t* frames, int n_frames, int fh, int fw, const int32_t* boxes, int n_boxes, int oh,
+                           int ow, const float* mean255, const float* inv_std255, int swap_rb, float* out, cudaStream_t st);
+
 // ---- k_heads.cu ----
 struct HeadsArgs {
   const void* feat;                 // T [B,C]

@@ -5,7 +5,7 @@ Same sub-package names as the reference (`builders`, `models`, `losses`, `traine
 `evaluation`, `utils`); everything outside the hot path (data loading, augmentation, geometry,
 tracking, OpenVINO export/demo) is intentionally absent -- see DESIGN.md.
 """
-from . import _lib, utils, models, losses, evaluation, builders, trainer, inference  # noqa: F401
+from . import _lib, utils, models, losses, evaluation, builders, trainer, inference, preprocess  # noqa: F401
 from .inference import InferSession  # noqa: F401
 
 __version__ = "0.1.0"

@@ -45,6 +45,12 @@ class InferSession:
         """Stage the crops (pinned host or device tensor) into the static device buffer."""
         self.imgs.copy_(imgs, non_blocking=True)
 
+    def load_rois(self, frames, boxes, **kw):
+        """Fill the batch straight from uint8 frames + detector boxes (preprocess.crop_resize_normalize): the fp32 crops
+        are produced on the device, only the frames cross PCIe."""
+        from .preprocess import crop_resize_normalize
+        crop_resize_normalize(frames, boxes, size=tuple(self.imgs.shape[2:]), out=self.imgs, **kw)
+
     def run(self):
         m = self.model
         m.eval()

@@ -187,6 +187,18 @@ int td3d_metrics_accum(const float* kp, const float* gt_kp, const float* logits,
 int td3d_optim_step(td3d_plan* plan, const td3d_optim_desc* desc, float* state0, float* state1,
                     int32_t* steps, const int32_t* head_present, void* stream);
 
+/* ---- ROI front-end: the step before the path ----------------------------------
+ * Replaces, per detector box, Regressor.crop + IEModel._preprocess (torchdet3d/utils/ie_wrappers.py:155-158,18-21:
+ * frame[y0:y1, x0:x1] -> cv.resize(img, (w, h)) -> transpose(2,0,1)), ConvertColor (utils/transforms.py:10-17) and the
+ * test-time Normalize (configs/default_config.py:9-10), bit-exact with OpenCV's uint8 INTER_LINEAR.
+ * frames  device u8  [n_frames, frame_h, frame_w, 3]
+ * boxes   device i32 [n_boxes, 5]: frame index, x0, y0, x1, y1 (x1 / y1 exclusive; clamped to the frame)
+ * mean255 / inv_std255  HOST f32 [3]: mean*255 and 1/(std*255) per output channel
+ * out     device f32 [n_boxes, 3, out_h, out_w] -- the `img` argument of td3d_forward / td3d_forward_export       */
+int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes,
+                         int n_boxes, int out_h, int out_w, const float* mean255, const float* inv_std255,
+                         int swap_rb, float* out, void* stream);
+
 /* ---- per-kernel entry points (unit tests / profiling) -------------------------------------- */
 int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W,
                     int C, int dtype, void* stream);

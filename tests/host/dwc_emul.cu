@@ -61,7 +61,7 @@ static int run_case(int B, int H, int W, int C, int act, bool with_xf, int item_
   a.B = B; a.H = H; a.W = W; a.C = C; a.Ho = Ho; a.Wo = Wo; a.slots = B;
   a.n_bands = (Ho + R - 1) / R; a.n_items = B * a.n_bands;
   a.item_lanes = item_lanes_req < a.n_items ? item_lanes_req : a.n_items;
-  a.cw = 0; a.n_cchunks = 0; a.ilb = 0; a.pf_dist = 0;
+  a.cw = 0; a.n_cchunks = 0; a.ilb = 0;
   std::vector<double> dw((size_t)C * KK, 0.0), st(2 * (size_t)C, 0.0);
   HostSink sink = {&dw, &st, KK, C};
   for (int c = 0; c < C; c += CPT)
@@ -166,7 +166,7 @@ static int run_fwd_case(int B, int H, int W, int C, int act, bool with_xf, int o
   a.B = B; a.H = H; a.W = W; a.C = C; a.Ho = Ho; a.Wo = Wo;
   a.n_bands = (Ho + R - 1) / R; a.n_items = B * a.n_bands;
   a.item_lanes = lanes_req < a.n_items ? lanes_req : a.n_items;
-  a.cw = 0; a.n_cchunks = 0; a.ilb = 0; a.pf_dist = 0;
+  a.cw = 0; a.n_cchunks = 0; a.ilb = 0;
   std::vector<double> st((size_t)B * 2 * C, 0.0), rst((size_t)B * 2 * C, 0.0);
   HostFwdSink sink = {&st, C};
   for (int c = 0; c < C; c += CPT)
