@@ -200,6 +200,7 @@ struct TcNtParams {
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
   int tma_store;        // 1: bf16 output leaves through swizzled smem + cp.async.bulk.tensor (coalesced), else st.global
+  int epi_groups;       // active epilogue groups = min(TC_EPI_GROUPS, n_acc), see the hand-off note in the epilogue
   int mma_warps;        // 1 or 2 MMA issuer warps (2 only when a tile's k blocks of both issuers fit the smem ring at once:
                         // a parity wait must never be more than one phase away from its barrier)
   int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
@@ -336,7 +337,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
     uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
-    for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; tile < num_tiles; tile += TC_EPI_GROUPS * gridDim.x, ti += TC_EPI_GROUPS) {
+    // Accumulator hand-off safety (root cause of the round-1 "launch failure at batch >= 1024" and of the rare aborts of
+    // stat-less GEMMs): tile ti uses barrier s_tfull[ti % n_acc]; a group that finished tile ti waits next for tile
+    // ti + G on barrier (ti + G) % n_acc with a PARITY wait, which is only meaningful if the previous phase of that
+    // barrier -- tile ti + G - n_acc -- has already completed.  With one in-order issuer that holds iff
+    // ti + G - n_acc <= ti, i.e. G <= n_acc.  Wide tiles (block_n > 128 -> n_acc = 2) with 3 groups broke it: the group
+    // could pass a wait on the not-yet-committed tile ti + 1, read a stage still being drained and release it early.
+    // Hence only min(TC_EPI_GROUPS, n_acc) groups take tiles.
+    const int G = p.epi_groups;
+    for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; eg < G && tile < num_tiles; tile += G * gridDim.x, ti += G) {
       const int m_tile = p.n_tiles == 1 ? tile : tile / p.n_tiles;
       const int m0 = m_tile * TC_BLOCK_M, n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
       mbar_wait(smem_u32(&s_tfull[as]), aphase);
@@ -440,7 +449,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
       }
       if (q == 2 && lane == 0) TC_STAMP(7, ti);
-      as += TC_EPI_GROUPS;                       // stage / phase of tile ti + TC_EPI_GROUPS
+      as += G;                                   // stage / phase of tile ti + G
       while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
     if (p.tma_store && lane == 0) bulk_wait_all();
@@ -675,6 +684,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
   if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
+  p.epi_groups = p.n_acc < TC_EPI_GROUPS ? p.n_acc : TC_EPI_GROUPS;
   CUtensorMap map_a, map_w, map_y;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
