@@ -28,20 +28,26 @@ int launch_dw_fwd(const DwArgs& a, int dtype, cudaStream_t st) {
   return launch_dw_fwd_v2(a, dtype, st);
 }
 
-// Measured on B200 (r02 call B, MobileNetV3-large batch 256): the one-pass column walker is correct but SLOWER than the
-// two-kernel backward of round 1 (5.25 ms vs 3.85 ms per step over the 15 layers; it stalls on its one-step-ahead
-// register prefetch at 16 warps / SM), so it is used where only it applies -- SiLU (EfficientNet) -- and the split
-// kernels stay the default.  TD3D_DW_BWD_FUSED=1 forces the one-pass kernel everywhere (A/B measurements).
-static int dw_bwd_fused() {
-  static int v = -1;
-  if (v < 0) {
+// Backward implementation choice, measured per layer on B200 (scripts/dw_bench.py, profiles/r02_dw_bench.txt, batch 256
+// bf16): after the inner-loop clean-up the one-pass column walker beats the two-kernel backward of round 1 on every
+// MobileNetV3-large layer (e.g. 112x112x64 s2: 407 vs 661 us, 56x56x72: 237 vs 604 us, 14x14x672 k5 s2: 209 vs 290 us)
+// except the 7x7 5x5 layers (210 vs 177 us: 49-pixel planes give a thread only 7 columns to walk between flushes of its 25
+// tap accumulators).  In the model: 12.65 vs 13.08 ms per step.  SiLU layers (EfficientNet) exist only in the one-pass
+// kernel.  TD3D_DW_BWD_FUSED=0 / 1 forces the split / one-pass kernels everywhere (A/B measurements).
+static int dw_bwd_force() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("TD3D_DW_BWD_FUSED");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : -1;
   }
   return v;
 }
 
-bool dw_bwd_is_split(const DwBwdArgs& a) { return !(dw_bwd_fused() || a.xf.act == TD3D_ACT_SILU); }
+bool dw_bwd_is_split(const DwBwdArgs& a) {
+  if (a.xf.act == TD3D_ACT_SILU) return false;
+  if (dw_bwd_force() >= 0) return dw_bwd_force() == 0;
+  return a.k == 5 && a.stride == 1 && a.H * a.W <= 64;
+}
 
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw bwd: C=%d must be a multiple of 8", a.C);

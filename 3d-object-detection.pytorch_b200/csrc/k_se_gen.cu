@@ -37,9 +37,13 @@ __global__ void __launch_bounds__(256) se_gen_fwd_kernel(SeArgs a) {
   }
   __syncthreads();
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float* w = a.w2 + (size_t)c * a.Ch;
     float acc = a.b2[c];
-    for (int h = 0; h < a.Ch; ++h) acc = fmaf(__ldg(w + h), hs[h], acc);
+    if (a.w2t) {                                         // W2^T [Ch, C]: lanes read consecutive channels
+      for (int h = 0; h < a.Ch; ++h) acc = fmaf(__ldg(a.w2t + (size_t)h * a.C + c), hs[h], acc);
+    } else {
+      const float* w = a.w2 + (size_t)c * a.Ch;
+      for (int h = 0; h < a.Ch; ++h) acc = fmaf(__ldg(w + h), hs[h], acc);
+    }
     a.pre[(size_t)b * a.C + c] = acc;
     a.gate[(size_t)b * a.C + c] = seg_sigmoid(acc);
   }

@@ -597,7 +597,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
       SeArgs s;
       s.w1 = c.P(b.se_w1); s.b1 = c.P(b.se_b1); s.w2 = c.P(b.se_w2); s.b2 = c.P(b.se_b2);
       s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
-      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
+      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo; s.w2t = c.pkf(b.pse_w2t);
       if (!b.se_post) {    // BN -> SE -> act (mobilenetv3.py:153-156): squeeze from the dw epilogue sums
         s.pool_stats = c.wsf(pl->bns[b.bn2].fstats); s.scale = sc; s.shift = sh;
         TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
@@ -699,7 +699,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
       SeArgs s;
       s.w1 = c.P(b.se_w1); s.b1 = c.P(b.se_b1); s.w2 = c.P(b.se_w2); s.b2 = c.P(b.se_b2);
       s.zbar = c.wsf(b.zbar); s.hid = c.wsf(b.hid); s.pre = c.wsf(b.pre); s.gate = c.wsf(b.gate);
-      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo;
+      s.B = B; s.C = E; s.Ch = b.d.se_hidden; s.inv_hw = 1.f / (float)HWo; s.w2t = c.pkf(b.pse_w2t);
       s.pool_stats = sq; s.scale = nullptr; s.shift = nullptr;
       TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
       TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(nullptr, nullptr, s.gate, act_in_dw ? TD3D_ACT_NONE : act), nullptr, c.ws(b.h2),

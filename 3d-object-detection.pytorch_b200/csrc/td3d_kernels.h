@@ -43,6 +43,7 @@ struct SeArgs {
   const float* w1; const float* b1; const float* w2; const float* b2;   // fc.0 [Ch,C], fc.2 [C,Ch]
   float* zbar; float* hid; float* pre; float* gate;    // [B,C] [B,Ch] [B,C] [B,C]
   int B; int C; int Ch;
+  const float* w2t = nullptr;                          // general flavour: packed W2^T [Ch,C] (coalesced), optional
 };
 int launch_se_fwd(const SeArgs& a, cudaStream_t st);
 int launch_se_gen_fwd(const SeArgs& a, cudaStream_t st);   // k_se_gen.cu: sigmoid gate / SiLU hidden, any Ch (hid holds the hidden PRE-activation)
