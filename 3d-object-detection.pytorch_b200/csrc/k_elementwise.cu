@@ -89,7 +89,8 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
         // branch-free activation from per-kernel constants: the `act` switch cost two uniform compare+branch
         // pairs per element (ncu: 30 % of the issued instructions)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = actk_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), ak);
+        for (int i = 0; i < 8; ++i)
+          v[i] = xf.se_post ? actk_fwd(fmaf(v[i], sc[i], sh[i]), ak) * se[i] : actk_fwd(se[i] * fmaf(v[i], sc[i], sh[i]), ak);
         if (res) {
           float r[8];
           rr[u].get(r);
@@ -99,7 +100,7 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
         if (out) store8(ob + off, v);
         if (stats) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];
+          for (int i = 0; i < 8; ++i) acc[i] += out ? to_f(from_f<T>(v[i])) : v[i];   // pooled sums of what the consumer reads
         }
       }
     }
@@ -147,7 +148,10 @@ affine2_kernel(const T* g, const T* __restrict__ y, const float* __restrict__ al
 }
 
 // gu = g * act'(u(y));  stats[b][0][c] += sum gu ; stats[b][1][c] += sum gu*y
-// g_pooled != nullptr: the incoming gradient is g_pooled[b,c] * g_scale for every pixel (avg-pool bwd)
+// g_pooled != nullptr, g == nullptr: the incoming gradient is g_pooled[b,c] * g_scale for every pixel (avg-pool bwd)
+// SE after the activation (xf.se_post, x = act(z)*se with z = scale*y+shift):
+//   gu == nullptr            : statistics only, second sum = sum g*act(z)  (= d loss / d gate, what the SE backward needs)
+//   gu != nullptr, g_pooled  : gu = (se*g + g_pooled*g_scale) * act'(z)    (gate path + squeeze path in one pass)
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS, 2)
 act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_scale,
@@ -180,9 +184,9 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
     const int p1 = min(HW, p0 + pix_per_block);
     const size_t base = (size_t)b * HW * C + c;          // per-thread base; pixel offsets p*C fit 32 bits
     const T* yb = y + base;
-    const T* gb = g_pooled ? nullptr : g + base;
+    const T* gb = (g_pooled && !xf.se_post) ? nullptr : g + base;
     const T* ab = addend ? addend + base : nullptr;
-    T* ub = gu + base;
+    T* ub = gu ? gu + base : nullptr;
     // batches of EW_U pixels: all loads of a batch are issued before the first use (memory-level parallelism)
     for (int pb = p0 + pl; pb < p1; pb += PL * EW_U) {
       RawV8<T> rg[EW_U], ry[EW_U], ra[EW_U];
@@ -192,7 +196,7 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
         if (p < p1) {
           const uint32_t off = (uint32_t)p * (uint32_t)C;
           ry[u].load(yb + off);
-          if (!g_pooled) rg[u].load(gb + off);
+          if (gb) rg[u].load(gb + off);
           if (addend) ra[u].load(ab + off);
         }
       }
@@ -203,7 +207,7 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
         const uint32_t off = (uint32_t)p * (uint32_t)C;
         float gv[8], yv[8];
         ry[u].get(yv);
-        if (g_pooled) {
+        if (!gb) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) gv[i] = gp[i];
         } else {
@@ -215,15 +219,23 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
 #pragma unroll
           for (int i = 0; i < 8; ++i) gv[i] += ad[i];
         }
+        if (!xf.se_post) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float uu = se[i] * fmaf(yv[i], sc[i], sh[i]);
-          gv[i] *= actk_bwd(uu, ak);
+          for (int i = 0; i < 8; ++i) {
+            const float uu = se[i] * fmaf(yv[i], sc[i], sh[i]);
+            gv[i] *= actk_bwd(uu, ak);
+          }
+        } else if (ub) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv[i] = fmaf(se[i], gv[i], gp[i]) * actk_bwd(fmaf(yv[i], sc[i], sh[i]), ak);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) yv[i] = actk_fwd(fmaf(yv[i], sc[i], sh[i]), ak);   // second sum pairs g with act(z)
         }
-        store8(ub + off, gv);
+        if (ub) store8(ub + off, gv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float r = to_f(from_f<T>(gv[i]));      // statistics of the stored (rounded) gradient
+          const float r = ub ? to_f(from_f<T>(gv[i])) : gv[i];      // statistics of the stored (rounded) gradient
           a1[i] += r;
           a2[i] = fmaf(r, yv[i], a2[i]);
         }

@@ -338,7 +338,6 @@ static int build(td3d_plan* pl) {
     const int64_t Mi = (int64_t)B * b.Hin * b.Win, Mo = (int64_t)B * b.Hout * b.Wout;
     if (b.expand) b.y1 = act(Mi, b.d.exp_ch);
     b.y2 = act(Mo, b.d.exp_ch);
-    if (b.se_post) b.h = act(Mo, b.d.exp_ch);
     b.h2 = act(Mo, b.d.exp_ch);
     b.y3 = act(Mo, b.d.out_ch);
     b.out = act(Mo, b.d.out_ch);
@@ -552,8 +551,8 @@ static int se_backward(const Ctx& c, const SeBwdArgs& s) {
   return c.pl->se_kind ? launch_se_gen_bwd(s, c.st) : launch_se_bwd(s, c.st);
 }
 
-static XForm xf_make(const float* scale, const float* shift, const float* se, int act) {
-  XForm x; x.scale = scale; x.shift = shift; x.se = se; x.act = act;
+static XForm xf_make(const float* scale, const float* shift, const float* se, int act, int se_post = 0) {
+  XForm x; x.scale = scale; x.shift = shift; x.se = se; x.act = act; x.se_post = se_post;
   return x;
 }
 
@@ -603,10 +602,12 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
         TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
         TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, s.gate, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
       } else {             // BN -> act -> SE (mobilenetv3.py:137-140; every torchvision MBConv)
-        TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h), c.wsf(b.hstats), B, HWo, E, dt, c.st));
+        // squeeze = mean of act(BN(y2)): a read-only pooling pass (act(BN(y2)) itself is never materialised), then ONE
+        // apply pass h2 = act(BN(y2)) * gate
+        TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, nullptr, c.wsf(b.hstats), B, HWo, E, dt, c.st));
         s.pool_stats = c.wsf(b.hstats); s.scale = nullptr; s.shift = nullptr;
         TD3D_K(PK_SE, 8.0 * b.d.exp_ch * b.d.se_hidden, se_forward(c, s));
-        TD3D_TRY(p_xform(c, c.ws(b.h), xf_make(nullptr, nullptr, s.gate, TD3D_ACT_NONE), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
+        TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, s.gate, act, 1), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
       }
     } else {
       TD3D_TRY(p_xform(c, c.ws(b.y2), xf_make(sc, sh, nullptr, act), nullptr, c.ws(b.h2), nullptr, B, HWo, E, dt, c.st));
@@ -906,17 +907,18 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       TD3D_TRY(bn_backward(c, b.bn2, HWo, gate, c.wsf(pl->se_gpool), c.wsf(bn2.fstats)));
     } else {
       if (b.d.use_se) {
-        // x = H * gate with H = act(BN(y2)):  g_H = gate*g_x + g_pool/HW
-        TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.h), xf_make(nullptr, nullptr, c.wsf(b.gate), TD3D_ACT_NONE), gw,
-                                      c.wsf(b.hbstats), B, HWo, E, dt, c.st));
+        // x = H * gate with H = act(BN(y2)), H recomputed from y2:
+        //   pass 1 (read only): d loss / d gate = sum_HW g_x * H        -> SE backward -> g_pool (gradient of the squeeze)
+        //   pass 2            : g_z = (gate*g_x + g_pool/HW) * act'(z)  + the BatchNorm-backward sums of bn2
+        TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act, 1), nullptr, c.wsf(b.hbstats), B, HWo,
+                                      E, dt, c.st));
         TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, se_backward(c, se_bwd_args(c.wsf(b.hbstats), nullptr, nullptr)));
-        scale_kernel<<<ceil_div(B * E, 256), 256, 0, c.st>>>(c.wsf(pl->se_gpool), 1.f / (float)HWo, c.wsf(pl->se_gpool_scaled), B * E);
-        TD3D_LAUNCH_CHECK();
-        TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->zeros_c), 0, sizeof(float) * E, c.st));
-        TD3D_TRY(p_affine2(c, gw, c.ws(b.h), c.wsf(b.gate), c.wsf(pl->zeros_c), c.wsf(pl->se_gpool_scaled), gw, B, HWo, E, dt, c.st));
+        TD3D_TRY(p_actbwd(c, gw, c.wsf(pl->se_gpool), 1.f / (float)HWo, c.ws(b.y2), xf_make(sc2, sh2, c.wsf(b.gate), act, 1), gw,
+                                      c.wsf(bn2.bstats), B, HWo, E, dt, c.st));
+      } else {
+        TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
+                                      dt, c.st));
       }
-      TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
-                                    dt, c.st));
       TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
     }
     // depthwise conv backward (data + weights)

@@ -51,6 +51,8 @@ struct XForm {
   const float* shift;  // [C]
   const float* se;     // [B,C] or nullptr
   int act;             // TD3D_ACT_*
+  int se_post;         // 0: x = act(se*(scale*y+shift)) (MobileNetV3 expanded block); 1: x = act(scale*y+shift)*se (SE after the
+                       // activation: torchvision MBConv, MobileNetV3 dw-first block) -- honoured by the elementwise kernels only
 };
 
 #ifdef __CUDACC__
