@@ -612,9 +612,30 @@ static int make_map_2d(CUtensorMap* map, const void* base, int rows, int cols, i
   return TD3D_OK;
 }
 
-static int env_int(const char* name, int dflt) {
+static int env_raw(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
+}
+// Tuning / debugging knobs of the NT GEMM.  Read ONCE (getenv on every eager launch showed up in host profiles);
+// TD3D_TC_LIVE_ENV=1 (micro-benchmarks that flip knobs inside one process) re-reads them on every launch.
+struct TcKnobs { int force_sw128, no_wres, tma_store, lbo, dbg, two_issuers, max_bn, tn_swap; };
+static TcKnobs read_knobs() {
+  TcKnobs k;
+  k.force_sw128 = env_raw("TD3D_TC_FORCE_SW128", 0);
+  k.no_wres = env_raw("TD3D_TC_NO_WRES", 0);
+  k.tma_store = env_raw("TD3D_TC_TMA_STORE", 0);
+  k.lbo = env_raw("TD3D_TC_LBO", 16);
+  k.dbg = env_raw("TD3D_TC_DBG", 0);
+  k.two_issuers = env_raw("TD3D_TC_TWO_ISSUERS", 0);
+  k.max_bn = env_raw("TD3D_TC_MAXBN", 256);
+  k.tn_swap = env_raw("TD3D_TC_TN_SWAP", 0);
+  return k;
+}
+static const TcKnobs& knobs() {
+  static const bool live = env_raw("TD3D_TC_LIVE_ENV", 0) != 0;
+  static TcKnobs k = read_knobs();
+  if (live) k = read_knobs();
+  return k;
 }
 
 int tc_timeline_read(unsigned long long* out, int n) {
@@ -641,15 +662,17 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   TD3D_REQUIRE(((uintptr_t)g.a & 15) == 0 && ((uintptr_t)g.w & 15) == 0, "gemm_nt_tc: operands must be 16B aligned");
   TcNtParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
+  const TcKnobs& kn = knobs();
   int sw = 128;
-  if (!env_int("TD3D_TC_FORCE_SW128", 0)) {
+  if (!kn.force_sw128) {
     if (g.K <= 16) sw = 32;
     else if (g.K <= 32) sw = 64;
   }
   p.swizzle_bytes = sw;
   p.block_k = sw / 2;
   // N tiling: equal tiles of <= 256 columns, each a multiple of 16
-  int n_tiles = ceil_div(g.N, 256);
+  int max_bn = kn.max_bn >= 16 && kn.max_bn <= 256 ? kn.max_bn : 256;
+  int n_tiles = ceil_div(g.N, max_bn);
   int bn = ceil_div(ceil_div(g.N, n_tiles), 16) * 16;
   p.block_n = bn;
   p.n_tiles = ceil_div(g.N, bn);
@@ -659,9 +682,9 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.tx_bytes = TC_BLOCK_M * sw + bn * sw;
   const int k_blocks = ceil_div(g.K, p.block_k);
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
-  p.w_resident = (wres_bytes <= 96 * 1024 && !env_int("TD3D_TC_NO_WRES", 0)) ? 1 : 0;
+  p.w_resident = (wres_bytes <= 96 * 1024 && !kn.no_wres) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
-  p.tma_store = (!g.out_f32 && env_int("TD3D_TC_TMA_STORE", 0)) ? 1 : 0;   // measured slower than st.global (fence + 2-deep staging): off
+  p.tma_store = (!g.out_f32 && kn.tma_store) ? 1 : 0;   // measured slower than st.global (fence + 2-deep staging): off
   const int ystage_bytes = p.tma_store ? TC_EPI_GROUPS * 4 * 2 * 2048 + 1024 : 0;
   int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0) - ystage_bytes;
   p.stages = budget / stage_bytes;
@@ -672,14 +695,14 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.act = g.act;
-  p.lbo_field_bytes = env_int("TD3D_TC_LBO", 16);
-  p.dbg = env_int("TD3D_TC_DBG", 0);
+  p.lbo_field_bytes = kn.lbo;
+  p.dbg = kn.dbg;
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
   // costs the statistics epilogue 4-8 % of its issue slots, and with two issuers the accumulator stages are no longer
   // committed in tile order: an epilogue group that runs >= 5 tiles ahead of the slower issuer could see the parity of
   // a stage's previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the
   // second issuer is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
-  p.mma_warps = (env_int("TD3D_TC_TWO_ISSUERS", 0) && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
+  p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
@@ -738,7 +761,7 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   p.m_per_part = ceil_div(ceil_div(g.M, parts), TN_BK) * TN_BK;
   parts = ceil_div(g.M, p.m_per_part);
   p.c = g.c;
-  p.swap_lbo_sbo = env_int("TD3D_TC_TN_SWAP", 0);
+  p.swap_lbo_sbo = knobs().tn_swap;
   CUtensorMap map_a, map_b;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.N1, TN_BK, 64, 128));
   TD3D_TRY(make_map_2d(&map_b, g.b, g.M, g.N2, TN_BK, 64, 128));

@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "3d-object-detection.pytorch_b200")); sys.
 import torch
 from torchdet3d_b200 import _lib as L
 import _k as K
+os.environ["TD3D_TC_LIVE_ENV"] = "1"
 L.require_b200()
 dev = "cuda"
 SHAPES = [(256 * 112 * 112, 64, 16), (256 * 112 * 112, 16, 16), (256 * 56 * 56, 24, 64), (256 * 56 * 56, 72, 24), (256 * 14 * 14, 480, 80), (256 * 14 * 14, 112, 672)]
