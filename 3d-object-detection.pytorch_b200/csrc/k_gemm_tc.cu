@@ -627,7 +627,7 @@ static TcKnobs read_knobs() {
   k.lbo = env_raw("TD3D_TC_LBO", 16);
   k.dbg = env_raw("TD3D_TC_DBG", 0);
   k.two_issuers = env_raw("TD3D_TC_TWO_ISSUERS", 0);
-  k.max_bn = env_raw("TD3D_TC_MAXBN", 256);
+  k.max_bn = env_raw("TD3D_TC_MAXBN", 0);        // 0 = rule in launch_gemm_nt_tc
   k.tn_swap = env_raw("TD3D_TC_TN_SWAP", 0);
   return k;
 }
@@ -671,7 +671,11 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.swizzle_bytes = sw;
   p.block_k = sw / 2;
   // N tiling: equal tiles of <= 256 columns, each a multiple of 16
-  int max_bn = kn.max_bn >= 16 && kn.max_bn <= 256 ? kn.max_bn : 256;
+  // N tile width.  256-column tiles leave 2 TMEM accumulator stages (hence 2 epilogue groups, see the hand-off note in the
+  // kernel); 128-column tiles keep 4 stages and all 3 groups at the price of fetching the A tile once per N tile.  Measured
+  // (scripts/gemm_bench2.py, profiles/r02_gemm_bench2.txt): 128 wins 10-20 % on every wide-N layer with K <= 112 and loses
+  // 15 % on 160 x 960 (K = 960: the A tile is the traffic).  TD3D_TC_MAXBN overrides.
+  int max_bn = kn.max_bn >= 16 && kn.max_bn <= 256 ? kn.max_bn : (g.K <= 256 ? 128 : 256);
   int n_tiles = ceil_div(g.N, max_bn);
   int bn = ceil_div(ceil_div(g.N, n_tiles), 16) * 16;
   p.block_n = bn;

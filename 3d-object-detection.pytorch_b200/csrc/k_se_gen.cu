@@ -9,7 +9,7 @@
 
 namespace td3d {
 
-__device__ __forceinline__ float seg_sigmoid(float u) { return 1.f / (1.f + __expf(-u)); }
+__device__ __forceinline__ float seg_sigmoid(float u) { return __fdividef(1.f, 1.f + __expf(-u)); }
 
 // grid = B, block = 256, smem = (C + Ch) floats
 __global__ void __launch_bounds__(256) se_gen_fwd_kernel(SeArgs a) {

@@ -60,14 +60,14 @@ struct XForm {
 __device__ __forceinline__ float act_fwd(float u, int act) {
   if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
   if (act == TD3D_ACT_HSWISH) return u * fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
-  if (act == TD3D_ACT_SILU) return u / (1.f + __expf(-u));
+  if (act == TD3D_ACT_SILU) return u * __fdividef(1.f, 1.f + __expf(-u));
   return u;
 }
 // d act(u) / du, matching autograd of x*relu6(x+3)/6 (hardtanh grad is 0 at both clamp points)
 __device__ __forceinline__ float act_bwd(float u, int act) {
   if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
   if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) * (1.f / 6.f));
-  if (act == TD3D_ACT_SILU) { const float s = 1.f / (1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
+  if (act == TD3D_ACT_SILU) { const float s = __fdividef(1.f, 1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
   return 1.f;
 }
 // Branch-free activations from per-kernel uniform constants (set up once with make_actk): the `act` switch of
@@ -88,11 +88,11 @@ __device__ __forceinline__ ActK make_actk(int act) {
   return k;
 }
 __device__ __forceinline__ float actk_fwd(float u, const ActK& k) {
-  if (k.silu) return u / (1.f + __expf(-u));
+  if (k.silu) return u * __fdividef(1.f, 1.f + __expf(-u));     // MUFU.EX2 + MUFU.RCP, no full-precision division slow path
   return u * __saturatef(fmaf(k.a, u, k.b));
 }
 __device__ __forceinline__ float actk_bwd(float u, const ActK& k) {
-  if (k.silu) { const float s = 1.f / (1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
+  if (k.silu) { const float s = __fdividef(1.f, 1.f + __expf(-u)); return s * fmaf(u, 1.f - s, 1.f); }
   float d = fmaf(u, k.da, k.db);
   d = u >= k.hi ? 1.f : d;
   return u <= k.lo ? 0.f : d;
