@@ -195,6 +195,7 @@ struct TcNtParams {
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
   int act;              // epilogue activation after the bias (TD3D_ACT_*), before the addend
+  const float* dact_scale; const float* dact_shift; int dact;   // y *= act'(scale[n]*ysaved + shift[n]) (fused activation backward)
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
   int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
@@ -333,6 +334,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
     const ActK eak = make_actk(p.act);
+    const ActK dak = make_actk(p.dact);
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
@@ -391,6 +393,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += ad[i];
             }
+            float ys[8];
+            if (p.ysaved) load8(p.ysaved + off, ys);
+            if (p.dact_scale) {                       // fused activation backward of the tensor this gradient belongs to
+              float dsc[8], dsh[8];
+              loadf8(p.dact_scale + n, dsc);
+              loadf8(p.dact_shift + n, dsh);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] *= actk_bwd(fmaf(ys[i], dsc[i], dsh[i]), dak);
+            }
             if (p.yf) {
               if (!(p.dbg & 1)) store8(p.yf + off, x);
             } else {
@@ -402,8 +413,6 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
               x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
             }
-            float ys[8];
-            if (p.ysaved) load8(p.ysaved + off, ys);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v[g * 8 + i] = x[i];
@@ -699,6 +708,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.act = g.act;
+  p.dact_scale = g.ysaved ? g.dact_scale : nullptr; p.dact_shift = g.dact_shift; p.dact = g.dact;
   p.lbo_field_bytes = kn.lbo;
   p.dbg = kn.dbg;
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but

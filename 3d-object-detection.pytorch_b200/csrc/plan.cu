@@ -879,9 +879,16 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     {
       GemmTN t = {c.ws(pl->g_y3), c.ws(b.h2), c.G(b.w3), Mo, b.d.out_ch, E};
       TD3D_TRY(gemm_tn(c, t));
+      Bn& bn2f = pl->bns[b.bn2];
       GemmNT g = {};
       g.a = c.ws(pl->g_y3); g.w = c.pk(b.pw3t); g.y = c.ws(pl->g_wide_a);
       g.M = Mo; g.N = E; g.K = b.d.out_ch;
+      if (!b.d.use_se) {
+        // no SE: the activation backward of h2 = act(BN(y2)) and the BatchNorm-backward sums of bn2 ride in this GEMM's
+        // epilogue (one read of y2) instead of a separate act_bwd_stats pass over the wide tensor
+        g.ysaved = c.ws(b.y2); g.stats = c.wsf(bn2f.bstats); g.slots = B;
+        g.dact_scale = c.wsf(bn2f.scale); g.dact_shift = c.wsf(bn2f.shift); g.dact = act;
+      }
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
     Bn& bn2 = pl->bns[b.bn2];
@@ -915,10 +922,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
         TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, se_backward(c, se_bwd_args(c.wsf(b.hbstats), nullptr, nullptr)));
         TD3D_TRY(p_actbwd(c, gw, c.wsf(pl->se_gpool), 1.f / (float)HWo, c.ws(b.y2), xf_make(sc2, sh2, c.wsf(b.gate), act, 1), gw,
                                       c.wsf(bn2.bstats), B, HWo, E, dt, c.st));
-      } else {
-        TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
-                                      dt, c.st));
-      }
+      }                                   // (no SE: act' and the sums were produced by the dgrad GEMM above)
       TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
     }
     // depthwise conv backward (data + weights)
