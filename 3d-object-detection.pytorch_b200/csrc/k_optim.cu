@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
   const int64_t head_end = a.head_off + a.head_stride * a.n_heads;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     int seg = 0;
+    if (i >= a.skip_begin && i < a.skip_end) continue;
     if (i >= a.head_off && i < head_end) {
       int k = (int)((i - a.head_off) / a.head_stride);
       if (a.present && !a.present[k]) continue;        // grad=None: tensor untouched

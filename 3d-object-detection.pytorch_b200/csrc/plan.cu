@@ -1292,6 +1292,8 @@ int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, f
   a.p = pl->P; a.g = pl->G; a.s0 = state0; a.s1 = state1; a.n = pl->param_floats;
   a.head_off = pl->w_reg0; a.head_stride = pl->head_stride; a.n_heads = pl->net.max_classes;
   a.steps = steps; a.present = head_present;
+  a.skip_begin = a.skip_end = 0;
+  if (pl->net.num_classes == 1) { a.skip_begin = pl->w_cls; a.skip_end = pl->param_floats; }
   Ctx c = {pl, (cudaStream_t)stream};
   {
     double per = desc->kind == TD3D_OPT_ADAMW ? 28.0 : (desc->kind == TD3D_OPT_ADADELTA ? 28.0 : 20.0);

@@ -166,6 +166,8 @@ struct OptimArgs {
   float* p; const float* g; float* s0; float* s1; int64_t n;
   int64_t head_off, head_stride; int n_heads;
   int32_t* steps; const int32_t* present;
+  int64_t skip_begin, skip_end;     // floats [skip_begin, skip_end) are left untouched (cls_fc when num_classes == 1: the reference
+                                    // never runs it, so its grad stays None and torch optimizers skip it, model_builder.py:140-144)
 };
 int launch_optim(const OptimArgs& a, cudaStream_t st);
 struct PackSeg { const float* src; void* dst; int rows, cols; int transpose; int out_dtype;

@@ -276,6 +276,9 @@ class Regressor(nn.Module):
                 if not present[k]:
                     p.grad = None
                     continue
+            if self.num_classes == 1 and pname.startswith("cls_fc."):
+                p.grad = None              # the reference never runs cls_fc then (model_builder.py:140-144)
+                continue
             p.grad = self._gflat[off:off + numel].view(shape)
 
     def forward(self, x, cats, dropout_keep=None):

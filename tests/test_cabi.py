@@ -61,6 +61,38 @@ def test_plan_param_table_matches_torchvision_efficientnet_through_the_wrapper(n
     assert all(torch.equal(m.state_dict()[k], ref[k]) for k in ref)
 
 
+def test_initialize_weights_distributions_match_reference():
+    """`_initialize_weights` (mobilenetv3.py:205-218): conv N(0, sqrt(2 / (k*k*Cout))), BatchNorm 1 / 0, Linear N(0, 0.01)
+    with zero bias -- run BEFORE the heads exist, so `regressors` / `cls_fc` keep torch's default Linear init
+    (uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)), model_builder.py:76-87); BatchNorm buffers 0 / 1 / 0."""
+    import math
+    torch.manual_seed(0)
+    m = Regressor("mobilenetv3_large", num_classes=9)
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if k.endswith("running_mean"):
+            assert float(v.abs().max()) == 0.0, k
+        elif k.endswith("running_var"):
+            assert torch.all(v == 1), k
+        elif k.endswith("num_batches_tracked"):
+            assert int(v) == 0, k
+        elif k.startswith("regressors") or k.startswith("cls_fc"):
+            bound = 1.0 / math.sqrt(1280)
+            assert float(v.abs().max()) <= bound + 1e-7, k
+            if v.numel() > 1000:
+                assert abs(float(v.std()) - bound / math.sqrt(3)) < 0.1 * bound, k        # uniform, not normal
+        elif v.dim() == 4:
+            std = math.sqrt(2.0 / (v.shape[2] * v.shape[3] * v.shape[0]))
+            if v.numel() >= 2000:
+                assert abs(float(v.std()) - std) < 0.12 * std and abs(float(v.mean())) < 0.1 * std, (k, float(v.std()), std)
+        elif v.dim() == 2:
+            assert abs(float(v.std()) - 0.01) < 0.002, k                                  # SE / classifier Linear
+        elif k.endswith(".weight"):
+            assert torch.all(v == 1), k                                                  # BatchNorm gamma
+        else:
+            assert float(v.abs().max()) == 0.0, k                                        # biases, BatchNorm beta
+
+
 def test_no_cpu_fallback():
     m = Regressor("mobilenetv3_small")
     with pytest.raises(L.Td3dError):

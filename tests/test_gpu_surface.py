@@ -223,3 +223,37 @@ def test_evaluator_runs_as_reference_main_calls_it(tmp_path):
     finally:
         set_iou_backend(None)
     assert abs(r["IOU"] - 0.5) < 1e-9 and sum(calls) == 2 * case["batch"]
+
+
+def test_single_class_model_leaves_cls_fc_untouched():
+    """num_classes == 1 (model_builder.py:140-144, regression_losses.py:84-88): forward returns the categories themselves,
+    LossManager runs without class criteria, and cls_fc -- never executed by the reference -- keeps grad=None, so the
+    optimizer must not decay or move it."""
+    case = CASES["small_adamw"]
+    cfg = make_cfg(case)
+    cfg.model.num_classes = 1
+    cfg.loss.names = ["l1", "add_loss"]
+    cfg.loss.coeffs = ([1.0, 0.1], [])
+    from torchdet3d_b200.builders import build_model
+    model = build_model(cfg)
+    state = tp.synth_state(case["model"], seed=0, num_classes=1)
+    model.load_state_dict(state)
+    model = model.to(DEV).train()
+    lm = LossManager(build_loss(cfg), cfg.loss.coeffs, cfg.loss.alwa)
+    opt = build_optimizer(cfg, model)
+    imgs, gt_kp, cats, _ = train_batch(case, 0)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    kp, targets = model(imgs.to(DEV), cats.to(DEV))
+    assert targets.shape == (case["batch"], 1) and torch.equal(targets.cpu().view(-1), cats)
+    loss = lm.parse_losses(kp, gt_kp.to(DEV), targets, cats.to(DEV), 0)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    for n, p in model.named_parameters():
+        if n.startswith("cls_fc."):
+            assert p.grad is None and torch.equal(p.detach(), before[n]), n
+    assert not torch.equal(model.state_dict()["features.0.0.weight"], before["features.0.0.weight"])
+    r = tp.train_step(state, case["model"], {}, imgs, gt_kp, cats, torch.ones(case["batch"], 1024),
+                      loss_cfg=dict(tp.DEFAULT_LOSS, names=["l1", "add_loss"], coeffs=([1.0, 0.1], [])), step_optimizer=False)
+    assert abs(loss.item() - r["loss"]) < 1e-3 * abs(r["loss"])
+    assert r["grads"]["cls_fc.1.weight"] is None and r["grads"]["cls_fc.1.bias"] is None
