@@ -30,8 +30,7 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
 gemm_nt_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, T* __restrict__ Y, float* __restrict__ Yf,
                     const T* __restrict__ addend, const float* __restrict__ bias, const T* __restrict__ ysaved,
-                    float* __restrict__ stats, int slots, int M, int N, int K, int act,
-                    const float* __restrict__ dact_scale, const float* __restrict__ dact_shift, int dact) {
+                    float* __restrict__ stats, int slots, int M, int N, int K, int act) {
   __shared__ __align__(16) float As[GS_BK][GS_BM + 4];
   __shared__ __align__(16) float Bs[GS_BK][GS_BN + 4];
   __shared__ float s_stat[2][GS_BN];
@@ -81,7 +80,6 @@ gemm_nt_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, T* __rest
       if (bias) v += bias[n];
       v = act_fwd(v, act);
       if (addend) v += to_f(addend[(size_t)m * N + n]);
-      if (dact_scale) v *= act_bwd(fmaf(to_f(ysaved[(size_t)m * N + n]), dact_scale[n], dact_shift[n]), dact);
       float r;
       if (Yf) { Yf[(size_t)m * N + n] = v; r = v; }
       else { T o = from_f<T>(v); Y[(size_t)m * N + n] = o; r = to_f(o); }
@@ -111,11 +109,11 @@ int launch_gemm_nt_simt(const GemmNT& g, int dtype, cudaStream_t st) {
   if (dtype == TD3D_BF16)
     gemm_nt_simt_kernel<bf16><<<grid, GS_THREADS, 0, st>>>(
         (const bf16*)g.a, (const bf16*)g.w, g.out_f32 ? nullptr : (bf16*)g.y, g.out_f32 ? (float*)g.y : nullptr,
-        (const bf16*)g.addend, g.bias, (const bf16*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act, g.ysaved ? g.dact_scale : nullptr, g.dact_shift, g.dact);
+        (const bf16*)g.addend, g.bias, (const bf16*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act);
   else
     gemm_nt_simt_kernel<float><<<grid, GS_THREADS, 0, st>>>(
         (const float*)g.a, (const float*)g.w, g.out_f32 ? nullptr : (float*)g.y, g.out_f32 ? (float*)g.y : nullptr,
-        (const float*)g.addend, g.bias, (const float*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act, g.ysaved ? g.dact_scale : nullptr, g.dact_shift, g.dact);
+        (const float*)g.addend, g.bias, (const float*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

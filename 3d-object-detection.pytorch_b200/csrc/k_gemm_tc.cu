@@ -195,7 +195,6 @@ struct TcNtParams {
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
   int act;              // epilogue activation after the bias (TD3D_ACT_*), before the addend
-  const float* dact_scale; const float* dact_shift; int dact;   // y *= act'(scale[n]*ysaved + shift[n]) (fused activation backward)
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
   int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
@@ -212,6 +211,9 @@ struct TcNtParams {
 // costs ~1 us of one-warp-per-scheduler latency-bound issue, the MMA/TMA side idles, and the kernel
 // runs at ~1 TB/s.  Hence TC_EPI_GROUPS groups work on different tiles concurrently, each draining its
 // own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
+// EPI_ACT: the bias + activation epilogue of the inference path is a template parameter so that the training GEMMs carry
+// none of its registers (the epilogue warps sit at the 128-register limit: every extra live value spills).
+template <bool EPI_ACT>
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, TcNtParams p) {
@@ -333,8 +335,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int et = (threadIdx.x - 32 * (1 + TC_MMA_WARPS)) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
-    const ActK eak = make_actk(p.act);
-    const ActK dak = make_actk(p.dact);
+    const ActK eak = make_actk(EPI_ACT ? p.act : TD3D_ACT_NONE);
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
@@ -382,7 +383,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += bb[i];
             }
-            if (p.act != TD3D_ACT_NONE) {
+            if (EPI_ACT) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] = actk_fwd(x[i], eak);
             }
@@ -392,15 +393,6 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               load8(p.addend + off, ad);
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += ad[i];
-            }
-            float ys[8];
-            if (p.ysaved) load8(p.ysaved + off, ys);
-            if (p.dact_scale) {                       // fused activation backward of the tensor this gradient belongs to
-              float dsc[8], dsh[8];
-              loadf8(p.dact_scale + n, dsc);
-              loadf8(p.dact_shift + n, dsh);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] *= actk_bwd(fmaf(ys[i], dsc[i], dsh[i]), dak);
             }
             if (p.yf) {
               if (!(p.dbg & 1)) store8(p.yf + off, x);
@@ -413,6 +405,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
               x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
             }
+            float ys[8];
+            if (p.ysaved) load8(p.ysaved + off, ys);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v[g * 8 + i] = x[i];
@@ -708,7 +702,6 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.act = g.act;
-  p.dact_scale = g.ysaved ? g.dact_scale : nullptr; p.dact_shift = g.dact_shift; p.dact = g.dact;
   p.lbo_field_bytes = kn.lbo;
   p.dbg = kn.dbg;
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
@@ -730,12 +723,14 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + ystage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     attr_set = true;
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_nt_tc_kernel<<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
+  if (p.act != TD3D_ACT_NONE) gemm_nt_tc_kernel<true><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
+  else gemm_nt_tc_kernel<false><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

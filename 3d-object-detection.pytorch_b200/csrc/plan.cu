@@ -124,7 +124,6 @@ struct td3d_plan {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool side_pending[2] = {false, false};
   int overlap = 1;
-  int fuse_dact = 1;                     // activation backward of SE-less blocks inside the dgrad GEMM epilogue (TD3D_FUSE_DACT=0: separate pass)
   td3d::PackTable pack_table;
   td3d::PackTable pack_table_eval;       // weights * eval-mode BatchNorm scale (rebuilt with the fold, td3d_pack_weights)
   td3d::BnFoldTable fold_table;
@@ -880,16 +879,9 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     {
       GemmTN t = {c.ws(pl->g_y3), c.ws(b.h2), c.G(b.w3), Mo, b.d.out_ch, E};
       TD3D_TRY(gemm_tn(c, t));
-      Bn& bn2f = pl->bns[b.bn2];
       GemmNT g = {};
       g.a = c.ws(pl->g_y3); g.w = c.pk(b.pw3t); g.y = c.ws(pl->g_wide_a);
       g.M = Mo; g.N = E; g.K = b.d.out_ch;
-      if (!b.d.use_se && pl->fuse_dact) {
-        // no SE: the activation backward of h2 = act(BN(y2)) and the BatchNorm-backward sums of bn2 ride in this GEMM's
-        // epilogue (one read of y2) instead of a separate act_bwd_stats pass over the wide tensor
-        g.ysaved = c.ws(b.y2); g.stats = c.wsf(bn2f.bstats); g.slots = B;
-        g.dact_scale = c.wsf(bn2f.scale); g.dact_shift = c.wsf(bn2f.shift); g.dact = act;
-      }
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
     Bn& bn2 = pl->bns[b.bn2];
@@ -923,10 +915,12 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
         TD3D_K(PK_SE, 16.0 * b.d.exp_ch * b.d.se_hidden, se_backward(c, se_bwd_args(c.wsf(b.hbstats), nullptr, nullptr)));
         TD3D_TRY(p_actbwd(c, gw, c.wsf(pl->se_gpool), 1.f / (float)HWo, c.ws(b.y2), xf_make(sc2, sh2, c.wsf(b.gate), act, 1), gw,
                                       c.wsf(bn2.bstats), B, HWo, E, dt, c.st));
-      } else if (!pl->fuse_dact) {
+      } else {
+        // Fusing this pass into the dgrad GEMM epilogue was built and measured (r02 call H): act_bwd_stats -0.48 ms, dgrad GEMM
+        // +0.37 ms, and the extra epilogue registers spilled and slowed EVERY tcgen05 GEMM (forward 1.77 -> 2.14 ms) -- removed.
         TD3D_TRY(p_actbwd(c, gw, nullptr, 1.f, c.ws(b.y2), xf_make(sc2, sh2, nullptr, act), gw, c.wsf(bn2.bstats), B, HWo, E,
                                       dt, c.st));
-      }                                   // (no SE, fused: act' and the sums were produced by the dgrad GEMM above)
+      }
       TD3D_TRY(bn_backward(c, b.bn2, HWo, nullptr, nullptr, nullptr));
     }
     // depthwise conv backward (data + weights)
@@ -1151,8 +1145,6 @@ int td3d_plan_bind(td3d_plan* pl, float* params, float* grads, float* bn_stats, 
   if (!pl->side[0]) {
     const char* e = getenv("TD3D_OVERLAP");
     pl->overlap = (e && atoi(e) == 0) ? 0 : 1;
-    const char* fd = getenv("TD3D_FUSE_DACT");
-    pl->fuse_dact = (fd && atoi(fd) == 0) ? 0 : 1;
     for (int i = 0; i < 2; ++i) {
       TD3D_CUDA(cudaStreamCreateWithFlags(&pl->side[i], cudaStreamNonBlocking));
       TD3D_CUDA(cudaEventCreateWithFlags(&pl->ev_fork[i], cudaEventDisableTiming));

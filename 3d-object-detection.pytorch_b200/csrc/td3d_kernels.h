@@ -111,9 +111,6 @@ struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m
   int M, N, K;
   int out_f32;               // write Y as float regardless of dtype
   int act;                   // TD3D_ACT_*: y = act(acc + bias) (+ addend)   (inference: BatchNorm folded into w / bias)
-  // activation backward fused into a data-gradient GEMM (needs ysaved): y *= act'(dact_scale[n]*ysaved + dact_shift[n]) before
-  // the store and the statistics -- the separate act_bwd_stats pass of blocks without SE disappears
-  const float* dact_scale; const float* dact_shift; int dact;
 };
 int launch_gemm_nt_simt(const GemmNT& g, int dtype, cudaStream_t st);
 int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st);       // bf16 only
