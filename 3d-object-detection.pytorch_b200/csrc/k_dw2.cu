@@ -1,6 +1,7 @@
-// Depthwise k x k convolution, generation 2 (k in {3,5}, stride in {1,2}, pad (k-1)/2, NHWC).
+// Depthwise k x k convolution FORWARD, tiled generation (k in {3,5}, stride in {1,2}, pad (k-1)/2, NHWC).
 // Reference op: nn.Conv2d(hidden, hidden, k, s, (k-1)//2, groups=hidden) inside InvertedResidual,
-// torchdet3d/models/mobilenetv3.py:136,152, and its autograd backward.
+// torchdet3d/models/mobilenetv3.py:136,152.  (The tiled backward twins of round 1 were superseded by the one-pass
+// column walker of k_dwc.cu and removed.)
 //
 // The depthwise tensors are the widest of the network, and at B200's HBM rate (~23 B/clk/SM) a 3x3
 // depthwise layer has a budget of only ~22 issued instructions per element; a 5x5 layer is FMA-bound
@@ -20,8 +21,6 @@
 //     and leave the CTA as one global atomic per channel.
 //
 //   forward   y  = dw(act(se*(scale*x+shift)))                      + sum y,  sum y^2   per (b,c)
-//   bwd-data  gx = act'(u(x)) * dw^T(alpha*g + beta*y + gamma)      + sum gx, sum gx*x  per (b,c)
-//   bwd-wgt   dW[c,ky,kx] += sum gy * x_t(shifted)   taps accumulate in registers across all items
 #include "td3d_kernels.h"
 
 #include <stdlib.h>
@@ -484,305 +483,6 @@ d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T*
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward data.  Stride 1: correlation of the staged gy tile with the flipped filter.  Stride 2:
-// the owned grid is the coarse (= output) grid; a thread produces the 2x2 input pixels under each
-// of its 2x2 coarse positions; tap (ky,kx) feeds exactly one of the four input parities with a
-// compile-time gy offset: no divergence, no wasted multiply.
-// ------------------------------------------------------------------------------------------------
-struct D2Fin {       // epilogue of the data gradient: gx = acc * act'(u(x)), statistics of the stored value
-  float4 sc, sh, se, s1, s2;
-  int act;
-  template <typename T>
-  __device__ __forceinline__ void apply(float4 acc, const float4& xv, T* __restrict__ gp) {
-    acc.x *= act_d(se.x * fmaf(xv.x, sc.x, sh.x), act);
-    acc.y *= act_d(se.y * fmaf(xv.y, sc.y, sh.y), act);
-    acc.z *= act_d(se.z * fmaf(xv.z, sc.z, sh.z), act);
-    acc.w *= act_d(se.w * fmaf(xv.w, sc.w, sh.w), act);
-    const float4 r = st4r(gp, acc);
-    add4(s1, r);
-    fma4(s2, r, xv);
-  }
-};
-
-template <typename T, int K, int S, int CG>
-__global__ void __launch_bounds__(D2_THREADS, 2)
-d2_bwd_data_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
-                   const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
-                   const float* __restrict__ w, T* __restrict__ gx, float* __restrict__ stats, int B, int H, int W, int Ho,
-                   int Wo, int C, D2Tile t, D2Smem sm) {
-  constexpr int P = (K - 1) / 2, PS = D2C<CG>::PS;
-  constexpr int HALO = S == 1 ? P : 1;              // staged halo (pixels of the gy grid) on each side
-  extern __shared__ __align__(16) uint8_t d2_smem[];
-  __shared__ D2Consts<CG> kc;
-  __shared__ __align__(16) float s_w[K * K * CG];
-  float* tile = reinterpret_cast<float*>(d2_smem);
-  float* part = tile + sm.tile_floats;
-  uint8_t* raw_g = reinterpret_cast<uint8_t*>(part + sm.part_floats);
-  uint8_t* raw_y = raw_g + sm.raw_bytes;
-  const uint32_t rawg_s = s_u32(raw_g), rawy_s = s_u32(raw_y);
-  const int c0 = blockIdx.y * CG;
-  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
-  const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
-  d2_load_chan_consts<CG>(kc, xf, beta, c0, C);
-  d2_load_w<K, CG>(s_w, w, c0, C, S == 1);
-  uint32_t rc[D2_NIT];
-  d2_items<CG>(rc, t.ih, t.iw, t.nb);
-  D2Map m;
-  m.init(t, D2C<CG>::NQ);
-  const int v8 = D2C<CG>::v8(), ch = c0 + v8 * 8;
-  __syncthreads();
-  D2Item cur, nxt;
-  cur.init(t, it0);
-  uint32_t mask = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rc, t.nit, cur.bb * t.nb, B, Ho, Wo, C, ch, cur.tyi * t.th - HALO,
-                                  cur.txi * t.tw - HALO);
-  D2Fin fin;
-  fin.s1 = make_float4(0.f, 0.f, 0.f, 0.f); fin.s2 = fin.s1; fin.act = xf.act;
-  fin.sc = lds4(&kc.sc[m.q * 4]); fin.sh = lds4(&kc.sh[m.q * 4]);
-  int cur_bb = -1;
-  const int c = c0 + m.q * 4;
-  const float* s_wq = s_w + m.q * 4;
-  const int row_stride = t.iw * PS;
-  for (int item = it0; item < it1; ++item) {
-    const int b0 = cur.bb * t.nb, ty0 = cur.tyi * t.th, tx0 = cur.txi * t.tw;
-    if (cur.bb != cur_bb) {
-      __syncthreads();                                // previous tile fully consumed (kc.al/ga/se, part)
-      if (stats && cur_bb >= 0)
-        d2_flush_stats<CG>(part, fin.s1, fin.s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
-      d2_load_sample_consts<CG>(kc, xf, alpha, gamma, b0, t.nb, B, c0, C);
-      cur_bb = cur.bb;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    d2_xform_gy<T, CG>(tile, raw_g, raw_y, mask, rc, t.nit, t.ih, t.iw, kc);
-    __syncthreads();
-    nxt = cur;
-    nxt.next(t);
-    if (item + 1 < it1)
-      mask = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rc, t.nit, nxt.bb * t.nb, B, Ho, Wo, C, ch, nxt.tyi * t.th - HALO,
-                             nxt.txi * t.tw - HALO);
-    if (m.active) {
-      const int b = b0 + m.nbi;
-      const bool live = b < B && c < C;
-      fin.se = lds4(&kc.se[m.nbi][m.q * 4]);
-      if (S == 1) {
-        constexpr int OY = 2, OX = 4;
-        float4 acc[OY][OX];
-#pragma unroll
-        for (int i = 0; i < OY; ++i)
-#pragma unroll
-          for (int j = 0; j < OX; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* base = tile + ((m.nbi * t.ih + m.ty * OY) * t.iw + m.tx * OX) * PS + m.q * 4;
-        const int yy0 = ty0 + m.ty * OY, xx0 = tx0 + m.tx * OX;
-        const size_t o0 = (((size_t)b * H + yy0) * W + xx0) * C + c;
-        Raw4<T> xr[OY][OX];                          // forward input of the owned pixels: issued now, used after the taps
-        if (live) {
-#pragma unroll
-          for (int oy = 0; oy < OY; ++oy)
-#pragma unroll
-            for (int ox = 0; ox < OX; ++ox)
-              if (yy0 + oy < H && xx0 + ox < W) xr[oy][ox].load(x + o0 + (size_t)((oy * W + ox) * C));
-        }
-        d2_conv<K, 1, OY, OX, CG>(acc, base, row_stride, s_wq);
-        if (live) {
-#pragma unroll
-          for (int oy = 0; oy < OY; ++oy) {
-            if (yy0 + oy >= H) continue;
-#pragma unroll
-            for (int ox = 0; ox < OX; ++ox) {
-              if (xx0 + ox >= W) continue;
-              const size_t o = o0 + (size_t)((oy * W + ox) * C);
-              fin.apply<T>(acc[oy][ox], xr[oy][ox].get(), gx + o);
-            }
-          }
-        }
-      } else {
-        constexpr int OYC = 2, OXC = 2;
-#pragma unroll 1
-        for (int rr = 0; rr < OYC; ++rr) {
-          const int cy = m.ty * OYC + rr;            // coarse row inside the tile
-          // window: coarse rows cy-1..cy+1 (tile rows cy..cy+2), coarse cols tx*2-1..tx*2+2 (tile cols tx*2..tx*2+3)
-          const int hh0 = 2 * (ty0 + cy), ww0 = 2 * (tx0 + m.tx * OXC);
-          const size_t o0 = (((size_t)b * H + hh0) * W + ww0) * C + c;
-          Raw4<T> xr[OXC][2][2];
-          if (live) {
-#pragma unroll
-            for (int i = 0; i < OXC; ++i)
-#pragma unroll
-              for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int bb = 0; bb < 2; ++bb)
-                  if (hh0 + a < H && ww0 + 2 * i + bb < W) xr[i][a][bb].load(x + o0 + (size_t)((a * W + 2 * i + bb) * C));
-          }
-          float4 win[3][OXC + 2];
-          const float* base = tile + ((m.nbi * t.ih + cy) * t.iw + m.tx * OXC) * PS + m.q * 4;
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < OXC + 2; ++j) win[r][j] = lds4(base + r * row_stride + j * PS);
-          float4 acc[OXC][2][2];
-#pragma unroll
-          for (int i = 0; i < OXC; ++i)
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-              for (int bb = 0; bb < 2; ++bb) acc[i][a][bb] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int ky = 0; ky < K; ++ky) {
-            const int a = (ky + P) & 1;              // input-row parity fed by this tap
-            const int dy = (a + P - ky) / 2;         // exact (a + P - ky is even); in [-1, 1]
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-              const int bb = (kx + P) & 1;
-              const int dx = (bb + P - kx) / 2;
-              const float4 wv = lds4(s_wq + (ky * K + kx) * CG);
-#pragma unroll
-              for (int i = 0; i < OXC; ++i) fma4(acc[i][a][bb], win[1 + dy][i + 1 + dx], wv);
-            }
-          }
-          if (live) {
-#pragma unroll
-            for (int i = 0; i < OXC; ++i)
-#pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                if (hh0 + a >= H) continue;
-#pragma unroll
-                for (int bb = 0; bb < 2; ++bb) {
-                  if (ww0 + 2 * i + bb >= W) continue;
-                  const size_t o = o0 + (size_t)((a * W + 2 * i + bb) * C);
-                  fin.apply<T>(acc[i][a][bb], xr[i][a][bb].get(), gx + o);
-                }
-              }
-          }
-        }
-      }
-    }
-    cur = nxt;
-  }
-  if (stats && cur_bb >= 0) {
-    __syncthreads();
-    d2_flush_stats<CG>(part, fin.s1, fin.s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward weights.  A thread owns V channels x (OY x OX) outputs; its K*K tap accumulators live in
-// registers across all items and leave the CTA once (shuffle -> smem -> one global atomic per tap
-// and channel).  Both operand tiles (x_t with halo, gy) are prefetched like in the other kernels.
-// ------------------------------------------------------------------------------------------------
-template <int K, int S> struct D2WGeo {
-  static constexpr int V = K == 3 ? 4 : 2;
-  static constexpr int OY = S == 1 ? 2 : 1, OX = 4;
-};
-
-template <typename T, int K, int S, int CG>
-__global__ void __launch_bounds__(D2_THREADS, 2)
-d2_bwd_weight_kernel(const T* __restrict__ g, const T* __restrict__ yo, const float* __restrict__ alpha,
-                     const float* __restrict__ beta, const float* __restrict__ gamma, const T* __restrict__ x, XForm xf,
-                     float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int C, D2Tile t, D2Smem sm) {
-  constexpr int P = (K - 1) / 2, V = D2WGeo<K, S>::V, OY = D2WGeo<K, S>::OY, OX = D2WGeo<K, S>::OX;
-  constexpr int NR = (OY - 1) * S + K, NC = (OX - 1) * S + K, PS = D2C<CG>::PS;
-  typedef typename VecOf<V>::type VT;
-  extern __shared__ __align__(16) uint8_t d2_smem[];
-  __shared__ D2Consts<CG> kc;
-  float* xt = reinterpret_cast<float*>(d2_smem);             // [nb][ih][iw][PS]
-  float* gt = xt + sm.tile_floats;                            // [nb][th][tw][PS]
-  float* part = gt + sm.tile2_floats;                         // [8 warps][K*K][CG]
-  uint8_t* raw_x = reinterpret_cast<uint8_t*>(part + sm.part_floats);
-  uint8_t* raw_g = raw_x + sm.raw_bytes;
-  uint8_t* raw_y = raw_g + sm.raw2_bytes;
-  const uint32_t rawx_s = s_u32(raw_x), rawg_s = s_u32(raw_g), rawy_s = s_u32(raw_y);
-  const int c0 = blockIdx.y * CG;
-  constexpr int NQV = CG / V;
-  const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
-  const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
-  d2_load_chan_consts<CG>(kc, xf, beta, c0, C);
-  uint32_t rcx[D2_NIT], rcg[D2_NIT];
-  d2_items<CG>(rcx, t.ih, t.iw, t.nb);
-  d2_items<CG>(rcg, t.th, t.tw, t.nb);
-  D2Map m;
-  m.init(t, NQV);
-  const int v8 = D2C<CG>::v8(), ch = c0 + v8 * 8;
-  __syncthreads();
-  const bool has_se = xf.se != nullptr;
-  VT acc[K * K];
-#pragma unroll
-  for (int i = 0; i < K * K; ++i) zerov(acc[i]);
-  D2Item cur, nxt;
-  cur.init(t, it0);
-  uint32_t mx = d2_fetch<T, CG>(rawx_s, x, nullptr, 0u, rcx, t.nit, cur.bb * t.nb, B, H, W, C, ch, cur.tyi * t.th * S - P,
-                                cur.txi * t.tw * S - P);
-  uint32_t mg = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rcg, t.nit2, cur.bb * t.nb, B, Ho, Wo, C, ch, cur.tyi * t.th,
-                                cur.txi * t.tw);
-  int cur_bb = -1;
-  const float* gb = gt + ((m.nbi * t.th + m.ty * OY) * t.tw + m.tx * OX) * PS + m.q * V;
-  const float* xb = xt + ((m.nbi * t.ih + m.ty * OY * S) * t.iw + m.tx * OX * S) * PS + m.q * V;
-  const int xrow = t.iw * PS, grow = t.tw * PS;
-  for (int item = it0; item < it1; ++item) {
-    if (cur.bb != cur_bb) {
-      __syncthreads();
-      d2_load_sample_consts<CG>(kc, xf, alpha, gamma, cur.bb * t.nb, t.nb, B, c0, C);
-      cur_bb = cur.bb;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    d2_xform_x<T, CG>(xt, raw_x, mx, rcx, t.nit, t.ih, t.iw, kc, xf.act, has_se);
-    d2_xform_gy<T, CG>(gt, raw_g, raw_y, mg, rcg, t.nit2, t.th, t.tw, kc);
-    __syncthreads();
-    nxt = cur;
-    nxt.next(t);
-    if (item + 1 < it1) {
-      mx = d2_fetch<T, CG>(rawx_s, x, nullptr, 0u, rcx, t.nit, nxt.bb * t.nb, B, H, W, C, ch, nxt.tyi * t.th * S - P,
-                           nxt.txi * t.tw * S - P);
-      mg = d2_fetch<T, CG>(rawg_s, g, yo, rawy_s, rcg, t.nit2, nxt.bb * t.nb, B, Ho, Wo, C, ch, nxt.tyi * t.th,
-                           nxt.txi * t.tw);
-    }
-    if (m.active) {
-      VT gv[OY][OX];
-#pragma unroll
-      for (int oy = 0; oy < OY; ++oy)
-#pragma unroll
-        for (int ox = 0; ox < OX; ++ox) ldsv(gv[oy][ox], gb + oy * grow + ox * PS);
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        VT row[NC];
-#pragma unroll
-        for (int j = 0; j < NC; ++j) ldsv(row[j], xb + r * xrow + j * PS);
-#pragma unroll
-        for (int oy = 0; oy < OY; ++oy) {
-          const int ky = r - oy * S;
-          if (ky < 0 || ky >= K) continue;
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-            for (int ox = 0; ox < OX; ++ox) fmav(acc[ky * K + kx], gv[oy][ox], row[ox * S + kx]);
-        }
-      }
-    }
-    cur = nxt;
-  }
-  // reduce over the lanes that share a channel vector, then over the warps, then flush
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < K * K; ++i) {
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float v = comp(acc[i], j);
-#pragma unroll
-      for (int o = NQV; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < NQV) part[(warp * K * K + i) * CG + lane * V + j] = v;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < K * K * CG; i += D2_THREADS) {
-    float s = 0.f;
-#pragma unroll
-    for (int wp = 0; wp < D2_THREADS / 32; ++wp) s += part[wp * K * K * CG + i];
-    const int tap = i / CG, c = c0 + i % CG;
-    if (c < C) atomicAdd(&dw[(size_t)c * K * K + tap], s);    // reference layout [C,1,K,K]
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 const long D2_SMEM_CAP_BYTES = 104 * 1024;    // per CTA -> 2 CTAs per SM
@@ -901,59 +601,6 @@ int d2_fwd_t(const DwArgs& a, cudaStream_t st) {
   return d2_fwd_launch<T, K, S, 16>(a, t, Ho, Wo, st);
 }
 
-template <typename T, int K, int S, int CG>
-int d2_bwd_data_launch(const DwBwdArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t st) {
-  static bool once = false;
-  if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_data_kernel<T, K, S, CG>)); once = true; }
-  const int part = D2C<CG>::NSP * 2 * CG;
-  const D2Smem sm = smem_layout(t, 0, sizeof(T), part);
-  dim3 grid(d2_grid_x(t), t.n_groups);
-  d2_bwd_data_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 2), st>>>(
-      (const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma, (const T*)a.x, a.xf, a.w_taps, (T*)a.gx, a.stats, a.B, a.H, a.W,
-      Ho, Wo, a.C, t, sm);
-  TD3D_LAUNCH_CHECK();
-  return TD3D_OK;
-}
-
-template <typename T, int K, int S, int CG>
-int d2_bwd_weight_launch(const DwBwdArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t st) {
-  static bool once = false;
-  if (!once) { TD3D_TRY(d2_ensure_smem(d2_bwd_weight_kernel<T, K, S, CG>)); once = true; }
-  const int part = (D2_THREADS / 32) * K * K * CG;
-  const D2Smem sm = smem_layout(t, 1, sizeof(T), part);
-  dim3 grid(d2_grid_x(t), t.n_groups);
-  d2_bwd_weight_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 1), st>>>(
-      (const T*)a.g, (const T*)a.y_out, a.alpha, a.beta, a.gamma, (const T*)a.x, a.xf, a.dw, a.B, a.H, a.W, Ho, Wo, a.C, t, sm);
-  TD3D_LAUNCH_CHECK();
-  return TD3D_OK;
-}
-
-template <typename T, int K, int S>
-int d2_bwd_t(const DwBwdArgs& a, cudaStream_t st) {
-  const int Ho = (a.H - 1) / S + 1, Wo = (a.W - 1) / S + 1;
-  const int cg = pick_cg(a.C);
-  if (a.gx) {
-    const int part = (D2_THREADS / (cg / 4)) * 2 * cg;
-    // stride 1: owned grid = input grid, thread tile 2x4, halo (K-1)/2.  stride 2: owned grid = coarse
-    // (= output) grid, a thread owns 2x2 coarse positions, staged gy = owned + 1-pixel halo.
-    const D2Tile t = S == 1 ? pick_tile(a.B, a.C, a.H, a.W, 2, 4, 1, K, 2, 0, 4, K, sizeof(T), part)
-                            : pick_tile(a.B, a.C, (a.H + 1) / 2, (a.W + 1) / 2, 2, 2, 1, 3, 2, 0, 4, K, sizeof(T), part);
-    TD3D_REQUIRE(t.cg > 0, "dw bwd-data: no tile fits");
-    if (t.cg == 32) TD3D_TRY((d2_bwd_data_launch<T, K, S, 32>(a, t, Ho, Wo, st)));
-    else TD3D_TRY((d2_bwd_data_launch<T, K, S, 16>(a, t, Ho, Wo, st)));
-  }
-  if (a.dw) {
-    constexpr int V = D2WGeo<K, S>::V;
-    const D2Tile t = pick_tile(a.B, a.C, Ho, Wo, D2WGeo<K, S>::OY, D2WGeo<K, S>::OX, S, K, 1, 1, V, K, sizeof(T),
-                               (D2_THREADS / 32) * K * K * cg);
-    TD3D_REQUIRE(t.cg > 0, "dw bwd-weight: no tile fits");
-    cudaStream_t wst = a.wgrad_stream ? (cudaStream_t)a.wgrad_stream : st;
-    if (t.cg == 32) TD3D_TRY((d2_bwd_weight_launch<T, K, S, 32>(a, t, Ho, Wo, wst)));
-    else TD3D_TRY((d2_bwd_weight_launch<T, K, S, 16>(a, t, Ho, Wo, wst)));
-  }
-  return TD3D_OK;
-}
-
 }  // namespace
 
 #define D2_DISPATCH(FN, ARGS)                                                                   \
@@ -982,14 +629,6 @@ int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st) {
   if (!d2_fits_32bit("dw fwd", a.B, a.H, a.W, a.C)) return TD3D_EINVAL;
   D2_DISPATCH(d2_fwd_t, a);
   set_last_error("dw fwd: unsupported kernel=%d stride=%d", a.k, a.stride);
-  return TD3D_EINVAL;
-}
-
-int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st) {
-  TD3D_REQUIRE(a.C % 8 == 0 && a.B > 0, "dw bwd: C=%d must be a multiple of 8", a.C);
-  if (!d2_fits_32bit("dw bwd", a.B, a.H, a.W, a.C)) return TD3D_EINVAL;
-  D2_DISPATCH(d2_bwd_t, a);
-  set_last_error("dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   return TD3D_EINVAL;
 }
 

@@ -1,8 +1,8 @@
 // Depthwise k x k convolution dispatch (reference op: nn.Conv2d(hidden, hidden, k, s, (k-1)//2, groups=hidden) inside
 // InvertedResidual, torchdet3d/models/mobilenetv3.py:136,152).
 //   forward : row walker (k_dww.cu) for small stride-1 planes, tiled persistent kernels (k_dw2.cu) otherwise
-//   backward: data- and weight-gradient kernels of k_dww.cu / k_dw2.cu (default), or the one-pass column walker
-//             (k_dwc.cu / dwc_core.cuh: both gradients + BatchNorm sums from a single read; SiLU layers)
+//   backward: one-pass column walker (k_dwc.cu / dwc_core.cuh: both gradients + BatchNorm sums from a single read of g,
+//             y_out, x); the row-walker data- / weight-gradient pair of k_dww.cu only for 7x7 planes with 5x5 taps
 #include "td3d_kernels.h"
 
 #include <stdlib.h>
@@ -44,17 +44,16 @@ static int dw_bwd_force() {
 }
 
 bool dw_bwd_is_split(const DwBwdArgs& a) {
-  if (a.xf.act == TD3D_ACT_SILU) return false;
+  if (a.xf.act == TD3D_ACT_SILU || !dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return false;   // split twins exist for small stride-1 planes only
   if (dw_bwd_force() >= 0) return dw_bwd_force() == 0;
-  return a.k == 5 && a.stride == 1 && a.H * a.W <= 64;
+  return a.k == 5 && a.H * a.W <= 64;
 }
 
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.C % 8 == 0 && a.B <= 65535, "dw bwd: C=%d must be a multiple of 8", a.C);
   TD3D_REQUIRE((a.k == 3 || a.k == 5) && (a.stride == 1 || a.stride == 2), "dw bwd: unsupported kernel=%d stride=%d", a.k, a.stride);
   if (!dw_bwd_is_split(a)) return launch_dw_bwd_fused(a, dtype, st);
-  if (dw_walker_supported(a.H, a.W, a.C, a.k, a.stride)) return launch_dw_bwd_walker(a, dtype, st);
-  return launch_dw_bwd_v2(a, dtype, st);
+  return launch_dw_bwd_walker(a, dtype, st);
 }
 
 }  // namespace td3d

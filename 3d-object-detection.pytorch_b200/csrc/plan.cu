@@ -1353,9 +1353,9 @@ int td3d_k_dw_bwd_ex(const void* g, const void* y_out, const float* alpha, const
   TD3D_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2) && C % 8 == 0, "dw_bwd_ex: bad kernel/stride/channels");
   if (impl == 2) return launch_dw_bwd_fused(a, dtype, (cudaStream_t)stream);
   if (impl == 1) {
-    TD3D_REQUIRE(act != TD3D_ACT_SILU, "dw_bwd_ex: SiLU needs the column walker");
-    if (dw_walker_supported(H, W, C, k, stride)) return launch_dw_bwd_walker(a, dtype, (cudaStream_t)stream);
-    return launch_dw_bwd_v2(a, dtype, (cudaStream_t)stream);
+    TD3D_REQUIRE(act != TD3D_ACT_SILU && dw_walker_supported(H, W, C, k, stride),
+                 "dw_bwd_ex: the data / weight gradient pair exists for small stride-1 planes (W <= 32) without SiLU only");
+    return launch_dw_bwd_walker(a, dtype, (cudaStream_t)stream);
   }
   return launch_dw_bwd(a, dtype, (cudaStream_t)stream);
 }

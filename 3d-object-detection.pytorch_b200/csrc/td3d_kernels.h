@@ -94,7 +94,6 @@ struct DwBwdArgs {
 int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
 bool dw_bwd_is_split(const DwBwdArgs& a);   // true: separate weight-gradient kernel (may run on wgrad_stream)
 int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu (default)
-int launch_dw_bwd_v2(const DwBwdArgs& a, int dtype, cudaStream_t st);
 bool dw_walker_supported(int H, int W, int C, int k, int stride);       // k_dww.cu: small planes (W <= 32), stride 1
 int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st);
 int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st);

@@ -165,11 +165,12 @@ def test_depthwise_explicit_implementations(code, k, stride, shape):
     assert rel_err(y2.float(), y1.float()) < (1e-5 if code == L.F32 else 8e-3)
     g = torch.randn_like(y1.float()).to(K.dt(code))
     alpha, gamma, beta = torch.randn(B, Cn, device=DEV), torch.randn(B, Cn, device=DEV) * 0.1, torch.randn(Cn, device=DEV) * 0.1
-    r1 = K.dw_bwd_ex(g, y1, alpha, beta, gamma, x, scale, shift, None, L.ACT_RELU, taps, k, stride, code, 1)
     r2 = K.dw_bwd_ex(g, y1, alpha, beta, gamma, x, scale, shift, None, L.ACT_RELU, taps, k, stride, code, 2)
-    assert rel_err(r2[0].float(), r1[0].float()) < (2e-5 if code == L.F32 else 1e-2)
-    assert rel_err(r2[1], r1[1]) < (2e-4 if code == L.F32 else 2e-2)
-    torch.testing.assert_close(r2[2].sum(0), r1[2].sum(0), rtol=1e-3, atol=5e-2 * B ** 0.5)
+    if stride == 1 and W <= 32:          # the split pair exists for small stride-1 planes only
+        r1 = K.dw_bwd_ex(g, y1, alpha, beta, gamma, x, scale, shift, None, L.ACT_RELU, taps, k, stride, code, 1)
+        assert rel_err(r2[0].float(), r1[0].float()) < (2e-5 if code == L.F32 else 1e-2)
+        assert rel_err(r2[1], r1[1]) < (2e-4 if code == L.F32 else 2e-2)
+        torch.testing.assert_close(r2[2].sum(0), r1[2].sum(0), rtol=1e-3, atol=5e-2 * B ** 0.5)
 
 
 GEMM_SHAPES = [(300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (5000, 16, 64),
