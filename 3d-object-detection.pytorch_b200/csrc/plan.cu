@@ -42,6 +42,9 @@ struct Bn {
   size_t scale = 0, shift = 0, mean = 0, invstd = 0;   // workspace (float) train-mode constants
   size_t escale = 0, eshift = 0;                       // packed arena (float) eval-mode constants
   size_t fstats = 0, bstats = 0;                       // workspace float [B][2][C]
+  int fslots = 0, bslots = 0;                          // statistic slots the last producer actually used (0 = all B):
+                                                       // GEMM epilogues spread their sums over GS slots only, so the
+                                                       // finalize kernels read 8x fewer partial sums for those
 };
 
 struct Block {
@@ -530,7 +533,7 @@ static int bn_forward(const Ctx& c, int idx, double count, int training, const f
   Bn& bn = c.pl->bns[idx];
   if (training) {
     BnFwdArgs a;
-    a.stats = c.wsf(bn.fstats); a.slots = c.pl->B; a.count = count;
+    a.stats = c.wsf(bn.fstats); a.slots = bn.fslots ? bn.fslots : c.pl->B; a.count = count;
     a.gamma = c.P(bn.gamma); a.beta = c.P(bn.beta);
     a.running_mean = c.pl->BNB + bn.rm; a.running_var = c.pl->BNB + bn.rm + bn.C;
     a.nbt = c.pl->NBT ? c.pl->NBT + idx : nullptr;
@@ -560,6 +563,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   td3d_plan* pl = c.pl;
   const td3d_net_desc& n = pl->net;
   const int B = pl->B, dt = pl->dtype;
+  const int GS = B < 32 ? B : 32;      // statistic slots of the GEMM epilogues (tile m_tile lands in slot m_tile % GS)
   TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->fstats_begin, 0, pl->fstats_end - pl->fstats_begin, c.st));
   const float *sc, *sh;
   pl->prof.tag = 0;
@@ -580,7 +584,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     if (b.expand) {
       GemmNT g = {};
       g.a = cur; g.w = c.pk(b.pw1); g.y = c.ws(b.y1);
-      g.stats = c.wsf(pl->bns[b.bn1].fstats); g.slots = B;
+      g.stats = c.wsf(pl->bns[b.bn1].fstats); g.slots = pl->bns[b.bn1].fslots = GS;
       g.M = Mi; g.N = E; g.K = b.d.in_ch;
       TD3D_TRY(gemm_nt(c, g));
       TD3D_TRY(bn_forward(c, b.bn1, (double)Mi, training, &sc, &sh));
@@ -614,7 +618,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
     }
     GemmNT g = {};
     g.a = c.ws(b.h2); g.w = c.pk(b.pw3); g.y = c.ws(b.y3);
-    g.stats = c.wsf(pl->bns[b.bn3].fstats); g.slots = B;
+    g.stats = c.wsf(pl->bns[b.bn3].fstats); g.slots = pl->bns[b.bn3].fslots = GS;
     g.M = Mo; g.N = b.d.out_ch; g.K = E;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, b.bn3, (double)Mo, training, &sc, &sh));
@@ -629,7 +633,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   {
     GemmNT g = {};
     g.a = cur; g.w = c.pk(pl->p_last); g.y = c.ws(pl->yc);
-    g.stats = c.wsf(pl->bns[pl->bn_last].fstats); g.slots = B;
+    g.stats = c.wsf(pl->bns[pl->bn_last].fstats); g.slots = pl->bns[pl->bn_last].fslots = GS;
     g.M = Ml; g.N = n.last_ch; g.K = Cl;
     TD3D_TRY(gemm_nt(c, g));
     TD3D_TRY(bn_forward(c, pl->bn_last, (double)Ml, training, &sc, &sh));
@@ -755,7 +759,7 @@ static int bn_backward(const Ctx& c, int idx, int HW, const float* se, const flo
   td3d_plan* pl = c.pl;
   Bn& bn = pl->bns[idx];
   BnBwdArgs a;
-  a.stats = c.wsf(bn.bstats); a.slots = pl->B;
+  a.stats = c.wsf(bn.bstats); a.slots = (bn.bslots && !se) ? bn.bslots : pl->B;
   a.mean = c.wsf(bn.mean); a.invstd = c.wsf(bn.invstd); a.gamma = c.P(bn.gamma);
   a.se = se; a.g_pool = g_pool; a.fwd_pool = fwd_pool;
   a.alpha = c.wsf(pl->alpha); a.beta = c.wsf(pl->beta); a.gammac = c.wsf(pl->gammac);
@@ -854,7 +858,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       TD3D_TRY(gemm_tn(c, t));
       GemmNT g = {};
       g.a = c.ws(pl->g_wide_a); g.w = c.pk(pl->p_lastt); g.y = c.ws(pl->g_narrow[nblk & 1]);
-      g.ysaved = c.ws(lb.y3); g.stats = c.wsf(pl->bns[lb.bn3].bstats); g.slots = B;
+      g.ysaved = c.ws(lb.y3); g.stats = c.wsf(pl->bns[lb.bn3].bstats); g.slots = pl->bns[lb.bn3].bslots = B < 32 ? B : 32;
       g.M = Ml; g.N = Cl; g.K = n.last_ch;
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     }
@@ -944,7 +948,7 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       GemmNT g = {};
       g.a = c.ws(pl->g_wide_b); g.w = c.pk(b.pw1t); g.y = g_in;
       g.addend = b.residual ? g_out : nullptr;
-      if (i > 0) { g.ysaved = prev_y; g.stats = prev_bstats; g.slots = B; }
+      if (i > 0) { g.ysaved = prev_y; g.stats = prev_bstats; g.slots = pl->bns[pl->blocks[i - 1].bn3].bslots = B < 32 ? B : 32; }
       g.M = Mi; g.N = b.d.in_ch; g.K = E;
       TD3D_TRY(gemm_nt(c, g, PK_GEMM_DGRAD));
     } else {
@@ -952,7 +956,8 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
       d.gx = g_in; d.stats = nullptr;
       TD3D_TRY(p_dwb(c, d, dt, c.st));
       if (i > 0) {
-        // previous block output is linear in y3: g_u = g (+ residual), statistics for its BN3
+        // previous block output is linear in y3: g_u = g (+ residual), statistics for its BN3 (one slot per sample)
+        pl->bns[pl->blocks[i - 1].bn3].bslots = 0;
         TD3D_TRY(p_actbwd(c, g_in, nullptr, 1.f, prev_y, xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), g_in,
                                       prev_bstats, B, HWi, b.d.in_ch, dt, c.st, b.residual ? g_out : nullptr));
       } else if (b.residual) {
