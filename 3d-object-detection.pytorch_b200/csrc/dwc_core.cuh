@@ -80,20 +80,9 @@ __host__ __device__ __forceinline__ float dv_scale(float a, float m) { return a 
 __host__ __device__ __forceinline__ float dv_get(const float2& v, int i) { return i ? v.y : v.x; }
 __host__ __device__ __forceinline__ float dv_get(const float& v, int) { return v; }
 
-// activation constants: act(u) = u * sat(a*u + b);  act'(u) = u <= lo ? 0 : (u >= hi ? 1 : da*u + db)
-struct DwcAct { float a, b, da, db, lo, hi; int silu; };
-__host__ __device__ inline DwcAct dwc_make_act(int act) {
-  DwcAct k;
-  const bool hs = act == TD3D_ACT_HSWISH, re = act == TD3D_ACT_RELU;
-  k.a = hs ? (1.f / 6.f) : (re ? 1.2676506e30f : 0.f);
-  k.b = hs ? 0.5f : (re ? 0.f : 1.f);
-  k.da = hs ? (1.f / 3.f) : 0.f;
-  k.db = hs ? 0.5f : 1.f;
-  k.lo = hs ? -3.f : (re ? 0.f : -3.0e38f);
-  k.hi = hs ? 3.f : 3.0e38f;
-  k.silu = act == TD3D_ACT_SILU;
-  return k;
-}
+// Activations are COMPILE-TIME (template int ACT = TD3D_ACT_*): the first versions carried the kind as run-time constants,
+// which cost seven registers, a uniform branch per element for SiLU and the dead code of every other activation in each
+// kernel -- at 128 registers per thread the compiler then re-derived row offsets inside the walk instead of keeping them.
 __host__ __device__ __forceinline__ float dwc_sat(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 __host__ __device__ __forceinline__ float dwc_sigmoid(float u) {
 #ifdef __CUDA_ARCH__
@@ -102,20 +91,22 @@ __host__ __device__ __forceinline__ float dwc_sigmoid(float u) {
   return 1.f / (1.f + expf(-u));
 #endif
 }
-__host__ __device__ __forceinline__ float dwc_act1(float u, const DwcAct& k) {
-  if (k.silu) return u * dwc_sigmoid(u);
-  return u * dwc_sat(u * k.a + k.b);
+template <int ACT> __host__ __device__ __forceinline__ float dwc_act1(float u) {
+  if (ACT == TD3D_ACT_RELU) return u > 0.f ? u : 0.f;
+  if (ACT == TD3D_ACT_HSWISH) return u * dwc_sat(u * (1.f / 6.f) + 0.5f);
+  if (ACT == TD3D_ACT_SILU) return u * dwc_sigmoid(u);
+  return u;
 }
-__host__ __device__ __forceinline__ float dwc_actd1(float u, const DwcAct& k) {
-  if (k.silu) { const float s = dwc_sigmoid(u); return s * (1.f + u * (1.f - s)); }
-  float d = u * k.da + k.db;
-  d = u >= k.hi ? 1.f : d;
-  return u <= k.lo ? 0.f : d;
+template <int ACT> __host__ __device__ __forceinline__ float dwc_actd1(float u) {
+  if (ACT == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (ACT == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : u * (1.f / 3.f) + 0.5f);
+  if (ACT == TD3D_ACT_SILU) { const float s = dwc_sigmoid(u); return s * (1.f + u * (1.f - s)); }
+  return 1.f;
 }
-__host__ __device__ __forceinline__ float2 dwc_act(float2 u, const DwcAct& k) { return make_float2(dwc_act1(u.x, k), dwc_act1(u.y, k)); }
-__host__ __device__ __forceinline__ float dwc_act(float u, const DwcAct& k) { return dwc_act1(u, k); }
-__host__ __device__ __forceinline__ float2 dwc_actd(float2 u, const DwcAct& k) { return make_float2(dwc_actd1(u.x, k), dwc_actd1(u.y, k)); }
-__host__ __device__ __forceinline__ float dwc_actd(float u, const DwcAct& k) { return dwc_actd1(u, k); }
+template <int ACT> __host__ __device__ __forceinline__ float2 dwc_act(float2 u) { return make_float2(dwc_act1<ACT>(u.x), dwc_act1<ACT>(u.y)); }
+template <int ACT> __host__ __device__ __forceinline__ float dwc_act(float u) { return dwc_act1<ACT>(u); }
+template <int ACT> __host__ __device__ __forceinline__ float2 dwc_actd(float2 u) { return make_float2(dwc_actd1<ACT>(u.x), dwc_actd1<ACT>(u.y)); }
+template <int ACT> __host__ __device__ __forceinline__ float dwc_actd(float u) { return dwc_actd1<ACT>(u); }
 
 // ---- raw loads / stores of CPT channels in the activation dtype ----------------------------------------------
 template <typename T, int CPT> struct DwcIo;
@@ -211,8 +202,20 @@ template <> __host__ __device__ __forceinline__ float dwc_ldc<1>(const float* p)
 //   sink.dw(c + i, tap, value), sink.stat(which, c + i, value)
 // ---------------------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int dwc_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// Pins a per-item value in a register: without it the compiler re-derives 64-bit base pointers and row offsets from the
+// kernel arguments inside the walk (~130 integer instructions per step in the SASS of the first versions).
+template <typename P> __host__ __device__ __forceinline__ void dwc_pin(P*& p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+l"(p));
+#endif
+}
+__host__ __device__ __forceinline__ void dwc_pin(uint32_t& v) {
+#ifdef __CUDA_ARCH__
+  asm volatile("" : "+r"(v));
+#endif
+}
 
-template <typename T, int K, int S, int R, int CPT>
+template <typename T, int K, int S, int R, int CPT, int ACT>
 struct DwcBwd {
   typedef typename DwcVec<CPT>::V V;
   typedef DwcIo<T, CPT> Io;
@@ -256,7 +259,7 @@ struct DwcBwd {
 
   template <int PH>
   static __host__ __device__ __forceinline__ void step(State& st, const DwcArgs& a, const T* gb, const T* yb, const T* xb,
-                                                       T* ob, int px, V al, V be, V ga, V sc, V sh, V se, const DwcAct& ak) {
+                                                       T* ob, int px, V al, V be, V ga, V sc, V sh) {
     // 1. the prefetched gradient column enters the window (slot of column px + HI), zero outside the plane
     constexpr int SLOT_NEW = (NB - 1 + PH) % NB;
     {
@@ -284,9 +287,9 @@ struct DwcBwd {
       for (int ey = 0; ey < RI; ++ey) {
         const float vm = col_ok ? st.mx[ey] : 0.f;
         const V xr = xv[ey][ex];
-        const V t = dv_mul(se, dv_fma(sc, xr, sh));
-        const V xa = dv_scale(dwc_act(t, ak), vm);
-        const V da = dv_scale(dwc_actd(t, ak), vm);
+        const V t = dv_fma(sc, xr, sh);                 // the SE gate (if any) is folded into sc / sh per item
+        const V xa = dv_scale(dwc_act<ACT>(t), vm);
+        const V da = dv_scale(dwc_actd<ACT>(t), vm);
         V acc;
         dv_set(acc, 0.f);
         const int r = ey / S, e = ey % S;
@@ -314,12 +317,12 @@ struct DwcBwd {
 
   static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcArgs& a, const T* gb, const T* yb,
                                                              const T* xb, T* ob, int px0, int px_end, V al, V be,
-                                                             V ga, V sc, V sh, V se, const DwcAct& ak) {
-    if (px0 + 0 < px_end) step<0>(st, a, gb, yb, xb, ob, px0 + 0, al, be, ga, sc, sh, se, ak);
-    if (NB > 1 && px0 + 1 < px_end) step<(NB > 1 ? 1 : 0)>(st, a, gb, yb, xb, ob, px0 + 1, al, be, ga, sc, sh, se, ak);
-    if (NB > 2 && px0 + 2 < px_end) step<(NB > 2 ? 2 : 0)>(st, a, gb, yb, xb, ob, px0 + 2, al, be, ga, sc, sh, se, ak);
-    if (NB > 3 && px0 + 3 < px_end) step<(NB > 3 ? 3 : 0)>(st, a, gb, yb, xb, ob, px0 + 3, al, be, ga, sc, sh, se, ak);
-    if (NB > 4 && px0 + 4 < px_end) step<(NB > 4 ? 4 : 0)>(st, a, gb, yb, xb, ob, px0 + 4, al, be, ga, sc, sh, se, ak);
+                                                             V ga, V sc, V sh) {
+    if (px0 + 0 < px_end) step<0>(st, a, gb, yb, xb, ob, px0 + 0, al, be, ga, sc, sh);
+    if (NB > 1 && px0 + 1 < px_end) step<(NB > 1 ? 1 : 0)>(st, a, gb, yb, xb, ob, px0 + 1, al, be, ga, sc, sh);
+    if (NB > 2 && px0 + 2 < px_end) step<(NB > 2 ? 2 : 0)>(st, a, gb, yb, xb, ob, px0 + 2, al, be, ga, sc, sh);
+    if (NB > 3 && px0 + 3 < px_end) step<(NB > 3 ? 3 : 0)>(st, a, gb, yb, xb, ob, px0 + 3, al, be, ga, sc, sh);
+    if (NB > 4 && px0 + 4 < px_end) step<(NB > 4 ? 4 : 0)>(st, a, gb, yb, xb, ob, px0 + 4, al, be, ga, sc, sh);
   }
 
   template <class Sink>
@@ -338,28 +341,32 @@ struct DwcBwd {
     V be = dwc_ldc<CPT>(a.beta + c), sc, sh;
     dv_set(sc, 1.f); dv_set(sh, 0.f);
     if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
-    const DwcAct ak = dwc_make_act(a.act);
+    V sc0 = sc, sh0 = sh;
     for (int item = il; item < a.n_items; item += a.item_lanes) {
       const int b = item / a.n_bands, band = item - b * a.n_bands;
       const int r0 = band * R;
       const V al = dwc_ldc<CPT>(a.alpha + (size_t)b * a.C + c), ga = dwc_ldc<CPT>(a.gamma + (size_t)b * a.C + c);
-      V se;
-      dv_set(se, 1.f);
-      if (a.se) se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+      if (a.se) {                                       // u = se*(scale*x + shift) = (se*scale)*x + se*shift
+        const V se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+        sc = dv_mul(se, sc0); sh = dv_mul(se, sh0);
+      }
       const T* gb = g + (size_t)b * a.Ho * a.Wo * a.C + c;
       const T* yb = y + (size_t)b * a.Ho * a.Wo * a.C + c;
       const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
       T* ob = gx + (size_t)b * a.H * a.W * a.C + c;
+      dwc_pin(gb); dwc_pin(yb); dwc_pin(xb); dwc_pin(ob);
 #pragma unroll
       for (int ar = 0; ar < NA; ++ar) {
         const int py = r0 + ar - LO;
         st.og[ar] = (uint32_t)(dwc_clampi(py, 0, a.Ho - 1) * a.Wo * a.C);
+        dwc_pin(st.og[ar]);
         st.mg[ar] = (py >= 0 && py < a.Ho) ? 1.f : 0.f;
       }
 #pragma unroll
       for (int ey = 0; ey < RI; ++ey) {
         const int qy = S * r0 + ey;
         st.ox[ey] = (uint32_t)(dwc_clampi(qy, 0, a.H - 1) * a.W * a.C);
+        dwc_pin(st.ox[ey]);
         st.mx[ey] = qy < a.H ? 1.f : 0.f;
       }
       // window fill: steps px = -(LO+HI) .. -1 only shift columns in; compute starts at px = 0
@@ -367,7 +374,7 @@ struct DwcBwd {
       prefetch(st, a, gb, yb, xb, px_begin);
 #pragma unroll 1
       for (int px0 = px_begin; px0 < a.Wo; px0 += NB)      // NB phases with compile-time window slots (no register moves)
-        run_phases(st, a, gb, yb, xb, ob, px0, a.Wo, al, be, ga, sc, sh, se, ak);
+        run_phases(st, a, gb, yb, xb, ob, px0, a.Wo, al, be, ga, sc, sh);
     }
 #pragma unroll
     for (int t = 0; t < K * K; ++t)
@@ -405,7 +412,7 @@ struct DwcFwdArgs {
   int cw, n_cchunks, ilb;
 };
 
-template <typename T, int K, int S, int R, int CPT>
+template <typename T, int K, int S, int R, int CPT, int ACT, int OACT>
 struct DwcFwd {
   typedef typename DwcVec<CPT>::V V;
   typedef DwcIo<T, CPT> Io;
@@ -434,8 +441,7 @@ struct DwcFwd {
 
   template <int PH>
   static __host__ __device__ __forceinline__ void step(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0, int px,
-                                                       V sc, V sh, V se, const DwcAct& ak, V ob_bias, const DwcAct& oak,
-                                                       V& s1, V& s2) {
+                                                       V sc, V sh, V ob_bias, V& s1, V& s2) {
     // 1. the prefetched columns enter the window, transformed once (zero outside the image: conv padding)
 #pragma unroll
     for (int e = 0; e < S; ++e) {
@@ -443,7 +449,7 @@ struct DwcFwd {
       const float cm = (qx >= 0 && qx < a.W) ? 1.f : 0.f;
 #pragma unroll
       for (int ai = 0; ai < NAI; ++ai)
-        st.Wn[ai][(S * PH + e) % K] = dv_scale(dwc_act(dv_mul(se, dv_fma(sc, Io::cvt(st.rx[ai][e]), sh)), ak), st.mx[ai] * cm);
+        st.Wn[ai][(S * PH + e) % K] = dv_scale(dwc_act<ACT>(dv_fma(sc, Io::cvt(st.rx[ai][e]), sh)), st.mx[ai] * cm);
     }
     prefetch(st, a, xb, px + 1);
     if (px < 0) return;
@@ -457,7 +463,7 @@ struct DwcFwd {
 #pragma unroll
         for (int j = 0; j < K; ++j) acc = dv_fma(st.wt[i * K + j], st.Wn[S * r + i][(S * PH + j + S) % K], acc);
       if (r0 + r < a.Ho) {
-        const V yr = Io::st(ob + (st.oy[r] + cyo), dwc_act(acc, oak));
+        const V yr = Io::st(ob + (st.oy[r] + cyo), dwc_act<OACT>(acc));
         s1 = dv_add(s1, yr);
         s2 = dv_fma(yr, yr, s2);
       }
@@ -465,13 +471,12 @@ struct DwcFwd {
   }
 
   static __host__ __device__ __forceinline__ void run_phases(State& st, const DwcFwdArgs& a, const T* xb, T* ob, int r0,
-                                                             int px0, V sc, V sh, V se, const DwcAct& ak, V obb,
-                                                             const DwcAct& oak, V& s1, V& s2) {
-    if (px0 + 0 < a.Wo) step<0>(st, a, xb, ob, r0, px0 + 0, sc, sh, se, ak, obb, oak, s1, s2);
-    if (K > 1 && px0 + 1 < a.Wo) step<(K > 1 ? 1 : 0)>(st, a, xb, ob, r0, px0 + 1, sc, sh, se, ak, obb, oak, s1, s2);
-    if (K > 2 && px0 + 2 < a.Wo) step<(K > 2 ? 2 : 0)>(st, a, xb, ob, r0, px0 + 2, sc, sh, se, ak, obb, oak, s1, s2);
-    if (K > 3 && px0 + 3 < a.Wo) step<(K > 3 ? 3 : 0)>(st, a, xb, ob, r0, px0 + 3, sc, sh, se, ak, obb, oak, s1, s2);
-    if (K > 4 && px0 + 4 < a.Wo) step<(K > 4 ? 4 : 0)>(st, a, xb, ob, r0, px0 + 4, sc, sh, se, ak, obb, oak, s1, s2);
+                                                             int px0, V sc, V sh, V obb, V& s1, V& s2) {
+    if (px0 + 0 < a.Wo) step<0>(st, a, xb, ob, r0, px0 + 0, sc, sh, obb, s1, s2);
+    if (K > 1 && px0 + 1 < a.Wo) step<(K > 1 ? 1 : 0)>(st, a, xb, ob, r0, px0 + 1, sc, sh, obb, s1, s2);
+    if (K > 2 && px0 + 2 < a.Wo) step<(K > 2 ? 2 : 0)>(st, a, xb, ob, r0, px0 + 2, sc, sh, obb, s1, s2);
+    if (K > 3 && px0 + 3 < a.Wo) step<(K > 3 ? 3 : 0)>(st, a, xb, ob, r0, px0 + 3, sc, sh, obb, s1, s2);
+    if (K > 4 && px0 + 4 < a.Wo) step<(K > 4 ? 4 : 0)>(st, a, xb, ob, r0, px0 + 4, sc, sh, obb, s1, s2);
   }
 
   // `Sink::stat(b, which, c, value)` receives the per-sample sums of one item
@@ -486,28 +491,31 @@ struct DwcFwd {
     dv_set(sc, 1.f); dv_set(sh, 0.f); dv_set(obb, 0.f);
     if (a.scale) { sc = dwc_ldc<CPT>(a.scale + c); sh = dwc_ldc<CPT>(a.shift + c); }
     if (a.out_bias) obb = dwc_ldc<CPT>(a.out_bias + c);
-    const DwcAct ak = dwc_make_act(a.act), oak = dwc_make_act(a.out_act);
+    V sc0 = sc, sh0 = sh;
     for (int item = il; item < a.n_items; item += a.item_lanes) {
       const int b = item / a.n_bands, band = item - b * a.n_bands;
       const int r0 = band * R;
-      V se;
-      dv_set(se, 1.f);
-      if (a.se) se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+      if (a.se) {                                       // u = se*(scale*x + shift) = (se*scale)*x + se*shift
+        const V se = dwc_ldc<CPT>(a.se + (size_t)b * a.C + c);
+        sc = dv_mul(se, sc0); sh = dv_mul(se, sh0);
+      }
       const T* xb = x + (size_t)b * a.H * a.W * a.C + c;
       T* ob = y + (size_t)b * a.Ho * a.Wo * a.C + c;
+      dwc_pin(xb); dwc_pin(ob);
 #pragma unroll
       for (int ai = 0; ai < NAI; ++ai) {
         const int qy = S * r0 - PAD + ai;
         st.ox[ai] = (uint32_t)(dwc_clampi(qy, 0, a.H - 1) * a.W * a.C);
+        dwc_pin(st.ox[ai]);
         st.mx[ai] = (qy >= 0 && qy < a.H) ? 1.f : 0.f;
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) st.oy[r] = (uint32_t)(dwc_clampi(r0 + r, 0, a.Ho - 1) * a.Wo * a.C);
+      for (int r = 0; r < R; ++r) { st.oy[r] = (uint32_t)(dwc_clampi(r0 + r, 0, a.Ho - 1) * a.Wo * a.C); dwc_pin(st.oy[r]); }
       V s1, s2;
       dv_set(s1, 0.f); dv_set(s2, 0.f);
       prefetch(st, a, xb, PXB);
 #pragma unroll 1
-      for (int px0 = PXB; px0 < a.Wo; px0 += K) run_phases(st, a, xb, ob, r0, px0, sc, sh, se, ak, obb, oak, s1, s2);
+      for (int px0 = PXB; px0 < a.Wo; px0 += K) run_phases(st, a, xb, ob, r0, px0, sc, sh, obb, s1, s2);
       if (a.stats) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {

@@ -65,7 +65,14 @@ static int run_case(int B, int H, int W, int C, int act, bool with_xf, int item_
   std::vector<double> dw((size_t)C * KK, 0.0), st(2 * (size_t)C, 0.0);
   HostSink sink = {&dw, &st, KK, C};
   for (int c = 0; c < C; c += CPT)
-    for (int il = 0; il < a.item_lanes; ++il) DwcBwd<T, K, S, R, CPT>::thread_main(a, c, il, sink);
+    for (int il = 0; il < a.item_lanes; ++il) {
+      switch (act) {            // the kernels take the activation as a template parameter
+        case TD3D_ACT_NONE: DwcBwd<T, K, S, R, CPT, TD3D_ACT_NONE>::thread_main(a, c, il, sink); break;
+        case TD3D_ACT_RELU: DwcBwd<T, K, S, R, CPT, TD3D_ACT_RELU>::thread_main(a, c, il, sink); break;
+        case TD3D_ACT_HSWISH: DwcBwd<T, K, S, R, CPT, TD3D_ACT_HSWISH>::thread_main(a, c, il, sink); break;
+        default: DwcBwd<T, K, S, R, CPT, TD3D_ACT_SILU>::thread_main(a, c, il, sink); break;
+      }
+    }
   // ---- reference ----
   std::vector<double> gy(g.size()), rgx(x.size(), 0.0), rdw((size_t)C * KK, 0.0), rst(2 * (size_t)C, 0.0);
   for (int b = 0; b < B; ++b)
@@ -170,7 +177,23 @@ static int run_fwd_case(int B, int H, int W, int C, int act, bool with_xf, int o
   std::vector<double> st((size_t)B * 2 * C, 0.0), rst((size_t)B * 2 * C, 0.0);
   HostFwdSink sink = {&st, C};
   for (int c = 0; c < C; c += CPT)
-    for (int il = 0; il < a.item_lanes; ++il) DwcFwd<T, K, S, R, CPT>::thread_main(a, c, il, sink);
+    for (int il = 0; il < a.item_lanes; ++il) {
+      // (input activation, output activation) pairs the launcher instantiates: (X, none) and (none, Y)
+      if (out_act == TD3D_ACT_NONE) {
+        switch (act) {
+          case TD3D_ACT_NONE: DwcFwd<T, K, S, R, CPT, TD3D_ACT_NONE, TD3D_ACT_NONE>::thread_main(a, c, il, sink); break;
+          case TD3D_ACT_RELU: DwcFwd<T, K, S, R, CPT, TD3D_ACT_RELU, TD3D_ACT_NONE>::thread_main(a, c, il, sink); break;
+          case TD3D_ACT_HSWISH: DwcFwd<T, K, S, R, CPT, TD3D_ACT_HSWISH, TD3D_ACT_NONE>::thread_main(a, c, il, sink); break;
+          default: DwcFwd<T, K, S, R, CPT, TD3D_ACT_SILU, TD3D_ACT_NONE>::thread_main(a, c, il, sink); break;
+        }
+      } else if (out_act == TD3D_ACT_HSWISH) {
+        DwcFwd<T, K, S, R, CPT, TD3D_ACT_NONE, TD3D_ACT_HSWISH>::thread_main(a, c, il, sink);
+      } else if (out_act == TD3D_ACT_SILU) {
+        DwcFwd<T, K, S, R, CPT, TD3D_ACT_NONE, TD3D_ACT_SILU>::thread_main(a, c, il, sink);
+      } else {
+        DwcFwd<T, K, S, R, CPT, TD3D_ACT_NONE, TD3D_ACT_RELU>::thread_main(a, c, il, sink);
+      }
+    }
   double err = 0, mx = 0;
   for (int b = 0; b < B; ++b)
     for (int py = 0; py < Ho; ++py)
@@ -206,9 +229,11 @@ static int run_all_fwd() {
   int bad = 0;
   const int shapes[][4] = {{2, 14, 14, 16}, {3, 7, 7, 24}, {2, 29, 23, 8}, {1, 56, 56, 8}, {2, 1, 5, 16}, {3, 2, 3, 8}, {1, 8, 8, 8}, {2, 5, 1, 8}};
   for (auto& s : shapes) {
-    for (int v = 0; v < 4; ++v) {
-      const int act = v, oact = v == 0 ? 2 : (v == 3 ? 3 : 0);
-      const bool xf = v != 0, bias = v == 0;
+    for (int v = 0; v < 5; ++v) {
+      // v = 0: inference epilogue (bias + h-swish); 1, 2: training inputs (ReLU / h-swish on load); 3: SiLU input;
+      // 4: inference epilogue with SiLU
+      const int act = v == 4 ? 0 : v, oact = v == 0 ? 2 : (v == 4 ? 3 : 0);
+      const bool xf = act != 0, bias = oact != 0;
       bad += run_fwd_case<T, 3, 1, 4, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 5);
       bad += run_fwd_case<T, 3, 1, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 1000);
       bad += run_fwd_case<T, 3, 2, 2, 2>(s[0], s[1], s[2], s[3], act, xf, oact, bias, 3);
