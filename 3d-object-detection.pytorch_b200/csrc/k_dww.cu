@@ -10,7 +10,7 @@
 //   * lane = (x, v): x = pixel column (XL = 8/16/32 lanes), v = 8-channel (16 B) vector; a warp owns
 //     one (sample, 32/XL vectors) plane at a time and WALKS ITS ROWS top to bottom;
 //   * each input element is loaded ONCE with a 16-byte load, transformed once in registers
-//     (BatchNorm fold + SE gate + activation, or the BatchNorm-backward affine of the gradient);
+//     (BatchNorm fold + SE gate + activation);
 //     horizontal neighbours come from warp shuffles, vertical reuse from K rolling accumulator
 //     rows held in registers -- no shared-memory tile, no CTA barrier in the main loop;
 //   * rows are prefetched 4-8 deep with cp.async into a per-warp shared-memory ring (each lane reads
@@ -18,12 +18,13 @@
 //     first version prefetched into registers and measured 2850 cycles per row step because the
 //     ring's register moves waited on the loads in flight;
 //   * statistics (BatchNorm sums / SE squeeze) stay in registers for the whole plane and leave the
-//     warp as one atomic per (sample, channel); the weight-gradient taps stay in registers for the
-//     whole kernel.
+//     warp as one atomic per (sample, channel).
 //
 //   forward   y  = dw(act(se*(scale*x+shift)))                      + sum y,  sum y^2   per (b,c)
-//   bwd-data  gx = act'(u(x)) * dw^T(alpha*g + beta*y + gamma)      + sum gx, sum gx*x  per (b,c)
-//   bwd-wgt   dW[c,ky,kx] += sum gy * x_t(shifted)
+//
+// Forward only: the backward twins of this kernel (round 1) lost to the one-pass column walker
+// (dwc_core.cuh) on every layer once that kernel's inner loop was cleaned up (profiles/r02_v5_dw_bench.txt)
+// and were removed.
 #include "td3d_kernels.h"
 
 #include <stdlib.h>
@@ -34,27 +35,15 @@ namespace {
 
 constexpr int WW_WARPS = 4;
 constexpr int WW_THREADS = 32 * WW_WARPS;
-enum { WW_FWD = 0, WW_DGRAD = 1 };
-
 struct WwArgs {
-  const void* s0;            // FWD: x (raw forward input);  DGRAD / WGRAD: g
-  const void* s1;            // DGRAD / WGRAD: y_out (saved raw conv output)
-  const void* xin;           // DGRAD / WGRAD: x (raw forward input)
+  const void* s0;            // x (raw forward input)
   XForm xf;                  // lazily applied transform of x
-  const float* alpha; const float* beta; const float* gamma;   // gy = alpha[b,c]*g + beta[c]*y + gamma[b,c]
   const float* w;            // [K*K][C] fp32 taps
-  void* out;                 // FWD: y; DGRAD: gx
+  void* out;                 // y
   float* stats;              // [B][2][C] or null
-  float* dw;                 // WGRAD: [C][K*K] (+=)
   int B, H, W, C;
   int xl_log2;               // lanes per image row = 1 << xl_log2 (>= W)
 };
-
-__device__ __forceinline__ float ww_actd(float u, int act) {
-  if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-  if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
-  return 1.f;
-}
 
 // ---- NV channels of one pixel as loaded from global memory (NV = 8: 16 B bf16 / 32 B fp32) ----
 __device__ __forceinline__ uint32_t ww_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,28 +84,6 @@ template <> struct WwRaw<float, 8> {
     v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
   }
 };
-template <> struct WwRaw<bf16, 4> {
-  uint2 r;
-  __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
-  static constexpr int BYTES = 8;
-  static __device__ __forceinline__ void fetch(uint32_t dst, const bf16* p) { ww_cp8(dst, p); }
-  __device__ __forceinline__ void lds(const uint8_t* p) { r = *reinterpret_cast<const uint2*>(p); }
-  __device__ __forceinline__ void get(float2 (&v)[2]) const {
-    v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
-    v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
-  }
-};
-template <> struct WwRaw<float, 4> {
-  float4 a;
-  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); }
-  static constexpr int BYTES = 16;
-  static __device__ __forceinline__ void fetch(uint32_t dst, const float* p) { ww_cp16(dst, p); }
-  __device__ __forceinline__ void lds(const uint8_t* p) { a = *reinterpret_cast<const float4*>(p); }
-  __device__ __forceinline__ void get(float2 (&v)[2]) const {
-    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
-  }
-};
-
 // store 8 channels in the activation dtype; r = the values as stored (rounded) for the statistics
 __device__ __forceinline__ void ww_store8(bf16* p, const float2 (&v)[4], float2 (&r)[4]) {
   uint4 raw;
@@ -153,39 +120,35 @@ __device__ __forceinline__ float2 ww_shift(const float2& v, int delta, int x, in
 }
 
 // per-channel constants in shared memory (written once per CTA): [which][channel of the warp's span]
-enum { WK_SC = 0, WK_SH, WK_BE, WK_N };
+enum { WK_SC = 0, WK_SH, WK_N };
 // per-(sample, channel) constants, double buffered per warp and prefetched one plane ahead with cp.async
-enum { WP_AL = 0, WP_GA, WP_SE, WP_N };
+enum { WP_SE = 0, WP_N };
 
-template <typename T> struct WwDepth {          // rows in flight per warp and tensor
+template <typename T> struct WwDepth {          // rows in flight per warp
   static constexpr int FWD = sizeof(T) == 2 ? 8 : 4;
-  static constexpr int BWD = sizeof(T) == 2 ? 6 : 3;
 };
 
 // prefetch the per-plane constants of sample b into kp[WP_N][NC] (NC floats per kind and warp);
 // `mine` = this lane copies the 16 bytes at channel offset `off` (floats) of the warp's span
 __device__ __forceinline__ void ww_fetch_plane_consts(float* kp, int NC, const WwArgs& a, int b, int c_span0, int off,
-                                                       bool mine, bool want_gy) {
+                                                       bool mine) {
   if (mine && b < a.B) {
     const size_t g = (size_t)b * a.C + c_span0 + off;
-    if (want_gy && a.alpha) ww_cp16(ww_s32(kp + WP_AL * NC + off), a.alpha + g);
-    if (want_gy && a.gamma) ww_cp16(ww_s32(kp + WP_GA * NC + off), a.gamma + g);
     if (a.xf.se) ww_cp16(ww_s32(kp + WP_SE * NC + off), a.xf.se + g);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward / backward-data
+// forward
 // ------------------------------------------------------------------------------------------------
-template <typename T, int K, int MODE, bool SEL>
+template <typename T, int K, bool SEL>
 __global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
 ww_conv_kernel(WwArgs a) {
   constexpr int P = (K - 1) / 2;
-  constexpr int NT = MODE == WW_FWD ? 1 : 3;                       // streamed tensors: x | g, y, x
-  constexpr int D = MODE == WW_FWD ? WwDepth<T>::FWD : WwDepth<T>::BWD;
+  constexpr int D = WwDepth<T>::FWD;
   constexpr int NS = D + 1;                                        // ring slots: the one consumed last step is refilled
   constexpr int VB = WwRaw<T, 8>::BYTES;
-  extern __shared__ __align__(16) uint8_t ww_dyn[];                // [warp][tensor][slot][lane] x VB bytes
+  extern __shared__ __align__(16) uint8_t ww_dyn[];                // [warp][slot][lane] x VB bytes
   __shared__ __align__(16) float s_w[K * K * WW_WARPS * 32];       // [tap][channel of the CTA span]
   __shared__ __align__(16) float s_k[WW_WARPS][WK_N][32];
   __shared__ __align__(16) float s_p[WW_WARPS][2][WP_N][32];
@@ -199,8 +162,7 @@ ww_conv_kernel(WwArgs a) {
   const int H = a.H, W = a.W, C = a.C;
   for (int i = threadIdx.x; i < K * K * span; i += WW_THREADS) {
     const int tap = i / span, cc = c_cta + i % span;
-    const int src = MODE == WW_DGRAD ? K * K - 1 - tap : tap;     // data gradient = correlation with the flipped filter
-    s_w[i] = cc < C ? a.w[(size_t)src * C + cc] : 0.f;
+    s_w[i] = cc < C ? a.w[(size_t)tap * C + cc] : 0.f;
   }
   const bool c_ok = c < C;
   const bool lane_ok = c_ok && x < W;
@@ -210,20 +172,13 @@ ww_conv_kernel(WwArgs a) {
     for (int i = 0; i < 8; ++i) {
       kw[WK_SC * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
       kw[WK_SH * 32 + v * 8 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
-      kw[WK_BE * 32 + v * 8 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {              // defaults of the per-plane constants (kept when a pointer is null)
-        s_p[warp][u][WP_AL][v * 8 + i] = 0.f;
-        s_p[warp][u][WP_GA][v * 8 + i] = 0.f;
-        s_p[warp][u][WP_SE][v * 8 + i] = 1.f;
-      }
+      for (int u = 0; u < 2; ++u) s_p[warp][u][WP_SE][v * 8 + i] = 1.f;   // default gate (kept when xf.se is null)
     }
   }
   __syncthreads();
   const float* wq = s_w + cl;
   const T* s0 = reinterpret_cast<const T*>(a.s0);
-  const T* s1 = reinterpret_cast<const T*>(a.s1);
-  const T* xin = reinterpret_cast<const T*>(a.xin);
   T* out = reinterpret_cast<T*>(a.out);
   const int act = a.xf.act;
   const ActK ak = make_actk(act);
@@ -233,9 +188,9 @@ ww_conv_kernel(WwArgs a) {
   const bool kc_mine = c_ok && x < 2;            // this lane copies 16 B (4 floats) of its vector's per-plane constants
   const int kc_off = v * 8 + x * 4;
 
-  uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
+  uint8_t* ring = ww_dyn + (size_t)warp * NS * 32 * VB + (size_t)lane * VB;
   const uint32_t ring_s = ww_s32(ring);
-  constexpr uint32_t SLOT = 32 * VB, TSTRIDE = NS * SLOT;          // bytes per ring slot / per tensor ring
+  constexpr uint32_t SLOT = 32 * VB, TSTRIDE = NS * SLOT;          // bytes per ring slot / per ring
 
   // ---- prefetch stream: 32-bit element offsets, advanced incrementally ----
   const uint32_t row_e = (uint32_t)W * (uint32_t)C;
@@ -245,14 +200,7 @@ ww_conv_kernel(WwArgs a) {
   uint32_t foff = (uint32_t)pb * (uint32_t)H * row_e + lane_e;     // element offset of row (pb, piy) for this lane
   uint32_t fslot = 0;                                              // byte offset of the slot to fill
   auto fetch = [&]() {
-    if (pb < a.B && lane_ok) {
-      if (piy < H) {
-        WwRaw<T, 8>::fetch(ring_s + fslot, s0 + foff);
-        if (MODE == WW_DGRAD) WwRaw<T, 8>::fetch(ring_s + TSTRIDE + fslot, s1 + foff);
-      }
-      if (MODE == WW_DGRAD && piy >= P)          // the x row of the output row emitted at that step
-        WwRaw<T, 8>::fetch(ring_s + 2 * TSTRIDE + fslot, xin + (foff - (uint32_t)P * row_e));
-    }
+    if (pb < a.B && lane_ok && piy < H) WwRaw<T, 8>::fetch(ring_s + fslot, s0 + foff);
     ww_commit();
     foff += row_e;
     if (++piy == steps) { piy = 0; pb += bstride; foff += plane_jump; }
@@ -260,7 +208,7 @@ ww_conv_kernel(WwArgs a) {
     if (fslot == TSTRIDE) fslot = 0;
   };
   // constants of the first plane, then the first D rows
-  ww_fetch_plane_consts(&s_p[warp][0][0][0], 32, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
+  ww_fetch_plane_consts(&s_p[warp][0][0][0], 32, a, (int)blockIdx.y, c_warp, kc_off, kc_mine);
   ww_commit();
   ww_wait<0>();
   __syncwarp();
@@ -274,7 +222,7 @@ ww_conv_kernel(WwArgs a) {
     if (steps <= D) ww_wait<0>();                // short planes: the constants' group may be younger than the ring depth
     __syncwarp();
     const float* kp = &s_p[warp][pbuf][0][0];
-    ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 32, a, b + bstride, c_warp, kc_off, kc_mine, MODE == WW_DGRAD);
+    ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 32, a, b + bstride, c_warp, kc_off, kc_mine);
     // S[k] = partial sums of output row (iy - P + k) before row iy is processed; row iy adds filter row 2P - k
     float2 S[K - 1][4];
 #pragma unroll
@@ -289,9 +237,8 @@ ww_conv_kernel(WwArgs a) {
 #pragma unroll 1
     for (int iy = 0; iy < steps; ++iy) {
       ww_wait<D - 1>();                                   // this step's rows have landed (own copies only)
-      WwRaw<T, 8> c0, c1, cx;
+      WwRaw<T, 8> c0;
       c0.lds(ring + cslot);
-      if (MODE == WW_DGRAD) { c1.lds(ring + TSTRIDE + cslot); cx.lds(ring + 2 * TSTRIDE + cslot); }
       cslot += SLOT;
       if (cslot == TSTRIDE) cslot = 0;
       fetch();                                            // refills the slot consumed one step ago
@@ -300,26 +247,14 @@ ww_conv_kernel(WwArgs a) {
         float2 vals[K][4];
         if (lane_ok) {
           c0.get(vals[P]);
-          if (MODE == WW_FWD) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
-              const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
-              const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
-              float2 u = __ffma2_rn(vals[P][i], sc, sh);
-              u = __fmul2_rn(u, e);
-              vals[P][i] = make_float2(actk_fwd(u.x, ak), actk_fwd(u.y, ak));
-            }
-          } else {
-            float2 yv[4];
-            c1.get(yv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 32 + v * 8 + 2 * i);
-              const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 32 + v * 8 + 2 * i);
-              const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 32 + v * 8 + 2 * i);
-              vals[P][i] = __ffma2_rn(al, vals[P][i], __ffma2_rn(be, yv[i], ga));
-            }
+          for (int i = 0; i < 4; ++i) {
+            const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
+            const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
+            const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
+            float2 u = __ffma2_rn(vals[P][i], sc, sh);
+            u = __fmul2_rn(u, e);
+            vals[P][i] = make_float2(actk_fwd(u.x, ak), actk_fwd(u.y, ak));
           }
         } else {
 #pragma unroll
@@ -367,31 +302,11 @@ ww_conv_kernel(WwArgs a) {
       if (iy >= P) {
         if (lane_ok) {
           float2 r[4];
-          if (MODE == WW_DGRAD) {
-            float2 xv[4];
-            cx.get(xv);
+          ww_store8(out + ooff, o, r);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 32 + v * 8 + 2 * i);
-              const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 32 + v * 8 + 2 * i);
-              const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 32 + v * 8 + 2 * i);
-              const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
-              o[i].x *= ww_actd(u.x, act);
-              o[i].y *= ww_actd(u.y, act);
-            }
-            ww_store8(out + ooff, o, r);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              st1[i] = __fadd2_rn(st1[i], r[i]);
-              st2[i] = __ffma2_rn(r[i], xv[i], st2[i]);
-            }
-          } else {
-            ww_store8(out + ooff, o, r);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              st1[i] = __fadd2_rn(st1[i], r[i]);
-              st2[i] = __ffma2_rn(r[i], r[i], st2[i]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            st1[i] = __fadd2_rn(st1[i], r[i]);
+            st2[i] = __ffma2_rn(r[i], r[i], st2[i]);
           }
         }
         ooff += row_e;
@@ -425,167 +340,6 @@ ww_conv_kernel(WwArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward weights: lane = (x, q) with q a 4-channel vector.  dW[ky][kx] += sum_o gy[o] x_t[o+k-P]:
-// per walked row the window of K transformed x rows stays unshifted and only the 4 gy values are
-// shifted horizontally (K-1 shuffles per channel), K*K FMAs per channel.
-// ------------------------------------------------------------------------------------------------
-template <typename T, int K, bool SEL>
-__global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
-ww_wgrad_kernel(WwArgs a) {
-  constexpr int P = (K - 1) / 2;
-  constexpr int NT = 3;
-  constexpr int D = WwDepth<T>::FWD;
-  constexpr int NS = D + 1;
-  constexpr int VB = WwRaw<T, 4>::BYTES;
-  extern __shared__ __align__(16) uint8_t ww_dyn[];
-  __shared__ __align__(16) float s_k[WW_WARPS][WK_N][16];
-  __shared__ __align__(16) float s_p[WW_WARPS][2][WP_N][16];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int XL = 1 << a.xl_log2, QL = 32 >> a.xl_log2;
-  const int x = lane & (XL - 1), q = lane >> a.xl_log2;
-  const int span = WW_WARPS * QL * 4;
-  const int c_warp = blockIdx.x * span + warp * QL * 4;
-  const int c = c_warp + q * 4;
-  const int H = a.H, W = a.W, C = a.C;
-  const bool c_ok = c < C;
-  const bool lane_ok = c_ok && x < W;
-  float* kw = &s_k[warp][0][0];
-  if (x == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      kw[WK_SC * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.scale[c + i] : 1.f;
-      kw[WK_SH * 16 + q * 4 + i] = (c_ok && a.xf.scale) ? a.xf.shift[c + i] : 0.f;
-      kw[WK_BE * 16 + q * 4 + i] = (c_ok && a.beta) ? a.beta[c + i] : 0.f;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        s_p[warp][u][WP_AL][q * 4 + i] = 0.f;
-        s_p[warp][u][WP_GA][q * 4 + i] = 0.f;
-        s_p[warp][u][WP_SE][q * 4 + i] = 1.f;
-      }
-    }
-  }
-  __syncwarp();
-  const T* gp = reinterpret_cast<const T*>(a.s0);
-  const T* yp = reinterpret_cast<const T*>(a.s1);
-  const T* xp = reinterpret_cast<const T*>(a.xin);
-  const ActK ak = make_actk(a.xf.act);
-  const int steps = H + P;
-  const int bstride = gridDim.y;
-  const bool kc_mine = c_ok && x == 0;           // one 16-byte copy per 4-channel vector and kind
-  const int kc_off = q * 4;
-
-  uint8_t* ring = ww_dyn + (size_t)warp * NT * NS * 32 * VB + (size_t)lane * VB;
-  const uint32_t ring_s = ww_s32(ring);
-  constexpr uint32_t SLOT = 32 * VB, TSTRIDE = NS * SLOT;
-  const uint32_t row_e = (uint32_t)W * (uint32_t)C;
-  const uint32_t lane_e = (uint32_t)x * (uint32_t)C + (uint32_t)c;
-  const uint32_t plane_jump = ((uint32_t)bstride * (uint32_t)H - (uint32_t)steps) * row_e;
-  int pb = blockIdx.y, piy = 0;
-  uint32_t foff = (uint32_t)pb * (uint32_t)H * row_e + lane_e;
-  uint32_t fslot = 0;
-  auto fetch = [&]() {
-    if (pb < a.B && lane_ok) {
-      if (piy < H) WwRaw<T, 4>::fetch(ring_s + 2 * TSTRIDE + fslot, xp + foff);                 // x row s
-      if (piy >= P) {                                                                           // gy row s - P
-        WwRaw<T, 4>::fetch(ring_s + fslot, gp + (foff - (uint32_t)P * row_e));
-        WwRaw<T, 4>::fetch(ring_s + TSTRIDE + fslot, yp + (foff - (uint32_t)P * row_e));
-      }
-    }
-    ww_commit();
-    foff += row_e;
-    if (++piy == steps) { piy = 0; pb += bstride; foff += plane_jump; }
-    fslot += SLOT;
-    if (fslot == TSTRIDE) fslot = 0;
-  };
-  ww_fetch_plane_consts(&s_p[warp][0][0][0], 16, a, (int)blockIdx.y, c_warp, kc_off, kc_mine, true);
-  ww_commit();
-  ww_wait<0>();
-  __syncwarp();
-#pragma unroll 1
-  for (int d = 0; d < D; ++d) fetch();
-  uint32_t cslot = 0;
-  int pbuf = 0;
-
-  float2 dwa[K * K][2];
-#pragma unroll
-  for (int t = 0; t < K * K; ++t) { dwa[t][0] = make_float2(0.f, 0.f); dwa[t][1] = dwa[t][0]; }
-
-  for (int b = blockIdx.y; b < a.B; b += bstride) {
-    if (steps <= D) ww_wait<0>();
-    __syncwarp();
-    const float* kp = &s_p[warp][pbuf][0][0];
-    ww_fetch_plane_consts(&s_p[warp][pbuf ^ 1][0][0], 16, a, b + bstride, c_warp, kc_off, kc_mine, true);
-    float2 xw[K][2];                // transformed x rows s-2P .. s (row o+ky-P of the current output row o = s-P)
-#pragma unroll
-    for (int k = 0; k < K; ++k) { xw[k][0] = make_float2(0.f, 0.f); xw[k][1] = xw[k][0]; }
-#pragma unroll 1
-    for (int s = 0; s < steps; ++s) {
-      ww_wait<D - 1>();
-      WwRaw<T, 4> cg, cy, cx;
-      cg.lds(ring + cslot);
-      cy.lds(ring + TSTRIDE + cslot);
-      cx.lds(ring + 2 * TSTRIDE + cslot);
-      cslot += SLOT;
-      if (cslot == TSTRIDE) cslot = 0;
-      fetch();
-#pragma unroll
-      for (int k = 0; k + 1 < K; ++k) { xw[k][0] = xw[k + 1][0]; xw[k][1] = xw[k + 1][1]; }
-      float2 gy[2];
-      const bool xrow = lane_ok && s < H;                  // rows below the plane are zero padding
-      const bool grow = lane_ok && s >= P;
-      float2 xv[2], gv[2], yv[2];
-      cx.get(xv); cg.get(gv); cy.get(yv);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float2 sc = *reinterpret_cast<const float2*>(kw + WK_SC * 16 + q * 4 + 2 * i);
-        const float2 sh = *reinterpret_cast<const float2*>(kw + WK_SH * 16 + q * 4 + 2 * i);
-        const float2 be = *reinterpret_cast<const float2*>(kw + WK_BE * 16 + q * 4 + 2 * i);
-        const float2 e = *reinterpret_cast<const float2*>(kp + WP_SE * 16 + q * 4 + 2 * i);
-        const float2 al = *reinterpret_cast<const float2*>(kp + WP_AL * 16 + q * 4 + 2 * i);
-        const float2 ga = *reinterpret_cast<const float2*>(kp + WP_GA * 16 + q * 4 + 2 * i);
-        const float2 u = __fmul2_rn(e, __ffma2_rn(xv[i], sc, sh));
-        xw[K - 1][i] = make_float2(xrow ? actk_fwd(u.x, ak) : 0.f, xrow ? actk_fwd(u.y, ak) : 0.f);
-        const float2 t = __ffma2_rn(al, gv[i], __ffma2_rn(be, yv[i], ga));
-        gy[i] = make_float2(grow ? t.x : 0.f, grow ? t.y : 0.f);
-      }
-      if (s >= P) {                                          // warp-uniform: output row o = s - P exists
-        // x_t[o+ky-P][x'] * gy[o][x' - kx + P] summed over x' (this lane's column)
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          float2 g0 = gy[0], g1 = gy[1];
-          if (kx != P) { g0 = ww_shift<SEL>(gy[0], P - kx, x, W); g1 = ww_shift<SEL>(gy[1], P - kx, x, W); }
-#pragma unroll
-          for (int ky = 0; ky < K; ++ky) {
-            dwa[ky * K + kx][0] = __ffma2_rn(xw[ky][0], g0, dwa[ky * K + kx][0]);
-            dwa[ky * K + kx][1] = __ffma2_rn(xw[ky][1], g1, dwa[ky * K + kx][1]);
-          }
-        }
-      }
-    }
-    pbuf ^= 1;
-  }
-  ww_wait<0>();
-  // ---- reduce the taps over the image-row lanes; one atomic per (channel, tap) and warp ----
-#pragma unroll
-  for (int t = 0; t < K * K; ++t) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      float vx = dwa[t][i].x, vy = dwa[t][i].y;
-      for (int o = 1; o < XL; o <<= 1) {
-        vx += __shfl_xor_sync(0xffffffffu, vx, o);
-        vy += __shfl_xor_sync(0xffffffffu, vy, o);
-      }
-      if (x == 0 && c_ok) {
-        atomicAdd(&a.dw[(size_t)(c + 2 * i) * K * K + t], vx);       // reference layout [C,1,K,K]
-        atomicAdd(&a.dw[(size_t)(c + 2 * i + 1) * K * K + t], vy);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------
 int ww_num_sms() {
   static int n = 0;
   if (!n) {
@@ -610,35 +364,21 @@ dim3 ww_grid(int B, int C, int span, int ctas_per_sm) {
   return dim3(gx, gy, 1);
 }
 
-template <typename T, int K, int MODE>
+template <typename T, int K>
 int ww_conv_launch(const WwArgs& a, cudaStream_t st) {
   const int XL = 1 << a.xl_log2;
   const int span = WW_WARPS * (32 >> a.xl_log2) * 8;
   const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
   const bool sel = a.W + (K - 1) / 2 > XL;
-  constexpr int D = MODE == WW_FWD ? WwDepth<T>::FWD : WwDepth<T>::BWD;
-  const size_t smem = (size_t)WW_WARPS * (MODE == WW_FWD ? 1 : 3) * (D + 1) * 32 * WwRaw<T, 8>::BYTES;
+  const size_t smem = (size_t)WW_WARPS * (WwDepth<T>::FWD + 1) * 32 * WwRaw<T, 8>::BYTES;
   static bool once = false;
   if (!once) {
-    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     once = true;
   }
-  if (sel) ww_conv_kernel<T, K, MODE, true><<<grid, WW_THREADS, smem, st>>>(a);
-  else ww_conv_kernel<T, K, MODE, false><<<grid, WW_THREADS, smem, st>>>(a);
-  TD3D_LAUNCH_CHECK();
-  return TD3D_OK;
-}
-
-template <typename T, int K>
-int ww_wgrad_launch(const WwArgs& a, cudaStream_t st) {
-  const int XL = 1 << a.xl_log2;
-  const int span = WW_WARPS * (32 >> a.xl_log2) * 4;
-  const dim3 grid = ww_grid(a.B, a.C, span, K == 3 ? 4 : 3);
-  const bool sel = a.W + (K - 1) / 2 > XL;
-  const size_t smem = (size_t)WW_WARPS * 3 * (WwDepth<T>::FWD + 1) * 32 * WwRaw<T, 4>::BYTES;
-  if (sel) ww_wgrad_kernel<T, K, true><<<grid, WW_THREADS, smem, st>>>(a);
-  else ww_wgrad_kernel<T, K, false><<<grid, WW_THREADS, smem, st>>>(a);
+  if (sel) ww_conv_kernel<T, K, true><<<grid, WW_THREADS, smem, st>>>(a);
+  else ww_conv_kernel<T, K, false><<<grid, WW_THREADS, smem, st>>>(a);
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -660,27 +400,8 @@ int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st) {
   WwArgs w = {};
   w.s0 = a.x; w.xf = a.xf; w.w = a.w_taps; w.out = a.y; w.stats = a.stats;
   w.B = a.B; w.H = a.H; w.W = a.W; w.C = a.C; w.xl_log2 = ww_xl_log2(a.W);
-  if (dtype == TD3D_BF16) return a.k == 3 ? ww_conv_launch<bf16, 3, WW_FWD>(w, st) : ww_conv_launch<bf16, 5, WW_FWD>(w, st);
-  return a.k == 3 ? ww_conv_launch<float, 3, WW_FWD>(w, st) : ww_conv_launch<float, 5, WW_FWD>(w, st);
-}
-
-int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st) {
-  TD3D_REQUIRE((double)a.B * a.H * a.W * a.C < 4294967296.0, "dw walker: tensor exceeds the 32-bit offset range");
-  WwArgs w = {};
-  w.s0 = a.g; w.s1 = a.y_out; w.xin = a.x; w.xf = a.xf;
-  w.alpha = a.alpha; w.beta = a.beta; w.gamma = a.gamma; w.w = a.w_taps;
-  w.out = a.gx; w.stats = a.stats; w.dw = a.dw;
-  w.B = a.B; w.H = a.H; w.W = a.W; w.C = a.C; w.xl_log2 = ww_xl_log2(a.W);
-  if (a.gx) {
-    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_conv_launch<bf16, 3, WW_DGRAD>(w, st) : ww_conv_launch<bf16, 5, WW_DGRAD>(w, st)));
-    else TD3D_TRY((a.k == 3 ? ww_conv_launch<float, 3, WW_DGRAD>(w, st) : ww_conv_launch<float, 5, WW_DGRAD>(w, st)));
-  }
-  if (a.dw) {
-    cudaStream_t wst = a.wgrad_stream ? (cudaStream_t)a.wgrad_stream : st;
-    if (dtype == TD3D_BF16) TD3D_TRY((a.k == 3 ? ww_wgrad_launch<bf16, 3>(w, wst) : ww_wgrad_launch<bf16, 5>(w, wst)));
-    else TD3D_TRY((a.k == 3 ? ww_wgrad_launch<float, 3>(w, wst) : ww_wgrad_launch<float, 5>(w, wst)));
-  }
-  return TD3D_OK;
+  if (dtype == TD3D_BF16) return a.k == 3 ? ww_conv_launch<bf16, 3>(w, st) : ww_conv_launch<bf16, 5>(w, st);
+  return a.k == 3 ? ww_conv_launch<float, 3>(w, st) : ww_conv_launch<float, 5>(w, st);
 }
 
 }  // namespace td3d

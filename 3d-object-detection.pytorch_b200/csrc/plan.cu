@@ -121,11 +121,11 @@ struct td3d_plan {
   uint64_t last_seed = 0; int last_training = 0;
   const int32_t* dropout_counter = nullptr;
   Prof prof;
-  // side streams of backward (created at bind time, outside any graph capture): [0] runs the weight-gradient
-  // GEMMs, [1] the depthwise weight-gradient kernels, concurrently with the data-gradient chain on the caller's stream
-  cudaStream_t side[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-  bool side_pending[2] = {false, false};
+  // side stream of backward (created at bind time, outside any graph capture): runs the weight-gradient GEMMs
+  // concurrently with the data-gradient chain on the caller's stream
+  cudaStream_t side[1] = {nullptr};
+  cudaEvent_t ev_fork[1] = {nullptr}, ev_join[1] = {nullptr};
+  bool side_pending[1] = {false};
   int overlap = 1;
   td3d::PackTable pack_table;
   td3d::PackTable pack_table_eval;       // weights * eval-mode BatchNorm scale (rebuilt with the fold, td3d_pack_weights)
@@ -473,23 +473,11 @@ static int p_dwf(const Ctx& c, const DwArgs& a, int dt, cudaStream_t st) {
   TD3D_K(PK_DW_FWD, (in + out) * c.esz(), launch_dw_fwd(a, dt, st));
   return TD3D_OK;
 }
-static int p_dwb(const Ctx& c, const DwBwdArgs& a0, int dt, cudaStream_t st) {
-  DwBwdArgs a = a0;
+static int p_dwb(const Ctx& c, const DwBwdArgs& a, int dt, cudaStream_t st) {
   int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
   double in = (double)a.B * a.H * a.W * a.C, out = (double)a.B * Ho * Wo * a.C;
-  // split backward: the weight-gradient kernel runs on side stream 1, concurrently with the data-gradient kernel (both
-  // read g, y_out, x: the second reader mostly hits L2); joined right after, because the next BatchNorm finalize
-  // overwrites the alpha/beta/gamma it reads.  The one-pass kernel (SiLU layers) needs no fork.
-  Ctx sc = c;
-  const bool split = dw_bwd_is_split(a);
-  if (split) TD3D_TRY(side_fork(c, 1, &sc));
-  a.wgrad_stream = sc.st != c.st ? (void*)sc.st : nullptr;
-  // algorithmic bytes = the fused ideal: read g, y_out, x once; write gx once
+  // algorithmic bytes: read g, y_out, x once; write gx once (what the one-pass kernel does)
   TD3D_K(PK_DW_BWD, (2 * out + 2 * in) * c.esz(), launch_dw_bwd(a, dt, st));
-  if (a.wgrad_stream) {
-    TD3D_TRY(side_done(c, 1));
-    TD3D_TRY(side_join(c, 1));
-  }
   return TD3D_OK;
 }
 
@@ -981,7 +969,6 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
                                c.G(pl->w_stem), B, pl->H, pl->W, n.stem_ch, dt, c.st));
   }
   TD3D_TRY(side_join(c, 0));          // every gradient of this stage range is final on c.st when the call returns
-  TD3D_TRY(side_join(c, 1));
   return TD3D_OK;
 }
 
@@ -1105,7 +1092,7 @@ int td3d_plan_create(const td3d_net_desc* net, int batch, int height, int width,
 
 void td3d_plan_destroy(td3d_plan* plan) {
   if (!plan) return;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 1; ++i) {
     if (plan->side[i]) cudaStreamDestroy(plan->side[i]);
     if (plan->ev_fork[i]) cudaEventDestroy(plan->ev_fork[i]);
     if (plan->ev_join[i]) cudaEventDestroy(plan->ev_join[i]);
@@ -1150,7 +1137,7 @@ int td3d_plan_bind(td3d_plan* pl, float* params, float* grads, float* bn_stats, 
   if (!pl->side[0]) {
     const char* e = getenv("TD3D_OVERLAP");
     pl->overlap = (e && atoi(e) == 0) ? 0 : 1;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 1; ++i) {
       TD3D_CUDA(cudaStreamCreateWithFlags(&pl->side[i], cudaStreamNonBlocking));
       TD3D_CUDA(cudaEventCreateWithFlags(&pl->ev_fork[i], cudaEventDisableTiming));
       TD3D_CUDA(cudaEventCreateWithFlags(&pl->ev_join[i], cudaEventDisableTiming));
@@ -1346,23 +1333,6 @@ int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, cons
     return launch_dw_fwd_v2(a, dtype, (cudaStream_t)stream);
   }
   return launch_dw_fwd(a, dtype, (cudaStream_t)stream);
-}
-int td3d_k_dw_bwd_ex(const void* g, const void* y_out, const float* alpha, const float* beta, const float* gamma,
-                     const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
-                     void* gx, float* dw, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, int impl,
-                     void* stream) {
-  DwBwdArgs a;
-  a.g = g; a.y_out = y_out; a.alpha = alpha; a.beta = beta; a.gamma = gamma;
-  a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.gx = gx; a.stats = stats; a.dw = dw;
-  a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
-  TD3D_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2) && C % 8 == 0, "dw_bwd_ex: bad kernel/stride/channels");
-  if (impl == 2) return launch_dw_bwd_fused(a, dtype, (cudaStream_t)stream);
-  if (impl == 1) {
-    TD3D_REQUIRE(act != TD3D_ACT_SILU && dw_walker_supported(H, W, C, k, stride),
-                 "dw_bwd_ex: the data / weight gradient pair exists for small stride-1 planes (W <= 32) without SiLU only");
-    return launch_dw_bwd_walker(a, dtype, (cudaStream_t)stream);
-  }
-  return launch_dw_bwd(a, dtype, (cudaStream_t)stream);
 }
 int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias, const void* ysaved,
                    float* stats, int stat_slots, int M, int N, int K, int dtype, int out_f32, int impl, void* stream) {

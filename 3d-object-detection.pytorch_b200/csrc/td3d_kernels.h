@@ -88,17 +88,13 @@ struct DwBwdArgs {
   float* stats;                                     // out: [B][2][C] sum gu_in, sum gu_in*x
   float* dw;                                        // out: grads arena, reference layout [C,1,k,k] (+=)
   int B, H, W, C, k, stride;
-  void* wgrad_stream = nullptr;                     // optional cudaStream_t for the weight-gradient kernel (null: same stream);
-                                                    // the caller orders it against the launching stream with events
 };
-int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);
-bool dw_bwd_is_split(const DwBwdArgs& a);   // true: separate weight-gradient kernel (may run on wgrad_stream)
-int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu (default)
+int launch_dw_bwd(const DwBwdArgs& a, int dtype, cudaStream_t st);      // = launch_dw_bwd_fused after argument checks
+int launch_dw_fwd_v2(const DwArgs& a, int dtype, cudaStream_t st);      // k_dw2.cu: tiled persistent kernels
 bool dw_walker_supported(int H, int W, int C, int k, int stride);       // k_dww.cu: small planes (W <= 32), stride 1
 int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st);
-int launch_dw_bwd_walker(const DwBwdArgs& a, int dtype, cudaStream_t st);
-int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);
-int launch_dw_fwd_cw(const DwArgs& a, int dtype, cudaStream_t st);        // k_dwc.cu: column walker (optional bias + activation epilogue)   // k_dwc.cu: one pass (data + weight gradient + sums)
+int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);  // k_dwc.cu: one pass (data + weight gradient + sums)
+int launch_dw_fwd_cw(const DwArgs& a, int dtype, cudaStream_t st);        // k_dwc.cu: column walker (optional bias + activation epilogue)
 
 // ---- k_gemm_simple.cu / k_gemm_tc.cu ----
 struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m,n])

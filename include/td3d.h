@@ -211,18 +211,14 @@ int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const fl
                   const float* gamma, const void* x, const float* scale, const float* shift,
                   const float* se, int act, const float* w_taps, void* gx, float* dw, float* stats,
                   int B, int H, int W, int C, int k, int stride, int dtype, void* stream);
-/* The same two ops with an explicit implementation choice (A/B measurements, kernel tests):
- *   fwd impl 0 = dispatch as the plan does, 1 = row walker / tiled kernels (k_dww.cu, k_dw2.cu), 2 = column walker (k_dwc.cu);
- *       out_bias / out_act (column walker only): y = out_act(dw(...) + out_bias[c]) -- the inference epilogue with eval-mode
- *       BatchNorm folded into the taps
- *   bwd impl 0 = dispatch, 1 = separate data / weight gradient kernels (stride 1, W <= 32 only), 2 = one-pass column walker */
+/* The forward with an explicit implementation choice (A/B measurements, kernel tests; the backward has a single
+ * implementation, the one-pass column walker):
+ *   impl 0 = dispatch as the plan does, 1 = row walker / tiled kernels (k_dww.cu, k_dw2.cu), 2 = column walker (k_dwc.cu);
+ *   out_bias / out_act (column walker only): y = out_act(dw(...) + out_bias[c]) -- the inference epilogue with eval-mode
+ *   BatchNorm folded into the taps */
 int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, const float* se, int act,
                      const float* w_taps, const float* out_bias, int out_act, void* y, float* stats, int B, int H,
                      int W, int C, int k, int stride, int dtype, int impl, void* stream);
-int td3d_k_dw_bwd_ex(const void* g, const void* y_out, const float* alpha, const float* beta,
-                     const float* gamma, const void* x, const float* scale, const float* shift,
-                     const float* se, int act, const float* w_taps, void* gx, float* dw, float* stats,
-                     int B, int H, int W, int C, int k, int stride, int dtype, int impl, void* stream);
 int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias,
                    const void* ysaved, float* stats, int stat_slots, int M, int N, int K, int dtype,
                    int out_f32, int impl, void* stream);

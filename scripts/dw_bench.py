@@ -37,7 +37,7 @@ def main():
     L.require_b200()
     dev, code = "cuda", L.BF16
     tot = [0.0] * 4
-    print(f"{'layer':28s} {'fwd old us':>10s} {'GB/s':>7s} {'fwd cw us':>10s} {'GB/s':>7s} {'bwd split us':>12s} {'GB/s':>7s} {'bwd fused us':>12s} {'GB/s':>7s}")
+    print(f"{'layer':28s} {'fwd old us':>10s} {'GB/s':>7s} {'fwd cw us':>10s} {'GB/s':>7s} {'fwd plan us':>11s} {'GB/s':>7s} {'bwd us':>12s} {'GB/s':>7s}")
     for i, (H, C, k, s) in enumerate(LAYERS):
         if only and i not in only:
             continue
@@ -50,16 +50,15 @@ def main():
         alpha, gamma, beta = torch.randn(B, C, device=dev), torch.randn(B, C, device=dev) * 0.1, torch.randn(C, device=dev) * 0.1
         fb = 2.0 * B * C * (H * H + Ho * Ho)
         bb = 2.0 * B * C * (2 * H * H + 2 * Ho * Ho)
-        has_split = s == 1 and H <= 32       # the data / weight gradient pair survives for small stride-1 planes only
         t = [timed(lambda: K.dw_fwd_ex(x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code, 1)),
              timed(lambda: K.dw_fwd_ex(x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code, 2)),
-             timed(lambda: K.dw_bwd_ex(g, y, alpha, beta, gamma, x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code, 1)) if has_split else float("nan"),
-             timed(lambda: K.dw_bwd_ex(g, y, alpha, beta, gamma, x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code, 2))]
+             timed(lambda: K.dw_fwd_ex(x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code, 0)),
+             timed(lambda: K.dw_bwd(g, y, alpha, beta, gamma, x, scale, shift, None, L.ACT_HSWISH, taps, k, s, code))]
         for j in range(4):
             tot[j] += t[j]
         print(f"{i + 1:2d} {H:3d}x{H:<3d} C={C:<4d} k={k} s={s}     {t[0]:10.1f} {fb / t[0] / 1e3:7.0f} {t[1]:10.1f} {fb / t[1] / 1e3:7.0f} "
-              f"{t[2]:12.1f} {bb / t[2] / 1e3:7.0f} {t[3]:12.1f} {bb / t[3] / 1e3:7.0f}")
-    print(f"{'total':28s} {tot[0]:10.1f} {'':7s} {tot[1]:10.1f} {'':7s} {tot[2]:12.1f} {'':7s} {tot[3]:12.1f}")
+              f"{t[2]:11.1f} {fb / t[2] / 1e3:7.0f} {t[3]:12.1f} {bb / t[3] / 1e3:7.0f}")
+    print(f"{'total':28s} {tot[0]:10.1f} {'':7s} {tot[1]:10.1f} {'':7s} {tot[2]:11.1f} {'':7s} {tot[3]:12.1f}")
 
 
 if __name__ == "__main__":

@@ -91,17 +91,6 @@ def dw_fwd_ex(x, scale, shift, se, act, w_taps, k, stride, code, impl, out_bias=
     return y, st
 
 
-def dw_bwd_ex(g, y_out, alpha, beta, gamma, x, scale, shift, se, act, w_taps, k, stride, code, impl):
-    B, H, W, Cn = x.shape
-    gx = torch.empty_like(x)
-    dw = torch.zeros(Cn, 1, k, k, device=x.device)
-    st = stats_buf(B, Cn, x.device)
-    L.check(L.lib().td3d_k_dw_bwd_ex(L.ptr(g), L.ptr(y_out), L.ptr(alpha), L.ptr(beta), L.ptr(gamma), L.ptr(x), L.ptr(scale),
-                                     L.ptr(shift), L.ptr(se), act, L.ptr(w_taps), L.ptr(gx), L.ptr(dw), L.ptr(st), B, H, W, Cn,
-                                     k, stride, code, impl, L.stream()))
-    return gx, dw, st
-
-
 def dw_bwd(g, y_out, alpha, beta, gamma, x, scale, shift, se, act, w_taps, k, stride, code):
     B, H, W, Cn = x.shape
     gx = torch.empty_like(x)
