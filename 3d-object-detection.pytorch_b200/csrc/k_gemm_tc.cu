@@ -204,7 +204,7 @@ struct TcNtParams {
   int mma_warps;        // 1 or 2 MMA issuer warps (2 only when a tile's k blocks of both issuers fit the smem ring at once:
                         // a parity wait must never be more than one phase away from its barrier)
   int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
-                        // 4 no shared atomics, 8 no global reductions, 16 no TMEM load
+                        // 8 no global reductions, 16 no TMEM load
 };
 
 // Measured on B200 (TD3D_TC_DBG=32 timeline): with a single 4-warp epilogue group every 32-column chunk
@@ -427,35 +427,34 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           ysel ^= 1u;
         }
         if (p.stats && !(p.dbg & 2)) {
-          float t1 = warp_transpose_sum32_tc(v);
-          float t2 = warp_transpose_sum32_tc(w2);
-          if (!(p.dbg & 4)) {
-            gstat[q][0][ch * 32 + lane] = t1;      // one warp per TMEM lane quarter owns row q
-            gstat[q][1][ch * 32 + lane] = t2;
-          } else if (t1 + t2 == 123.456f) {
-            gstat[q][0][lane] = t1;
-          }
+          // column sums of this warp's 32 rows, accumulated over ALL tiles of the CTA in the warp's own shared-memory
+          // row (every tile of a CTA covers the same N tile, see the launcher): no barrier, no atomics per tile
+          const float t1 = warp_transpose_sum32_tc(v);
+          const float t2 = warp_transpose_sum32_tc(w2);
+          gstat[q][0][ch * 32 + lane] += t1;
+          gstat[q][1][ch * 32 + lane] += t2;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (q == 2 && lane == 0) TC_STAMP(6, ti);
       if (lane == 0) mbar_arrive(smem_u32(&s_tempty[as]));
-      if (p.stats) {
-        asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
-        const int slot = m_tile % p.slots;
-        for (int j = et; j < 2 * p.block_n; j += 128) {
-          const int which = j / p.block_n, nn = j % p.block_n;
-          const float tot = (gstat[0][which][nn] + gstat[1][which][nn]) + (gstat[2][which][nn] + gstat[3][which][nn]);
-          if (n0 + nn < p.N && !(p.dbg & 8)) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
-      }
-      if (q == 2 && lane == 0) TC_STAMP(7, ti);
       as += G;                                   // stage / phase of tile ti + G
       while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
     if (p.tma_store && lane == 0) bulk_wait_all();
+    // one flush per CTA and epilogue group: the four lane-quarter rows are added and leave as one atomic per column.
+    // The slot only spreads the atomics of the CTAs (the finalize kernels add all slots).
+    if (p.stats && eg < G && (int)blockIdx.x + eg * (int)gridDim.x < num_tiles) {
+      asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
+      const int n0 = p.n_tiles == 1 ? 0 : ((int)blockIdx.x % p.n_tiles) * p.block_n;
+      const int slot = ((int)blockIdx.x / p.n_tiles) % p.slots;
+      for (int j = et; j < 2 * p.block_n; j += 128) {
+        const int which = j / p.block_n, nn = j % p.block_n;
+        const float tot = (gstat[0][which][nn] + gstat[1][which][nn]) + (gstat[2][which][nn] + gstat[3][which][nn]);
+        if (n0 + nn < p.N && !(p.dbg & 8)) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -704,17 +703,18 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.act = g.act;
   p.lbo_field_bytes = kn.lbo;
   p.dbg = kn.dbg;
-  // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
-  // costs the statistics epilogue 4-8 % of its issue slots, and with two issuers the accumulator stages are no longer
-  // committed in tile order: an epilogue group that runs >= 5 tiles ahead of the slower issuer could see the parity of
-  // a stage's previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the
-  // second issuer is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
-  p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
   p.n_acc = TC_TMEM_COLS / p.acc_stride;
   if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
   p.epi_groups = p.n_acc < TC_EPI_GROUPS ? p.n_acc : TC_EPI_GROUPS;
+  // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
+  // costs the statistics epilogue 4-8 % of its issue slots, and with two issuers the accumulator stages are no longer
+  // committed in tile order: nothing bounds how far one issuer may fall behind the other (up to the smem ring depth), so an
+  // epilogue group that runs >= n_acc - G tiles ahead of the slower issuer could see the parity of a stage's
+  // previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the second issuer
+  // is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
+  p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   CUtensorMap map_a, map_w, map_y;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
@@ -729,6 +729,9 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms()) grid = num_sms();
+  // tile t covers N tile t % n_tiles and CTA c takes tiles c, c + grid, ...: with grid a multiple of n_tiles every tile of
+  // a CTA lies in the same N tile, which lets the statistics epilogue keep one accumulator row per CTA (flushed once)
+  grid -= grid % p.n_tiles;
   if (p.act != TD3D_ACT_NONE) gemm_nt_tc_kernel<true><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
   else gemm_nt_tc_kernel<false><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
   TD3D_LAUNCH_CHECK();
