@@ -23,6 +23,7 @@ struct SmemSink {
 
 template <typename T, int K, int S, int R, int CPT, int ACT>
 __global__ void __launch_bounds__(256, 2) dwc_bwd_kernel(DwcArgs a) {
+  pdl_entry();
   extern __shared__ float s_acc[];
   constexpr int KK = K * K;
   const int chunk = blockIdx.x % a.n_cchunks, ib = blockIdx.x / a.n_cchunks;
@@ -106,7 +107,7 @@ int dwc_launch_a(const DwBwdArgs& b, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)(K * K + 2) * a.cw * CPT;
   auto kern = dwc_bwd_kernel<T, K, S, R, CPT, ACT>;
   if (smem > 48 * 1024) TD3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ib * a.n_cchunks, threads, smem, st>>>(a);
+  TD3D_CUDA(launch_kernel(kern, ib * a.n_cchunks, threads, smem, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -148,6 +149,7 @@ struct GlobalStatSink {
 
 template <typename T, int K, int S, int R, int CPT, int ACT, int OACT>
 __global__ void __launch_bounds__(256, 2) dwc_fwd_kernel(DwcFwdArgs a) {
+  pdl_entry();
   const int chunk = blockIdx.x % a.n_cchunks, ib = blockIdx.x / a.n_cchunks;
   const int ncg = a.C / CPT;
   const int cg0 = chunk * a.cw;
@@ -183,7 +185,7 @@ int dwc_fwd_launch_a(const DwArgs& b, cudaStream_t st) {
   if (ib > ib_max) ib = ib_max;
   a.item_lanes = ib * a.ilb;
   if (a.item_lanes > a.n_items) a.item_lanes = a.n_items;
-  dwc_fwd_kernel<T, K, S, R, CPT, ACT, OACT><<<ib * a.n_cchunks, threads, 0, st>>>(a);
+  TD3D_CUDA(launch_kernel(dwc_fwd_kernel<T, K, S, R, CPT, ACT, OACT>, ib * a.n_cchunks, threads, 0, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -13,6 +13,7 @@ static const int BN_WARPS = 16;   // block = 16 warps x 32 channels; warps strid
 
 // block: 32 consecutive channels (lane) x BN_WARPS slot-lanes (warp). Coalesced slot reads, double sums.
 __global__ void __launch_bounds__(32 * BN_WARPS) bn_finalize_fwd_kernel(BnFwdArgs a) {
+  pdl_entry();
   __shared__ double s_sum[2][BN_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -60,13 +61,14 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_finalize_fwd_kernel(BnFwdArg
 }
 
 int launch_bn_finalize_fwd(const BnFwdArgs& a, cudaStream_t st) {
-  bn_finalize_fwd_kernel<<<ceil_div(a.C, 32), 32 * BN_WARPS, 0, st>>>(a);
+  TD3D_CUDA(launch_kernel(bn_finalize_fwd_kernel, ceil_div(a.C, 32), 32 * BN_WARPS, 0, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
 __global__ void bn_eval_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
                                     float* scale, float* shift, int C, float eps) {
+  pdl_entry();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   // same operation order as ATen's eval-mode batch_norm: (x - mean) * (gamma / sqrt(var + eps)) + beta
@@ -78,7 +80,7 @@ __global__ void bn_eval_fold_kernel(const float* gamma, const float* beta, const
 
 int launch_bn_eval_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
                         float* shift, int C, float eps, cudaStream_t st) {
-  bn_eval_fold_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, rm, rv, scale, shift, C, eps);
+  TD3D_CUDA(launch_kernel(bn_eval_fold_kernel, ceil_div(C, 128), 128, 0, st, gamma, beta, rm, rv, scale, shift, C, eps));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -90,6 +92,7 @@ int launch_bn_eval_fold(const float* gamma, const float* beta, const float* rm, 
 //   g_y = a*(g_z - mean_M(g_z) - x_hat*mean_M(g_z*x_hat))
 //       = alpha[b,c]*g_u + beta[c]*y + gammac[b,c]
 __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArgs a) {
+  pdl_entry();
   __shared__ double s_sum[2][BN_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(32 * BN_WARPS) bn_bwd_finalize_kernel(BnBwdArg
 int launch_bn_bwd_finalize(const BnBwdArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(!a.se || a.slots == a.B, "bn_bwd_finalize: SE mode needs slots == B");
   const int gy = a.B >= 64 ? 8 : 1;
-  bn_bwd_finalize_kernel<<<dim3(ceil_div(a.C, 32), gy), 32 * BN_WARPS, 0, st>>>(a);
+  TD3D_CUDA(launch_kernel(bn_bwd_finalize_kernel, dim3(ceil_div(a.C, 32), gy), 32 * BN_WARPS, 0, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

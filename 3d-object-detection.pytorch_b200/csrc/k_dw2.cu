@@ -403,6 +403,7 @@ template <typename T, int K, int S, int CG>
 __global__ void __launch_bounds__(D2_THREADS, 2)
 d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T* __restrict__ y,
               float* __restrict__ stats, int B, int H, int W, int Ho, int Wo, int C, D2Tile t, D2Smem sm) {
+  pdl_entry();
   constexpr int P = (K - 1) / 2, OY = D2Geo<S>::OY, OX = D2Geo<S>::OX, PS = D2C<CG>::PS;
   extern __shared__ __align__(16) uint8_t d2_smem[];
   __shared__ D2Consts<CG> kc;
@@ -584,8 +585,8 @@ int d2_fwd_launch(const DwArgs& a, const D2Tile& t, int Ho, int Wo, cudaStream_t
   const int part = D2C<CG>::NSP * 2 * CG;
   const D2Smem sm = smem_layout(t, 0, sizeof(T), part);
   dim3 grid(d2_grid_x(t), t.n_groups);
-  d2_fwd_kernel<T, K, S, CG><<<grid, D2_THREADS, smem_bytes(sm, 1), st>>>((const T*)a.x, a.xf, a.w_taps, (T*)a.y, a.stats, a.B,
-                                                                          a.H, a.W, Ho, Wo, a.C, t, sm);
+  TD3D_CUDA(launch_kernel(d2_fwd_kernel<T, K, S, CG>, grid, D2_THREADS, smem_bytes(sm, 1), st, (const T*)a.x, a.xf, a.w_taps, (T*)a.y, a.stats, a.B,
+                                                                          a.H, a.W, Ho, Wo, a.C, t, sm));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -144,6 +144,7 @@ __device__ __forceinline__ void ww_fetch_plane_consts(float* kp, int NC, const W
 template <typename T, int K, bool SEL>
 __global__ void __launch_bounds__(WW_THREADS, K == 3 ? 4 : 3)
 ww_conv_kernel(WwArgs a) {
+  pdl_entry();
   constexpr int P = (K - 1) / 2;
   constexpr int D = WwDepth<T>::FWD;
   constexpr int NS = D + 1;                                        // ring slots: the one consumed last step is refilled
@@ -377,8 +378,8 @@ int ww_conv_launch(const WwArgs& a, cudaStream_t st) {
     TD3D_CUDA(cudaFuncSetAttribute(ww_conv_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     once = true;
   }
-  if (sel) ww_conv_kernel<T, K, true><<<grid, WW_THREADS, smem, st>>>(a);
-  else ww_conv_kernel<T, K, false><<<grid, WW_THREADS, smem, st>>>(a);
+  if (sel) TD3D_CUDA(launch_kernel(ww_conv_kernel<T, K, true>, grid, WW_THREADS, smem, st, a));
+  else TD3D_CUDA(launch_kernel(ww_conv_kernel<T, K, false>, grid, WW_THREADS, smem, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

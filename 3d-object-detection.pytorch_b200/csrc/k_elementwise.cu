@@ -43,6 +43,7 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res, T* __restrict__ out,
                    float* __restrict__ stats, int HW, int C, int pix_per_block) {
+  pdl_entry();
   extern __shared__ float s_acc[];  // [C] when stats
   const int b = blockIdx.y;
   const ActK ak = make_actk(xf.act);
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 affine2_kernel(const T* g, const T* __restrict__ y, const float* __restrict__ alpha,
                const float* __restrict__ beta, const float* __restrict__ gamma, T* out,
                int HW, int C, int pix_per_block) {
+  pdl_entry();
   const int b = blockIdx.y;
   for (int cv0 = 0; cv0 < (C >> 3); cv0 += blockDim.x) {
     int CV = min((int)blockDim.x, (C >> 3) - cv0);
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(EW_THREADS, 2)
 act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_scale,
                      const T* __restrict__ y, XForm xf, T* gu, float* __restrict__ stats,
                      const T* __restrict__ addend, int HW, int C, int pix_per_block) {
+  pdl_entry();
   extern __shared__ float s_acc[];  // [2][C]
   const int b = blockIdx.y;
   const ActK ak = make_actk(xf.act);
@@ -260,6 +263,7 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
 template <typename T>
 __global__ void pool_finalize_kernel(const float* __restrict__ stats, float scale, T* __restrict__ out,
                                      int B, int C) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   int b = i / C, c = i % C;
@@ -288,9 +292,9 @@ int launch_apply_xform(const void* y, const XForm& xf, const void* res, void* ou
   ew_grid(B, HW, C, &grid, &ppb);
   size_t smem = pool_stats ? sizeof(float) * C : 0;
   if (dtype == TD3D_BF16)
-    apply_xform_kernel<bf16><<<grid, EW_THREADS, smem, st>>>((const bf16*)y, xf, (const bf16*)res, (bf16*)out, pool_stats, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(apply_xform_kernel<bf16>, grid, EW_THREADS, smem, st, (const bf16*)y, xf, (const bf16*)res, (bf16*)out, pool_stats, HW, C, ppb));
   else
-    apply_xform_kernel<float><<<grid, EW_THREADS, smem, st>>>((const float*)y, xf, (const float*)res, (float*)out, pool_stats, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(apply_xform_kernel<float>, grid, EW_THREADS, smem, st, (const float*)y, xf, (const float*)res, (float*)out, pool_stats, HW, C, ppb));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -301,9 +305,9 @@ int launch_affine2(const void* g, const void* y, const float* alpha, const float
   dim3 grid; int ppb;
   ew_grid(B, HW, C, &grid, &ppb);
   if (dtype == TD3D_BF16)
-    affine2_kernel<bf16><<<grid, EW_THREADS, 0, st>>>((const bf16*)g, (const bf16*)y, alpha, beta, gamma, (bf16*)out, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(affine2_kernel<bf16>, grid, EW_THREADS, 0, st, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, (bf16*)out, HW, C, ppb));
   else
-    affine2_kernel<float><<<grid, EW_THREADS, 0, st>>>((const float*)g, (const float*)y, alpha, beta, gamma, (float*)out, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(affine2_kernel<float>, grid, EW_THREADS, 0, st, (const float*)g, (const float*)y, alpha, beta, gamma, (float*)out, HW, C, ppb));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -315,9 +319,9 @@ int launch_act_bwd_stats(const void* g, const float* g_pooled, float g_scale, co
   ew_grid(B, HW, C, &grid, &ppb);
   size_t smem = stats ? sizeof(float) * 2 * C : 0;
   if (dtype == TD3D_BF16)
-    act_bwd_stats_kernel<bf16><<<grid, EW_THREADS, smem, st>>>((const bf16*)g, g_pooled, g_scale, (const bf16*)y, xf, (bf16*)gu, stats, (const bf16*)addend, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(act_bwd_stats_kernel<bf16>, grid, EW_THREADS, smem, st, (const bf16*)g, g_pooled, g_scale, (const bf16*)y, xf, (bf16*)gu, stats, (const bf16*)addend, HW, C, ppb));
   else
-    act_bwd_stats_kernel<float><<<grid, EW_THREADS, smem, st>>>((const float*)g, g_pooled, g_scale, (const float*)y, xf, (float*)gu, stats, (const float*)addend, HW, C, ppb);
+    TD3D_CUDA(launch_kernel(act_bwd_stats_kernel<float>, grid, EW_THREADS, smem, st, (const float*)g, g_pooled, g_scale, (const float*)y, xf, (float*)gu, stats, (const float*)addend, HW, C, ppb));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -325,9 +329,9 @@ int launch_act_bwd_stats(const void* g, const float* g_pooled, float g_scale, co
 int launch_pool_finalize(const float* stats, float scale, void* out, int B, int C, int dtype, cudaStream_t st) {
   int n = B * C;
   if (dtype == TD3D_BF16)
-    pool_finalize_kernel<bf16><<<ceil_div(n, 256), 256, 0, st>>>(stats, scale, (bf16*)out, B, C);
+    TD3D_CUDA(launch_kernel(pool_finalize_kernel<bf16>, ceil_div(n, 256), 256, 0, st, stats, scale, (bf16*)out, B, C));
   else
-    pool_finalize_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(stats, scale, (float*)out, B, C);
+    TD3D_CUDA(launch_kernel(pool_finalize_kernel<float>, ceil_div(n, 256), 256, 0, st, stats, scale, (float*)out, B, C));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(GS_THREADS)
 gemm_nt_simt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, T* __restrict__ Y, float* __restrict__ Yf,
                     const T* __restrict__ addend, const float* __restrict__ bias, const T* __restrict__ ysaved,
                     float* __restrict__ stats, int slots, int M, int N, int K, int act) {
+  pdl_entry();
   __shared__ __align__(16) float As[GS_BK][GS_BM + 4];
   __shared__ __align__(16) float Bs[GS_BK][GS_BN + 4];
   __shared__ float s_stat[2][GS_BN];
@@ -107,13 +108,13 @@ int launch_gemm_nt_simt(const GemmNT& g, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(!g.stats || g.slots > 0, "gemm_nt: stats need slots > 0");
   dim3 grid(ceil_div(g.M, GS_BM), ceil_div(g.N, GS_BN));
   if (dtype == TD3D_BF16)
-    gemm_nt_simt_kernel<bf16><<<grid, GS_THREADS, 0, st>>>(
+    TD3D_CUDA(launch_kernel(gemm_nt_simt_kernel<bf16>, grid, GS_THREADS, 0, st, 
         (const bf16*)g.a, (const bf16*)g.w, g.out_f32 ? nullptr : (bf16*)g.y, g.out_f32 ? (float*)g.y : nullptr,
-        (const bf16*)g.addend, g.bias, (const bf16*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act);
+        (const bf16*)g.addend, g.bias, (const bf16*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act));
   else
-    gemm_nt_simt_kernel<float><<<grid, GS_THREADS, 0, st>>>(
+    TD3D_CUDA(launch_kernel(gemm_nt_simt_kernel<float>, grid, GS_THREADS, 0, st, 
         (const float*)g.a, (const float*)g.w, g.out_f32 ? nullptr : (float*)g.y, g.out_f32 ? (float*)g.y : nullptr,
-        (const float*)g.addend, g.bias, (const float*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act);
+        (const float*)g.addend, g.bias, (const float*)g.ysaved, g.stats, g.slots, g.M, g.N, g.K, g.act));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -123,6 +124,7 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
 gemm_tn_simt_kernel(const T* __restrict__ A, const T* __restrict__ Bm, float* __restrict__ C, int M, int N1, int N2,
                     int m_per_part) {
+  pdl_entry();
   __shared__ __align__(16) float As[GS_BK][GS_BM + 4];
   __shared__ __align__(16) float Bs[GS_BK][GS_BN + 4];
   const int n10 = blockIdx.x * GS_BM, n20 = blockIdx.y * GS_BN;
@@ -180,9 +182,9 @@ int launch_gemm_tn_simt(const GemmTN& g, int dtype, cudaStream_t st) {
   parts = ceil_div(g.M, mpp);
   dim3 grid(ceil_div(g.N1, GS_BM), ceil_div(g.N2, GS_BN), parts);
   if (dtype == TD3D_BF16)
-    gemm_tn_simt_kernel<bf16><<<grid, GS_THREADS, 0, st>>>((const bf16*)g.a, (const bf16*)g.b, g.c, g.M, g.N1, g.N2, mpp);
+    TD3D_CUDA(launch_kernel(gemm_tn_simt_kernel<bf16>, grid, GS_THREADS, 0, st, (const bf16*)g.a, (const bf16*)g.b, g.c, g.M, g.N1, g.N2, mpp));
   else
-    gemm_tn_simt_kernel<float><<<grid, GS_THREADS, 0, st>>>((const float*)g.a, (const float*)g.b, g.c, g.M, g.N1, g.N2, mpp);
+    TD3D_CUDA(launch_kernel(gemm_tn_simt_kernel<float>, grid, GS_THREADS, 0, st, (const float*)g.a, (const float*)g.b, g.c, g.M, g.N1, g.N2, mpp));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -217,6 +217,7 @@ template <bool EPI_ACT>
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, TcNtParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[TC_MAX_ACC], s_tempty[TC_MAX_ACC];
   __shared__ __align__(8) uint64_t s_wfull;
@@ -482,6 +483,7 @@ struct TcTnParams {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcTnParams p) {
+  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[TN_STAGES], s_empty[TN_STAGES], s_tfull;
   __shared__ uint32_t s_tmem_base;
@@ -732,8 +734,8 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // tile t covers N tile t % n_tiles and CTA c takes tiles c, c + grid, ...: with grid a multiple of n_tiles every tile of
   // a CTA lies in the same N tile, which lets the statistics epilogue keep one accumulator row per CTA (flushed once)
   grid -= grid % p.n_tiles;
-  if (p.act != TD3D_ACT_NONE) gemm_nt_tc_kernel<true><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
-  else gemm_nt_tc_kernel<false><<<grid, TC_NT_THREADS, smem, st>>>(map_a, map_w, map_y, p);
+  if (p.act != TD3D_ACT_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<true>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -784,7 +786,7 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(n1_tiles, n2_tiles, parts);
-  gemm_tn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  TD3D_CUDA(launch_kernel(gemm_tn_tc_kernel, grid, TC_THREADS, smem, st, map_a, map_b, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

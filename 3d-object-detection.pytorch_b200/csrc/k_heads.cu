@@ -39,6 +39,7 @@ __device__ __forceinline__ float dropout_keep(const float* keep, uint64_t seed, 
 
 template <typename T>
 __global__ void __launch_bounds__(128) heads_fwd_kernel(HeadsArgs a, const T* __restrict__ feat) {
+  pdl_entry();
   extern __shared__ float s_f[];   // [C] features, [C] dropped features
   float* s_d = s_f + a.C;
   const int b = blockIdx.x;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(HeadsArgs a, const T* __
 // export mode: all heads, kp_all[k][b][o]
 template <typename T>
 __global__ void __launch_bounds__(128) heads_all_kernel(HeadsArgs a, const T* __restrict__ feat, float* kp_all) {
+  pdl_entry();
   extern __shared__ float s_f[];
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) s_f[c] = to_f(feat[(size_t)b * a.C + c]);
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(128) heads_all_kernel(HeadsArgs a, const T* __
 
 __global__ void select_argmax_kernel(const float* kp_all, const float* logits, float* kp_sel, int64_t* labels,
                                      int B, int P, int nc, int max_classes) {
+  pdl_entry();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int best = 0;
@@ -117,6 +120,7 @@ __global__ void select_argmax_kernel(const float* kp_all, const float* logits, f
 // g_pre[b,o] = d_kp[b,o]*kp*(1-kp);  g_feat[b,c] = W_reg[cat]^T g_pre + keep*(W_cls^T d_logits)
 template <typename T>
 __global__ void __launch_bounds__(128) heads_bwd_feat_kernel(HeadsBwdArgs a) {
+  pdl_entry();
   __shared__ float s_g[64];   // [P] g_pre, then [nc] d_logits
   const HeadsArgs& f = a.f;
   const int b = blockIdx.x;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(128) heads_bwd_feat_kernel(HeadsBwdArgs a) {
 static const int HW_WARPS = 8;
 template <typename T>
 __global__ void __launch_bounds__(32 * HW_WARPS) heads_bwd_wgrad_kernel(HeadsBwdArgs a, const T* __restrict__ feat) {
+  pdl_entry();
   __shared__ float s_red[HW_WARPS][33][32];     // [warp][output row; 32 = bias][lane]
   __shared__ int s_tot[HW_WARPS];
   const HeadsArgs& f = a.f;
@@ -205,23 +210,23 @@ __global__ void __launch_bounds__(32 * HW_WARPS) heads_bwd_wgrad_kernel(HeadsBwd
 int launch_heads_fwd(const HeadsArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(a.P + a.nc <= 64 && a.P <= 32 && a.nc <= 32, "heads: too many outputs (P=%d nc=%d)", a.P, a.nc);
   size_t smem = sizeof(float) * 2 * a.C;
-  if (dtype == TD3D_BF16) heads_fwd_kernel<bf16><<<a.B, 128, smem, st>>>(a, (const bf16*)a.feat);
-  else heads_fwd_kernel<float><<<a.B, 128, smem, st>>>(a, (const float*)a.feat);
+  if (dtype == TD3D_BF16) TD3D_CUDA(launch_kernel(heads_fwd_kernel<bf16>, a.B, 128, smem, st, a, (const bf16*)a.feat));
+  else TD3D_CUDA(launch_kernel(heads_fwd_kernel<float>, a.B, 128, smem, st, a, (const float*)a.feat));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
 int launch_heads_all(const HeadsArgs& a, float* kp_all, int dtype, cudaStream_t st) {
   size_t smem = sizeof(float) * a.C;
-  if (dtype == TD3D_BF16) heads_all_kernel<bf16><<<a.B, 128, smem, st>>>(a, (const bf16*)a.feat, kp_all);
-  else heads_all_kernel<float><<<a.B, 128, smem, st>>>(a, (const float*)a.feat, kp_all);
+  if (dtype == TD3D_BF16) TD3D_CUDA(launch_kernel(heads_all_kernel<bf16>, a.B, 128, smem, st, a, (const bf16*)a.feat, kp_all));
+  else TD3D_CUDA(launch_kernel(heads_all_kernel<float>, a.B, 128, smem, st, a, (const float*)a.feat, kp_all));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
 int launch_select_argmax(const float* kp_all, const float* logits, float* kp_sel, int64_t* labels, int B, int P,
                          int nc, int max_classes, cudaStream_t st) {
-  select_argmax_kernel<<<ceil_div(B, 128), 128, 0, st>>>(kp_all, logits, kp_sel, labels, B, P, nc, max_classes);
+  TD3D_CUDA(launch_kernel(select_argmax_kernel, ceil_div(B, 128), 128, 0, st, kp_all, logits, kp_sel, labels, B, P, nc, max_classes));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -231,13 +236,13 @@ int launch_heads_bwd(const HeadsBwdArgs& a, int dtype, cudaStream_t st) {
   TD3D_REQUIRE(f.P + f.nc <= 64 && f.P <= 32 && f.nc <= 32, "heads bwd: too many outputs");
   dim3 grid(ceil_div(f.C, 32), f.max_classes + 1);
   if (dtype == TD3D_BF16) {
-    heads_bwd_feat_kernel<bf16><<<f.B, 128, 0, st>>>(a);
+    TD3D_CUDA(launch_kernel(heads_bwd_feat_kernel<bf16>, f.B, 128, 0, st, a));
     TD3D_LAUNCH_CHECK();
-    heads_bwd_wgrad_kernel<bf16><<<grid, 32 * HW_WARPS, 0, st>>>(a, (const bf16*)f.feat);
+    TD3D_CUDA(launch_kernel(heads_bwd_wgrad_kernel<bf16>, grid, 32 * HW_WARPS, 0, st, a, (const bf16*)f.feat));
   } else {
-    heads_bwd_feat_kernel<float><<<f.B, 128, 0, st>>>(a);
+    TD3D_CUDA(launch_kernel(heads_bwd_feat_kernel<float>, f.B, 128, 0, st, a));
     TD3D_LAUNCH_CHECK();
-    heads_bwd_wgrad_kernel<float><<<grid, 32 * HW_WARPS, 0, st>>>(a, (const float*)f.feat);
+    TD3D_CUDA(launch_kernel(heads_bwd_wgrad_kernel<float>, grid, 32 * HW_WARPS, 0, st, a, (const float*)f.feat));
   }
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 loss_kernel(td3d_loss_desc d, const float* __restrict__ kp, const float* __restrict__ gt,
             const float* __restrict__ logits, const int64_t* __restrict__ cats, int B, int nc,
             float* __restrict__ loss_out, float* __restrict__ d_kp, float* __restrict__ d_logits) {
+  pdl_entry();
   __shared__ double s_part[32][7];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const float inv_elems = 1.f / ((float)B * NPT), inv_b = 1.f / (float)B;
@@ -131,7 +132,7 @@ int launch_loss(const td3d_loss_desc& d, const float* kp, const float* gt, const
                 int B, int nc, float* loss_out, float* d_kp, float* d_logits, cudaStream_t st) {
   TD3D_REQUIRE(B > 0 && nc >= 1 && nc <= 32, "loss: bad shape B=%d nc=%d", B, nc);
   TD3D_REQUIRE(d.w_ce == 0.f || (logits && cats), "loss: cross entropy needs logits and cats");
-  loss_kernel<<<1, LOSS_THREADS, 0, st>>>(d, kp, gt, logits, cats, B, nc, loss_out, d_kp, d_logits);
+  TD3D_CUDA(launch_kernel(loss_kernel, 1, LOSS_THREADS, 0, st, d, kp, gt, logits, cats, B, nc, loss_out, d_kp, d_logits));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -140,6 +141,7 @@ int launch_loss(const td3d_loss_desc& d, const float* kp, const float* gt, const
 __global__ void __launch_bounds__(256)
 metrics_kernel(const float* __restrict__ kp, const float* __restrict__ gt, const float* __restrict__ logits,
                const int64_t* __restrict__ cats, int B, int nc, int max_classes, double* __restrict__ acc) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -183,7 +185,7 @@ metrics_kernel(const float* __restrict__ kp, const float* __restrict__ gt, const
 int launch_metrics(const float* kp, const float* gt, const float* logits, const int64_t* cats, int B, int nc,
                    int max_classes, double* acc, cudaStream_t st) {
   TD3D_REQUIRE(B > 0, "metrics: empty batch");
-  metrics_kernel<<<ceil_div(B, 8), 256, 0, st>>>(kp, gt, logits, cats, B, nc, max_classes, acc);
+  TD3D_CUDA(launch_kernel(metrics_kernel, ceil_div(B, 8), 256, 0, st, kp, gt, logits, cats, B, nc, max_classes, acc));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -9,12 +9,14 @@
 namespace td3d {
 
 __global__ void optim_prepare_kernel(int32_t* steps, const int32_t* present, int n_heads) {
+  pdl_entry();
   int k = threadIdx.x;
   if (k > n_heads) return;
   if (k == 0 || !present || present[k - 1]) steps[k] += 1;
 }
 
 __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
+  pdl_entry();
   __shared__ float s_bc1[33], s_bc2s[33];
   __shared__ int s_step[33];
   if ((int)threadIdx.x <= a.n_heads) {
@@ -74,28 +76,31 @@ __global__ void __launch_bounds__(256) optim_kernel(OptimArgs a) {
 
 int launch_optim(const OptimArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(a.n_heads <= 32, "optim: too many heads");
-  optim_prepare_kernel<<<1, 64, 0, st>>>(a.steps, a.present, a.n_heads);
+  TD3D_CUDA(launch_kernel(optim_prepare_kernel, 1, 64, 0, st, a.steps, a.present, a.n_heads));
   TD3D_LAUNCH_CHECK();
   int blocks = (int)((a.n + 256 * 4 - 1) / (256 * 4));
   if (blocks > 148 * 16) blocks = 148 * 16;
-  optim_kernel<<<blocks, 256, 0, st>>>(a);
+  TD3D_CUDA(launch_kernel(optim_kernel, blocks, 256, 0, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = from_f<T>(src[i]);
 }
 template <typename T>
 __global__ void cast_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = to_f(src[i]);
 }
 // dst[c*rows + r] = src[r*cols + c]
 template <typename T>
 __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols) {
+  pdl_entry();
   __shared__ float tile[32][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -112,6 +117,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, T* __restri
 
 // ---- table-driven weight packing: ONE launch refreshes every compute-layout copy ------------------
 __global__ void __launch_bounds__(256) pack_table_kernel(const __grid_constant__ PackTable t) {
+  pdl_entry();
   const PackSeg sg = t.seg[blockIdx.y];
   const int64_t n = (int64_t)sg.rows * sg.cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const __grid_constant__
   }
 }
 __global__ void __launch_bounds__(128) bn_fold_table_kernel(const __grid_constant__ BnFoldTable t, float eps) {
+  pdl_entry();
   const BnFoldSeg sg = t.seg[blockIdx.y];
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < sg.C; c += gridDim.x * blockDim.x) {
     float invstd = 1.f / sqrtf(sg.rv[c] + eps);
@@ -137,13 +144,13 @@ __global__ void __launch_bounds__(128) bn_fold_table_kernel(const __grid_constan
 }
 int launch_pack_table(const PackTable& t, cudaStream_t st) {
   if (t.n <= 0) return TD3D_OK;
-  pack_table_kernel<<<dim3(148, t.n), 256, 0, st>>>(t);   // the two 1.2 M-element classifier segments set the duration
+  TD3D_CUDA(launch_kernel(pack_table_kernel, dim3(148, t.n), 256, 0, st, t));   // the two 1.2 M-element classifier segments set the duration
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 int launch_bn_fold_table(const BnFoldTable& t, float eps, cudaStream_t st) {
   if (t.n <= 0) return TD3D_OK;
-  bn_fold_table_kernel<<<dim3(2, t.n), 128, 0, st>>>(t, eps);
+  TD3D_CUDA(launch_kernel(bn_fold_table_kernel, dim3(2, t.n), 128, 0, st, t, eps));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -152,8 +159,8 @@ int launch_cast(const float* src, void* dst, int64_t n, int dtype, cudaStream_t 
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  if (dtype == TD3D_BF16) cast_kernel<bf16><<<blocks, 256, 0, st>>>(src, (bf16*)dst, n);
-  else cast_kernel<float><<<blocks, 256, 0, st>>>(src, (float*)dst, n);
+  if (dtype == TD3D_BF16) TD3D_CUDA(launch_kernel(cast_kernel<bf16>, blocks, 256, 0, st, src, (bf16*)dst, n));
+  else TD3D_CUDA(launch_kernel(cast_kernel<float>, blocks, 256, 0, st, src, (float*)dst, n));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -161,15 +168,15 @@ int launch_cast_f32(const void* src, float* dst, int64_t n, int dtype, cudaStrea
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  if (dtype == TD3D_BF16) cast_f32_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)src, dst, n);
-  else cast_f32_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, dst, n);
+  if (dtype == TD3D_BF16) TD3D_CUDA(launch_kernel(cast_f32_kernel<bf16>, blocks, 256, 0, st, (const bf16*)src, dst, n));
+  else TD3D_CUDA(launch_kernel(cast_f32_kernel<float>, blocks, 256, 0, st, (const float*)src, dst, n));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 int launch_transpose_cast(const float* src, void* dst, int rows, int cols, int dtype, cudaStream_t st) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
-  if (dtype == TD3D_BF16) transpose_cast_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, rows, cols);
-  else transpose_cast_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, rows, cols);
+  if (dtype == TD3D_BF16) TD3D_CUDA(launch_kernel(transpose_cast_kernel<bf16>, grid, block, 0, st, src, (bf16*)dst, rows, cols));
+  else TD3D_CUDA(launch_kernel(transpose_cast_kernel<float>, grid, block, 0, st, src, (float*)dst, rows, cols));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -40,6 +40,7 @@ __device__ __forceinline__ void roi_axis(int d, int src, int dst, int& i0, int& 
 }
 
 __global__ void __launch_bounds__(256) roi_crop_resize_kernel(RoiArgs a) {
+  pdl_entry();
   const int n = blockIdx.z;
   const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
   if (dx >= a.ow) return;
@@ -82,7 +83,7 @@ int launch_roi_crop_resize(const uint8_t* frames, int n_frames, int fh, int fw, 
   for (int c = 0; c < 3; ++c) { a.mean[c] = mean255[c]; a.inv[c] = inv_std255[c]; }
   a.swap_rb = swap_rb; a.out = out;
   const int threads = ow >= 256 ? 256 : ((ow + 31) / 32) * 32;
-  roi_crop_resize_kernel<<<dim3(ceil_div(ow, threads), oh, n_boxes), threads, 0, st>>>(a);
+  TD3D_CUDA(launch_kernel(roi_crop_resize_kernel, dim3(ceil_div(ow, threads), oh, n_boxes), threads, 0, st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ float se_transpose_sum32(float v[32]) {
 
 template <int AMODE, int EMODE>
 __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(SeFc p) {
+  pdl_entry();
   extern __shared__ __align__(16) float se_sa[];     // [SE_SB][K]
   const int b0 = blockIdx.x * SE_SB, n0 = blockIdx.y * SE_NB;
   const int K = p.K;
@@ -150,7 +151,7 @@ static int se_fc_launch(const SeFc& p, cudaStream_t st) {
     configured = 160 * 1024;
   }
   dim3 grid(ceil_div(p.B, SE_SB), ceil_div(p.N, SE_NB));
-  se_fc_kernel<AMODE, EMODE><<<grid, SE_THREADS, smem, st>>>(p);
+  TD3D_CUDA(launch_kernel(se_fc_kernel<AMODE, EMODE>, grid, SE_THREADS, smem, st, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -175,6 +176,7 @@ struct SeTnPair { SeTn p[2]; int B; };
 static const int SE_TM = 64;
 
 __global__ void __launch_bounds__(SE_THREADS) se_wgrad_kernel(SeTnPair q) {
+  pdl_entry();
   __shared__ __align__(16) float sa[SE_TM][32];
   __shared__ __align__(16) float sb[SE_TM][32];
   const int which = (int)blockIdx.x < q.p[0].n_ctas ? 0 : 1;
@@ -249,7 +251,7 @@ int launch_se_bwd(const SeBwdArgs& a, cudaStream_t st) {
     q.p[i].tiles2 = ceil_div(q.p[i].N2, 32);
     q.p[i].n_ctas = ceil_div(q.p[i].N1, 32) * q.p[i].tiles2;
   }
-  se_wgrad_kernel<<<q.p[0].n_ctas + q.p[1].n_ctas, SE_THREADS, 0, st>>>(q);
+  TD3D_CUDA(launch_kernel(se_wgrad_kernel, q.p[0].n_ctas + q.p[1].n_ctas, SE_THREADS, 0, st, q));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

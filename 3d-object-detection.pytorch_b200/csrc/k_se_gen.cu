@@ -13,6 +13,7 @@ __device__ __forceinline__ float seg_sigmoid(float u) { return __fdividef(1.f, 1
 
 // grid = B, block = 256, smem = (C + Ch) floats
 __global__ void __launch_bounds__(256) se_gen_fwd_kernel(SeArgs a) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* z = sm;
   float* hs = sm + a.C;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) se_gen_fwd_kernel(SeArgs a) {
 
 // grid = B, block = 256, smem = (C + Ch) floats.  g_gate[b,c] = sum_HW g_out * x arrives as the second statistic.
 __global__ void __launch_bounds__(256) se_gen_bwd_kernel(SeBwdArgs a) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* gp = sm;
   float* ga = sm + a.C;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) se_gen_bwd_kernel(SeBwdArgs a) {
 // The first version looped one thread over the whole batch: 225-320 us per launch at batch 512 whatever the layer size
 // (a serial chain of L2 round trips); the batch is now split over up to 32 chunks that meet in fp32 atomics.
 __global__ void __launch_bounds__(256) se_gen_wgrad_kernel(SeBwdArgs a, int b_chunk) {
+  pdl_entry();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.C * a.Ch) return;
   const int h = idx / a.C, c = idx - h * a.C;
@@ -111,18 +114,18 @@ __global__ void __launch_bounds__(256) se_gen_wgrad_kernel(SeBwdArgs a, int b_ch
 
 int launch_se_gen_fwd(const SeArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(a.B > 0 && a.C > 0 && a.Ch > 0 && (a.C + a.Ch) * sizeof(float) <= 48 * 1024, "se_gen fwd: bad shape C=%d Ch=%d", a.C, a.Ch);
-  se_gen_fwd_kernel<<<a.B, 256, sizeof(float) * (a.C + a.Ch), st>>>(a);
+  TD3D_CUDA(launch_kernel(se_gen_fwd_kernel, a.B, 256, sizeof(float) * (a.C + a.Ch), st, a));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
 
 int launch_se_gen_bwd(const SeBwdArgs& a, cudaStream_t st) {
   TD3D_REQUIRE(a.B > 0 && a.C > 0 && a.Ch > 0 && a.w1 && a.w2t, "se_gen bwd: bad arguments");
-  se_gen_bwd_kernel<<<a.B, 256, sizeof(float) * (a.C + a.Ch), st>>>(a);
+  TD3D_CUDA(launch_kernel(se_gen_bwd_kernel, a.B, 256, sizeof(float) * (a.C + a.Ch), st, a));
   TD3D_LAUNCH_CHECK();
   const int chunks = a.B < 32 ? a.B : 32;
   const int b_chunk = ceil_div(a.B, chunks);
-  se_gen_wgrad_kernel<<<dim3(ceil_div((int64_t)a.C * a.Ch, 256), ceil_div(a.B, b_chunk)), 256, 0, st>>>(a, b_chunk);
+  TD3D_CUDA(launch_kernel(se_gen_wgrad_kernel, dim3(ceil_div((int64_t)a.C * a.Ch, 256), ceil_div(a.B, b_chunk)), 256, 0, st, a, b_chunk));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

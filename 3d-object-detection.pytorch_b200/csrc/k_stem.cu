@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(ST_TH * ST_TW)
 stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, T* __restrict__ y,
                 float* __restrict__ stats, int H, int W, int Ho, int Wo, int C, const float* __restrict__ out_bias,
                 int out_act) {
+  pdl_entry();
   __shared__ float s_in[3][ST_IH][ST_IW + 1];
   __shared__ float s_w[27 * ST_C];
   __shared__ float s_acc[2 * ST_C];
@@ -111,9 +112,9 @@ int launch_stem_fwd(const float* img, const float* w27xC, void* y, float* stats,
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   dim3 grid(ceil_div(Wo, ST_TW), ceil_div(Ho, ST_TH), B);
   if (dtype == TD3D_BF16)
-    stem_fwd_kernel<bf16><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (bf16*)y, stats, H, W, Ho, Wo, C, out_bias, out_act);
+    TD3D_CUDA(launch_kernel(stem_fwd_kernel<bf16>, grid, ST_TH * ST_TW, 0, st, img, w27xC, (bf16*)y, stats, H, W, Ho, Wo, C, out_bias, out_act));
   else
-    stem_fwd_kernel<float><<<grid, ST_TH * ST_TW, 0, st>>>(img, w27xC, (float*)y, stats, H, W, Ho, Wo, C, out_bias, out_act);
+    TD3D_CUDA(launch_kernel(stem_fwd_kernel<float>, grid, ST_TH * ST_TW, 0, st, img, w27xC, (float*)y, stats, H, W, Ho, Wo, C, out_bias, out_act));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
 stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ g, const T* __restrict__ y,
                   const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gamma,
                   float* __restrict__ dw, int B, int H, int W, int Ho, int Wo, int tiles_per_cta, int C) {
+  pdl_entry();
   __shared__ float s_in[3 * ST_IH * ST_IW];      // [ci][row][col], odd row stride
   __shared__ __align__(16) float s_gy[ST_TH * ST_TW][SW_GS];
   __shared__ float s_al[ST_C], s_be[ST_C], s_ga[ST_C];
@@ -285,9 +287,9 @@ int launch_stem_wgrad(const float* img, const void* g, const void* y, const floa
   int per = ceil_div(n_tiles, ctas);
   dim3 grid(ceil_div(n_tiles, per), ceil_div(C, ST_C));
   if (dtype == TD3D_BF16)
-    stem_wgrad_kernel<bf16><<<grid, SW_THREADS, 0, st>>>(img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C);
+    TD3D_CUDA(launch_kernel(stem_wgrad_kernel<bf16>, grid, SW_THREADS, 0, st, img, (const bf16*)g, (const bf16*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C));
   else
-    stem_wgrad_kernel<float><<<grid, SW_THREADS, 0, st>>>(img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C);
+    TD3D_CUDA(launch_kernel(stem_wgrad_kernel<float>, grid, SW_THREADS, 0, st, img, (const float*)g, (const float*)y, alpha, beta, gamma, dw, B, H, W, Ho, Wo, per, C));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

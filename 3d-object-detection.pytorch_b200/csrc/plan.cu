@@ -398,11 +398,13 @@ struct Ctx {
     if (!pl->prof.enabled) return;
     ProfRec r; r.kind = kind; r.bytes = bytes; r.tag = pl->prof.tag;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    pdl_break(st);                             // timed launches are plain launches
     cudaEventRecord(r.e0, st);
     pl->prof.recs.push_back(r);
   }
   void pe() const {
     if (!pl->prof.enabled) return;
+    pdl_break(st);
     cudaEventRecord(pl->prof.recs.back().e1, st);
   }
   double esz() const { return (double)pl->esz; }
@@ -419,6 +421,8 @@ static int side_fork(const Ctx& c, int which, Ctx* out) {
   *out = c;
   if (!side_on(c, which)) return TD3D_OK;
   td3d_plan* pl = c.pl;
+  pdl_break(c.st);                             // the launches on either side of an event record / wait are plain launches
+  pdl_break(pl->side[which]);
   TD3D_CUDA(cudaEventRecord(pl->ev_fork[which], c.st));
   TD3D_CUDA(cudaStreamWaitEvent(pl->side[which], pl->ev_fork[which], 0));
   out->st = pl->side[which];
@@ -426,12 +430,14 @@ static int side_fork(const Ctx& c, int which, Ctx* out) {
 }
 static int side_done(const Ctx& c, int which) {        // call after the side launches of one fork
   if (!side_on(c, which)) return TD3D_OK;
+  pdl_break(c.pl->side[which]);
   TD3D_CUDA(cudaEventRecord(c.pl->ev_join[which], c.pl->side[which]));
   c.pl->side_pending[which] = true;
   return TD3D_OK;
 }
 static int side_join(const Ctx& c, int which) {
   if (!c.pl->side_pending[which]) return TD3D_OK;
+  pdl_break(c.st);
   TD3D_CUDA(cudaStreamWaitEvent(c.st, c.pl->ev_join[which], 0));
   c.pl->side_pending[which] = false;
   return TD3D_OK;
@@ -552,6 +558,7 @@ static int forward_backbone(const Ctx& c, const float* img, int training, const 
   const td3d_net_desc& n = pl->net;
   const int B = pl->B, dt = pl->dtype;
   const int GS = B < 32 ? B : 32;      // statistic slots of the GEMM epilogues (tile m_tile lands in slot m_tile % GS)
+  pdl_break(c.st);
   TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->fstats_begin, 0, pl->fstats_end - pl->fstats_begin, c.st));
   const float *sc, *sh;
   pl->prof.tag = 0;
@@ -678,6 +685,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
       dw.x = cur;
     }
     float* sq = c.wsf(pl->bns[b.bn2].fstats);          // per-sample sums of the depthwise output: the SE squeeze
+    pdl_break(c.st);
     if (b.d.use_se) TD3D_CUDA(cudaMemsetAsync(sq, 0, sizeof(float) * 2 * (size_t)B * E, c.st));
     // dw-first layout is BN -> act -> SE (mobilenetv3.py:137-140), expanded layout BN -> SE -> act (:153-156)
     const bool act_in_dw = !b.d.use_se || b.se_post;
@@ -713,6 +721,7 @@ static int forward_infer(const Ctx& c, const float* img, const void** feat_out) 
     g.a = cur; g.w = c.pk(pl->pi_last); g.y = c.ws(pl->yc); g.bias = eshift(pl->bn_last); g.act = pl->stem_act;
     g.M = Ml; g.N = n.last_ch; g.K = Cl;
     TD3D_TRY(gemm_nt(c, g));
+    pdl_break(c.st);
     TD3D_CUDA(cudaMemsetAsync(c.wsf(pl->pool_stats), 0, sizeof(float) * 2 * (size_t)B * n.last_ch, c.st));
     TD3D_TRY(p_xform(c, c.ws(pl->yc), xf_make(nullptr, nullptr, nullptr, TD3D_ACT_NONE), nullptr, nullptr,
                      c.wsf(pl->pool_stats), B, HWl, n.last_ch, dt, c.st));
@@ -760,6 +769,7 @@ static int bn_backward(const Ctx& c, int idx, int HW, const float* se, const flo
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ gammac,
               const float* __restrict__ bstats, const float* __restrict__ fstats, float* __restrict__ out, int B, int C) {
+  pdl_entry();
   // sum_b (alpha[b,c]*g_u + beta[c]*y + gammac[b,c]) from the per-sample sums (HW = 1)
   __shared__ double s[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -778,6 +788,7 @@ colsum_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, c
 }
 
 __global__ void scale_kernel(const float* __restrict__ src, float s, float* __restrict__ dst, int n) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i] * s;
 }
@@ -797,8 +808,11 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
 
   if (in_range(0)) {
     pl->prof.tag = 1000 + nblk + 1;
+    pdl_break(c.st);
     TD3D_CUDA(cudaMemsetAsync(pl->G, 0, sizeof(float) * (size_t)pl->param_floats, c.st));
+    pdl_break(c.st);
     TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->bstats_begin, 0, pl->bstats_end - pl->bstats_begin, c.st));
+    pdl_break(c.st);
     TD3D_CUDA(cudaMemsetAsync(pl->WS + pl->zeros_c, 0, sizeof(float) * 16, c.st));
     // heads
     HeadsBwdArgs hb;
@@ -816,8 +830,8 @@ static int backward_impl(const Ctx& c, const float* d_kp, const float* d_logits,
     TD3D_TRY(p_actbwd(c, nullptr, c.wsf(pl->g_feat), 1.f, c.ws(pl->yfc), xfc, c.ws(pl->g_wide_a), c.wsf(bfc.bstats),
                                   B, 1, n.head_ch, dt, c.st));
     TD3D_TRY(bn_backward(c, pl->bn_fc, 1, nullptr, nullptr, nullptr));
-    colsum_kernel<<<ceil_div(n.head_ch, 32), 256, 0, c.st>>>(c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
-                                                              c.wsf(bfc.bstats), c.wsf(bfc.fstats), c.G(pl->b_fc), B, n.head_ch);
+    TD3D_CUDA(launch_kernel(colsum_kernel, ceil_div(n.head_ch, 32), 256, 0, c.st, c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
+                                                              c.wsf(bfc.bstats), c.wsf(bfc.fstats), c.G(pl->b_fc), B, n.head_ch));
     TD3D_LAUNCH_CHECK();
     TD3D_TRY(p_affine2(c, c.ws(pl->g_wide_a), c.ws(pl->yfc), c.wsf(pl->alpha), c.wsf(pl->beta), c.wsf(pl->gammac),
                             c.ws(pl->g_wide_a), B, 1, n.head_ch, dt, c.st));
@@ -1189,6 +1203,7 @@ int td3d_plan_profile_launch(td3d_plan* pl, int64_t index, int* kind, int* tag, 
 #define TD3D_BOUND(pl) TD3D_REQUIRE((pl) && (pl)->P && (pl)->WS, "plan is not bound (call td3d_plan_bind)")
 
 int td3d_pack_weights(td3d_plan* pl, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_BOUND(pl);
   Ctx c = {pl, (cudaStream_t)stream};
   return pack_impl(c, true);
@@ -1196,6 +1211,7 @@ int td3d_pack_weights(td3d_plan* pl, void* stream) {
 
 int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const float* dropout_keep, uint64_t seed,
                  int training, float* kp, float* logits, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_BOUND(pl);
   TD3D_REQUIRE(img && cats && kp && logits, "forward: null argument");
   Ctx c = {pl, (cudaStream_t)stream};
@@ -1204,7 +1220,9 @@ int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const flo
   else TD3D_TRY(forward_infer(c, img, &feat));
   HeadsArgs h = heads_args(c, feat, cats, dropout_keep, seed, training);
   TD3D_K(PK_HEADS, 4.0 * pl->B * pl->net.head_ch, launch_heads_fwd(h, pl->dtype, c.st));
+  pdl_break(c.st);
   TD3D_CUDA(cudaMemcpyAsync(kp, h.kp, sizeof(float) * pl->B * pl->net.num_points, cudaMemcpyDeviceToDevice, c.st));
+  pdl_break(c.st);
   TD3D_CUDA(cudaMemcpyAsync(logits, h.logits, sizeof(float) * pl->B * pl->net.num_classes, cudaMemcpyDeviceToDevice, c.st));
   pl->last_img = img; pl->last_cats = cats; pl->last_keep = dropout_keep; pl->last_seed = seed; pl->last_training = training;
   return TD3D_OK;
@@ -1212,6 +1230,7 @@ int td3d_forward(td3d_plan* pl, const float* img, const int64_t* cats, const flo
 
 int td3d_forward_export(td3d_plan* pl, const float* img, float* kp_all, float* logits, int select, float* kp_sel,
                         int64_t* labels, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_BOUND(pl);
   TD3D_REQUIRE(img && kp_all && logits, "forward_export: null argument");
   TD3D_REQUIRE(!select || (kp_sel && labels), "forward_export: select needs kp_sel and labels");
@@ -1232,6 +1251,7 @@ int td3d_backward_stages(const td3d_plan* pl) { return pl ? n_stages(pl) : 0; }
 
 int td3d_backward(td3d_plan* pl, const float* d_kp, const float* d_logits, int32_t* head_present, int stage_begin,
                   int stage_end, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_BOUND(pl);
   TD3D_REQUIRE(pl->G, "backward: no gradient arena bound");
   TD3D_REQUIRE(d_kp && d_logits && head_present, "backward: null argument");
@@ -1255,18 +1275,21 @@ int td3d_backward_ready_range(const td3d_plan* pl, int stage, int64_t* begin, in
 int td3d_loss_fwd_bwd(const td3d_loss_desc* desc, const float* kp, const float* gt_kp, const float* logits,
                       const int64_t* cats, int batch, int num_classes, float* loss_out, float* d_kp, float* d_logits,
                       void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_REQUIRE(desc && kp && gt_kp && loss_out, "loss: null argument");
   return launch_loss(*desc, kp, gt_kp, logits, cats, batch, num_classes, loss_out, d_kp, d_logits, (cudaStream_t)stream);
 }
 
 int td3d_metrics_accum(const float* kp, const float* gt_kp, const float* logits, const int64_t* cats, int batch,
                        int num_classes, int max_classes, double* acc, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_REQUIRE(kp && gt_kp && cats && acc, "metrics: null argument");
   return launch_metrics(kp, gt_kp, logits, cats, batch, num_classes, max_classes, acc, (cudaStream_t)stream);
 }
 
 int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, float* state1, int32_t* steps,
                     const int32_t* head_present, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   TD3D_BOUND(pl);
   TD3D_REQUIRE(desc && state0 && steps && pl->G, "optim_step: null argument");
   TD3D_REQUIRE(desc->kind >= TD3D_OPT_SGD && desc->kind <= TD3D_OPT_ADADELTA, "optim_step: unknown optimizer %d", desc->kind);
@@ -1290,6 +1313,7 @@ int td3d_optim_step(td3d_plan* pl, const td3d_optim_desc* desc, float* state0, f
 int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* boxes, int n_boxes,
                          int out_h, int out_w, const float* mean255, const float* inv_std255, int swap_rb, float* out,
                          void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_roi_crop_resize(frames, n_frames, frame_h, frame_w, boxes, n_boxes, out_h, out_w, mean255, inv_std255, swap_rb,
                                 out, (cudaStream_t)stream);
 }
@@ -1297,14 +1321,17 @@ int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int f
 // ---- per-kernel entry points ----------------------------------------------------------------
 int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W, int C, int dtype,
                     void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_stem_fwd(img, w27x16, y, stats, B, H, W, C, dtype, (cudaStream_t)stream);
 }
 int td3d_k_stem_wgrad(const float* img, const void* g, const void* y, const float* alpha, const float* beta,
                       const float* gamma, float* dw, int B, int H, int W, int C, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_stem_wgrad(img, g, y, alpha, beta, gamma, dw, B, H, W, C, dtype, (cudaStream_t)stream);
 }
 int td3d_k_dw_fwd(const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
                   void* y, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   DwArgs a;
   a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.y = y; a.stats = stats;
   a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride;
@@ -1313,6 +1340,7 @@ int td3d_k_dw_fwd(const void* x, const float* scale, const float* shift, const f
 int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const float* beta, const float* gamma,
                   const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
                   void* gx, float* dw, float* stats, int B, int H, int W, int C, int k, int stride, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   DwBwdArgs a;
   a.g = g; a.y_out = y_out; a.alpha = alpha; a.beta = beta; a.gamma = gamma;
   a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.gx = gx; a.stats = stats; a.dw = dw;
@@ -1322,6 +1350,7 @@ int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const fl
 int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, const float* se, int act, const float* w_taps,
                      const float* out_bias, int out_act, void* y, float* stats, int B, int H, int W, int C, int k, int stride,
                      int dtype, int impl, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   DwArgs a;
   a.x = x; a.xf = xf_make(scale, shift, se, act); a.w_taps = w_taps; a.y = y; a.stats = stats;
   a.B = B; a.H = H; a.W = W; a.C = C; a.k = k; a.stride = stride; a.out_bias = out_bias; a.out_act = out_act;
@@ -1336,6 +1365,7 @@ int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, cons
 }
 int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias, const void* ysaved,
                    float* stats, int stat_slots, int M, int N, int K, int dtype, int out_f32, int impl, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   GemmNT g = {};
   g.a = a; g.w = w; g.y = y; g.addend = addend; g.bias = bias; g.ysaved = ysaved; g.stats = stats; g.slots = stat_slots;
   g.M = M; g.N = N; g.K = K; g.out_f32 = out_f32;
@@ -1346,6 +1376,7 @@ int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, co
   return launch_gemm_nt_simt(g, dtype, (cudaStream_t)stream);
 }
 int td3d_k_gemm_tn(const void* a, const void* b, float* c, int M, int N1, int N2, int dtype, int impl, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   GemmTN g = {a, b, c, M, N1, N2};
   if (impl == TD3D_GEMM_TCGEN05) {
     TD3D_REQUIRE(dtype == TD3D_BF16, "tcgen05 GEMM is bf16 only");
@@ -1356,14 +1387,17 @@ int td3d_k_gemm_tn(const void* a, const void* b, float* c, int M, int N1, int N2
 int td3d_debug_tc_timeline(uint64_t* out, int n) { return tc_timeline_read((unsigned long long*)out, n); }
 int td3d_k_apply_xform(const void* y, const float* scale, const float* shift, const float* se, int act, const void* res,
                        void* out, float* pool_stats, int B, int HW, int C, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_apply_xform(y, xf_make(scale, shift, se, act), res, out, pool_stats, B, HW, C, dtype, (cudaStream_t)stream);
 }
 int td3d_k_affine2(const void* g, const void* y, const float* alpha, const float* beta, const float* gamma, void* out,
                    int B, int HW, int C, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_affine2(g, y, alpha, beta, gamma, out, B, HW, C, dtype, (cudaStream_t)stream);
 }
 int td3d_k_act_bwd_stats(const void* g, const void* y, const float* scale, const float* shift, const float* se, int act,
                          void* gu, float* stats, int B, int HW, int C, int dtype, void* stream) {
+  pdl_break_all();                           // other libraries' work may precede this call on the stream
   return launch_act_bwd_stats(g, nullptr, 1.f, y, xf_make(scale, shift, se, act), gu, stats, B, HW, C, dtype,
                               (cudaStream_t)stream, nullptr);
 }

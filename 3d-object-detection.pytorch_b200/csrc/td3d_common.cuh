@@ -43,6 +43,23 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL) for EAGER launches.  A step is a chain of ~360 dependent kernels, a third of them
+// tiny (BatchNorm finalize, SE FCs), and launched one by one it is launch-latency bound: 12.18 ms against 11.69 ms for the
+// CUDA-graph replay (MobileNetV3-large, B=256).  Every kernel of this library therefore starts with pdl_entry() -- wait for
+// the previous grid to complete and flush, then let the next grid be scheduled -- and every launch goes through
+// launch_kernel(), which sets the programmatic-stream-serialization attribute when the previous operation this library
+// enqueued on the stream was one of its own kernels.  The next grid's CTAs then become resident while the last wave of the
+// current one drains and block in griddepcontrol.wait until it has completed: launch latency and CTA scheduling leave the
+// critical path, ordering and memory visibility stay those of a plain stream.  Measured: eager 12.18 -> 11.70 ms, i.e. the
+// graph's speed without a graph (variable batch shapes, the first steps before capture).  Under stream capture the
+// attribute is NOT set: graph edges are already that cheap (11.65 vs 11.69 ms with programmatic edges, inference 1 % slower),
+// so captured graphs keep plain edges.  TD3D_PDL=0 disables it.
+// ---------------------------------------------------------------------------------------------
+bool pdl_take(cudaStream_t st);    // true: the launch may carry the attribute; either way `st` now ends in one of our kernels
+void pdl_break(cudaStream_t st);   // a non-kernel operation (memset, copy, event record / wait) was enqueued on `st`
+void pdl_break_all();              // C-ABI entry: other libraries' work may sit between two calls
+
+// ---------------------------------------------------------------------------------------------
 // lazily-applied producer transform:  u = se[b,c] * (scale[c]*y + shift[c]);  x = act(u)
 //   (BatchNorm fold + SE scale + activation; reference mobilenetv3.py:133-160)
 // ---------------------------------------------------------------------------------------------
@@ -56,6 +73,25 @@ struct XForm {
 };
 
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // no-op for a launch without the attribute
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... P, typename... A>
+inline cudaError_t launch_kernel(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  cfg.numAttrs = (cap == cudaStreamCaptureStatusNone && pdl_take(st)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
 
 __device__ __forceinline__ float act_fwd(float u, int act) {
   if (act == TD3D_ACT_RELU) return fmaxf(u, 0.f);
