@@ -102,6 +102,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ---- TMA store path of the epilogue (bulk async group per epilogue warp) ----
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
@@ -196,7 +207,12 @@ struct TcNtParams {
   float* stats; int slots;
   int act;              // epilogue activation after the bias (TD3D_ACT_*), before the addend
   int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
-  int n_acc, acc_stride; // TMEM accumulator stages and the column stride between them
+  int n_acc, acc_stride; // TMEM accumulator stages; columns of one 128-row accumulator (power of two >= block_n)
+  int m_sub;            // 128-row MMA blocks per tile (1 or 2).  The single-thread producer / issuer loops and the epilogue
+                        // hand-off cost ~0.8 us per tile whatever its size (timeline in profiles/r01_v3_gemm_bench_timeline.txt);
+                        // 256-row tiles (one TMA box, one barrier round trip, two tcgen05.mma per k step into adjacent
+                        // accumulators) halve that per row on the long-M layers
+  int stage_cols;       // TMEM columns of one accumulator stage = acc_stride * m_sub
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
   int tma_store;        // 1: bf16 output leaves through swizzled smem + cp.async.bulk.tensor (coalesced), else st.global
@@ -213,7 +229,17 @@ struct TcNtParams {
 // own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
 // EPI_ACT: the bias + activation epilogue of the inference path is a template parameter so that the training GEMMs carry
 // none of its registers (the epilogue warps sit at the 128-register limit: every extra live value spills).
-template <bool EPI_ACT>
+// STATS: how the BatchNorm statistic sums of the epilogue are formed (the epilogue warps sit at the 128-register limit and
+// bound every wide layer, so each flavour is its own instance):
+//   TC_ST_NONE  : no statistics (inference, data gradients without a BatchNorm behind them)
+//   TC_ST_CHUNK : per 32-column chunk, a 2 x 31-shuffle transpose-sum of the warp's 32 rows
+//   TC_ST_LOCAL : lane = row keeps its contributions in 64 registers over the row blocks of a 256-row tile and -- when the tile
+//                 is a single chunk (N <= 32: every tile shows a thread the same 32 columns) -- over ALL tiles of the CTA; the
+//                 transpose-sum runs once per 256 rows, or once per CTA.  The chunk is then read from TMEM in 16-column halves
+//                 (a 32-register load next to the 64 live sums spilled).  Measured (profiles/r02_gemm_bench3.txt): N=16: 118 ->
+//                 102 us, N=24: 46 -> 44 us; as the only flavour it cost the 128-row layers 7 %, hence the split.
+enum { TC_ST_NONE = 0, TC_ST_CHUNK = 1, TC_ST_LOCAL = 2 };
+template <bool EPI_ACT, int STATS>
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_y, TcNtParams p) {
@@ -265,14 +291,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         // single-thread loops: no runtime divisions on the common single-N-tile path (timeline: the MMA
         // issuer needs ~800 ns per 128-row tile of a K=16 layer, which caps such layers at ~1.4 TB/s)
-        const int m0 = (p.n_tiles == 1 ? tile : tile / p.n_tiles) * TC_BLOCK_M;
+        const int m0 = (p.n_tiles == 1 ? tile : tile / p.n_tiles) * TC_BLOCK_M * p.m_sub;
         const int n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
           TC_STAMP(0, ti);
           const uint32_t full = smem_u32(&s_full[stage]);
           const uint32_t a_dst = ring + stage * stage_bytes, b_dst = a_dst + p.a_stage_bytes;
-          mbar_expect_tx(full, (uint32_t)(p.w_resident ? TC_BLOCK_M * p.swizzle_bytes : p.tx_bytes));
+          mbar_expect_tx(full, (uint32_t)(p.w_resident ? p.a_stage_bytes : p.tx_bytes));
           tma_load_2d(a_dst, &map_a, full, kb * p.block_k, m0);
           if (!p.w_resident) tma_load_2d(b_dst, &map_w, full, kb * p.block_k, n0);
           TC_STAMP(1, ti);
@@ -304,7 +330,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         TC_STAMP(2, ti);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.stage_cols);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_full[stage]), phase);
           TC_STAMP(3, ti);
@@ -313,10 +339,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t b_src = p.w_resident ? wres + (uint32_t)((n_tile * k_blocks + kb) * p.b_stage_bytes) : a_src + p.a_stage_bytes;
           const int k_left = p.K - kb * p.block_k;
           const int k_steps = ((k_left < p.block_k ? k_left : p.block_k) + 15) >> 4;   // UMMA_K = 16 (bf16)
-          for (int ks = 0; ks < k_steps; ++ks) {
-            const uint64_t da = make_smem_desc(a_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
-            const uint64_t db = make_smem_desc(b_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
-            umma_bf16(d_tmem, da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+          for (int h = 0; h < p.m_sub; ++h) {                      // rows h * 128 ... of the tile -> accumulator h of the stage
+            const uint32_t a_h = a_src + (uint32_t)(h * TC_BLOCK_M * p.swizzle_bytes);
+            for (int ks = 0; ks < k_steps; ++ks) {
+              const uint64_t da = make_smem_desc(a_h + ks * 32, p.lbo_field_bytes, sbo, layout_type);
+              const uint64_t db = make_smem_desc(b_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
+              umma_bf16(d_tmem + (uint32_t)(h * p.acc_stride), da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&s_empty[stage]));                 // frees the smem slot when MMAs retire
           if (kb == k_blocks - 1) umma_commit(smem_u32(&s_tfull[as]));
@@ -341,6 +370,12 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
     uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
+    // lane = row, v[j] / w2[j] = this row's contribution to the two sums of column j of the current 32-column chunk
+    constexpr int NV = STATS == TC_ST_LOCAL ? 32 : 1;
+    float v[NV], w2[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = 0.f; w2[i] = 0.f; }
+    const bool persist = n_chunks == 1;
     // Accumulator hand-off safety (root cause of the round-1 "launch failure at batch >= 1024" and of the rare aborts of
     // stat-less GEMMs): tile ti uses barrier s_tfull[ti % n_acc]; a group that finished tile ti waits next for tile
     // ti + G on barrier (ti + G) % n_acc with a PARITY wait, which is only meaningful if the previous phase of that
@@ -351,14 +386,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int G = p.epi_groups;
     for (int ti = eg, tile = blockIdx.x + eg * gridDim.x; eg < G && tile < num_tiles; tile += G * gridDim.x, ti += G) {
       const int m_tile = p.n_tiles == 1 ? tile : tile / p.n_tiles;
-      const int m0 = m_tile * TC_BLOCK_M, n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
+      const int n0 = p.n_tiles == 1 ? 0 : (tile % p.n_tiles) * p.block_n;
       mbar_wait(smem_u32(&s_tfull[as]), aphase);
       if (q == 2 && lane == 0) TC_STAMP(5, ti);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        uint32_t r[32];
+      for (int hc = 0; hc < p.m_sub * n_chunks; ++hc) {
+        const int ch = p.m_sub == 2 ? hc >> 1 : hc, h = p.m_sub == 2 ? hc & 1 : 0;   // 32-column chunk, 128-row block of the tile
+        const int m0 = (m_tile * p.m_sub + h) * TC_BLOCK_M;
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
         // a full 32-column box may be stored by TMA (it clips at M and N); a chunk that would spill into the
         // next N tile keeps the masked st.global path
         const bool via_tma = p.tma_store && (p.n_tiles == 1 || ch * 32 + 32 <= p.block_n);
@@ -367,16 +403,20 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (lane == 0) bulk_wait_read_1();          // the store issued from this buffer two chunks ago has read it
           __syncwarp();
         }
-        if (!(p.dbg & 16)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.acc_stride + ch * 32), r);
         const int nb = n0 + ch * 32;
-        float v[32], w2[32];
+        constexpr int NR = STATS == TC_ST_LOCAL ? 16 : 32, NC = STATS == TC_ST_CHUNK ? 32 : 1;
+        uint32_t r[NR];
+        float vc[NC], wc[NC];
+        const uint32_t t_chunk = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.stage_cols + h * p.acc_stride + ch * 32);
+        if (STATS != TC_ST_LOCAL && !(p.dbg & 16)) tmem_ld32(t_chunk, *reinterpret_cast<uint32_t(*)[32]>(r));
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (STATS == TC_ST_LOCAL && (g & 1) == 0 && !(p.dbg & 16)) tmem_ld16(t_chunk + g * 8, *reinterpret_cast<uint32_t(*)[16]>(r));
           const int n = nb + g * 8;
           const bool ok = row_ok && n < p.N && (n - n0) < p.block_n;
           float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[g * 8 + i]);
+          for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[(STATS == TC_ST_LOCAL ? (g & 1) : g) * 8 + i]);
           if (ok) {
             if (p.bias) {
               float bb[8];
@@ -401,21 +441,31 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const uint4 pk = pack8_bf16(x);
               if (via_tma) sts_v4(ybuf + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4), pk);
               else if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.y + off) = pk;
-              x[0] = __uint_as_float(pk.x << 16); x[1] = __uint_as_float(pk.x & 0xffff0000u);
-              x[2] = __uint_as_float(pk.y << 16); x[3] = __uint_as_float(pk.y & 0xffff0000u);
-              x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
-              x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
+              if (STATS != TC_ST_NONE) {     // the statistics describe the stored (rounded) values
+                x[0] = __uint_as_float(pk.x << 16); x[1] = __uint_as_float(pk.x & 0xffff0000u);
+                x[2] = __uint_as_float(pk.y << 16); x[3] = __uint_as_float(pk.y & 0xffff0000u);
+                x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
+                x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
+              }
             }
-            float ys[8];
-            if (p.ysaved) load8(p.ysaved + off, ys);
+            if (STATS != TC_ST_NONE) {
+              float ys[8];
+              if (p.ysaved) load8(p.ysaved + off, ys);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[g * 8 + i] = x[i];
-              w2[g * 8 + i] = x[i] * (p.ysaved ? ys[i] : x[i]);
+              for (int i = 0; i < 8; ++i) {
+                const float other = p.ysaved ? ys[i] : x[i];
+                if (STATS == TC_ST_LOCAL) {
+                  v[(g * 8 + i) % NV] += x[i];
+                  w2[(g * 8 + i) % NV] = fmaf(x[i], other, w2[(g * 8 + i) % NV]);
+                } else {
+                  vc[(g * 8 + i) % NC] = x[i];
+                  wc[(g * 8 + i) % NC] = x[i] * other;
+                }
+              }
             }
-          } else {
+          } else if (STATS == TC_ST_CHUNK) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[g * 8 + i] = 0.f; w2[g * 8 + i] = 0.f; }
+            for (int i = 0; i < 8; ++i) { vc[(g * 8 + i) % NC] = 0.f; wc[(g * 8 + i) % NC] = 0.f; }
           }
         }
         if (via_tma) {
@@ -427,13 +477,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           ysel ^= 1u;
         }
-        if (p.stats && !(p.dbg & 2)) {
-          // column sums of this warp's 32 rows, accumulated over ALL tiles of the CTA in the warp's own shared-memory
-          // row (every tile of a CTA covers the same N tile, see the launcher): no barrier, no atomics per tile
-          const float t1 = warp_transpose_sum32_tc(v);
-          const float t2 = warp_transpose_sum32_tc(w2);
+        // column sums of this warp's rows, accumulated over ALL tiles of the CTA in the warp's own shared-memory
+        // row (every tile of a CTA covers the same N tile, see the launcher): no barrier, no atomics per tile
+        if (STATS == TC_ST_CHUNK && !(p.dbg & 2)) {
+          const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(vc));
+          const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(wc));
           gstat[q][0][ch * 32 + lane] += t1;
           gstat[q][1][ch * 32 + lane] += t2;
+        }
+        if (STATS == TC_ST_LOCAL && !persist && h == p.m_sub - 1 && !(p.dbg & 2)) {
+          const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(v));
+          const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(w2));
+          gstat[q][0][ch * 32 + lane] += t1;
+          gstat[q][1][ch * 32 + lane] += t2;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) { v[i] = 0.f; w2[i] = 0.f; }
         }
       }
       tc_fence_before();
@@ -444,9 +502,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
     if (p.tma_store && lane == 0) bulk_wait_all();
+    if (STATS == TC_ST_LOCAL && persist && eg < G && !(p.dbg & 2)) {
+      const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(v));
+      const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(w2));
+      gstat[q][0][lane] += t1;
+      gstat[q][1][lane] += t2;
+    }
     // one flush per CTA and epilogue group: the four lane-quarter rows are added and leave as one atomic per column.
     // The slot only spreads the atomics of the CTAs (the finalize kernels add all slots).
-    if (p.stats && eg < G && (int)blockIdx.x + eg * (int)gridDim.x < num_tiles) {
+    if (STATS != TC_ST_NONE && eg < G && (int)blockIdx.x + eg * (int)gridDim.x < num_tiles) {
       asm volatile("bar.sync %0, 128;" ::"r"(eg + 1) : "memory");
       const int n0 = p.n_tiles == 1 ? 0 : ((int)blockIdx.x % p.n_tiles) * p.block_n;
       const int slot = ((int)blockIdx.x / p.n_tiles) % p.slots;
@@ -622,7 +686,7 @@ static int env_raw(const char* name, int dflt) {
 }
 // Tuning / debugging knobs of the NT GEMM.  Read ONCE (getenv on every eager launch showed up in host profiles);
 // TD3D_TC_LIVE_ENV=1 (micro-benchmarks that flip knobs inside one process) re-reads them on every launch.
-struct TcKnobs { int force_sw128, no_wres, tma_store, lbo, dbg, two_issuers, max_bn, tn_swap; };
+struct TcKnobs { int force_sw128, no_wres, tma_store, lbo, dbg, two_issuers, max_bn, tn_swap, m_sub; };
 static TcKnobs read_knobs() {
   TcKnobs k;
   k.force_sw128 = env_raw("TD3D_TC_FORCE_SW128", 0);
@@ -631,6 +695,8 @@ static TcKnobs read_knobs() {
   k.lbo = env_raw("TD3D_TC_LBO", 16);
   k.dbg = env_raw("TD3D_TC_DBG", 0);
   k.two_issuers = env_raw("TD3D_TC_TWO_ISSUERS", 0);
+  k.m_sub = env_raw("TD3D_TC_MSUB", 0);            // 0 auto, 1 / 2 force (A/B measurements)
+  if (k.m_sub < 0 || k.m_sub > 2) k.m_sub = 0;
   k.max_bn = env_raw("TD3D_TC_MAXBN", 0);        // 0 = rule in launch_gemm_nt_tc
   k.tn_swap = env_raw("TD3D_TC_TN_SWAP", 0);
   return k;
@@ -684,10 +750,17 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   int bn = ceil_div(ceil_div(g.N, n_tiles), 16) * 16;
   p.block_n = bn;
   p.n_tiles = ceil_div(g.N, bn);
-  p.m_tiles = ceil_div(g.M, TC_BLOCK_M);
-  p.a_stage_bytes = TC_BLOCK_M * sw;
+  // 256-row tiles where every CTA still gets several of them.  Measured (scripts/gemm_bench3.py, profiles/r02_gemm_bench3.txt,
+  // M = 0.2 .. 3.2 M rows): they win for N <= 40 with or without statistics (N=16: 136 -> 86 us, N=24: 46 -> 36 us) and for
+  // N = 64 with statistics (297 -> 272 us: the transpose-sum runs once per 256 rows); they lose for N = 64 without statistics
+  // (151 -> 193 us) and for every N > 64 (two accumulators of 128 columns leave 2 TMEM stages, hence 2 epilogue groups).
+  const bool long_m = (int64_t)ceil_div(g.M, 2 * TC_BLOCK_M) * p.n_tiles >= 3 * (int64_t)num_sms();
+  p.m_sub = kn.m_sub ? kn.m_sub : ((long_m && (bn <= 48 || (bn <= 64 && g.stats))) ? 2 : 1);
+  if (bn > 128) p.m_sub = 1;
+  p.m_tiles = ceil_div(g.M, TC_BLOCK_M * p.m_sub);
+  p.a_stage_bytes = TC_BLOCK_M * p.m_sub * sw;
   p.b_stage_bytes = ceil_div(bn * sw, 1024) * 1024;
-  p.tx_bytes = TC_BLOCK_M * sw + bn * sw;
+  p.tx_bytes = p.a_stage_bytes + bn * sw;
   const int k_blocks = ceil_div(g.K, p.block_k);
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
   p.w_resident = (wres_bytes <= 96 * 1024 && !kn.no_wres) ? 1 : 0;
@@ -707,7 +780,8 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.dbg = kn.dbg;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
-  p.n_acc = TC_TMEM_COLS / p.acc_stride;
+  p.stage_cols = p.acc_stride * p.m_sub;
+  p.n_acc = TC_TMEM_COLS / p.stage_cols;
   if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
   p.epi_groups = p.n_acc < TC_EPI_GROUPS ? p.n_acc : TC_EPI_GROUPS;
   // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
@@ -718,15 +792,17 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
   p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   CUtensorMap map_a, map_w, map_y;
-  TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M, p.block_k, sw));
+  TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M * p.m_sub, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
   if (p.tma_store) TD3D_TRY(make_map_2d(&map_y, g.y, g.M, g.N, 32, 32, 64));
   else map_y = map_a;
   size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + ystage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     attr_set = true;
   }
   int grid = p.m_tiles * p.n_tiles;
@@ -734,8 +810,12 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // tile t covers N tile t % n_tiles and CTA c takes tiles c, c + grid, ...: with grid a multiple of n_tiles every tile of
   // a CTA lies in the same N tile, which lets the statistics epilogue keep one accumulator row per CTA (flushed once)
   grid -= grid % p.n_tiles;
-  if (p.act != TD3D_ACT_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<true>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  TD3D_REQUIRE(p.act == TD3D_ACT_NONE || !p.stats, "gemm_nt_tc: the activation epilogue (inference) has no statistics flavour");
+  const bool lane_local = p.m_sub == 2 || bn <= 32;
+  if (p.act != TD3D_ACT_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<true, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else if (!p.stats) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else if (lane_local) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_CHUNK>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

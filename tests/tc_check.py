@@ -20,7 +20,10 @@ def rel_err(a, b):
 
 NT = [(128, 64, 64), (300, 64, 16), (1000, 24, 72), (257, 88, 24), (129, 960, 160), (64, 1280, 960), (50000, 16, 64),
       (130, 200, 80), (128, 184, 80), (77, 40, 120), (20000, 72, 24), (4096, 240, 40), (3000, 576, 96), (100, 16, 16),
-      (100, 32, 32), (640, 120, 40)]
+      (100, 32, 32), (640, 120, 40),
+      # long-M layers with N <= 64 run 256-row tiles (two MMA row blocks per tile): ragged last tile whose second row block is
+      # partly / entirely beyond M, one and several k blocks
+      (120001, 16, 16), (115000, 64, 16), (130050, 24, 64), (114177, 40, 120), (113600, 64, 200)]
 TN = [(256, 64, 64), (1000, 64, 16), (5000, 24, 72), (257, 88, 24), (4097, 960, 160), (64, 1280, 960), (50000, 16, 64),
       (130, 200, 80), (20000, 72, 24), (3000, 96, 576), (640, 40, 120)]
 
