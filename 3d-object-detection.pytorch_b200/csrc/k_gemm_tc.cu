@@ -229,16 +229,21 @@ struct TcNtParams {
 // own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
 // EPI_ACT: the bias + activation epilogue of the inference path is a template parameter so that the training GEMMs carry
 // none of its registers (the epilogue warps sit at the 128-register limit: every extra live value spills).
-// STATS: how the BatchNorm statistic sums of the epilogue are formed (the epilogue warps sit at the 128-register limit and
-// bound every wide layer, so each flavour is its own instance):
-//   TC_ST_NONE  : no statistics (inference, data gradients without a BatchNorm behind them)
-//   TC_ST_CHUNK : per 32-column chunk, a 2 x 31-shuffle transpose-sum of the warp's 32 rows
-//   TC_ST_LOCAL : lane = row keeps its contributions in 64 registers over the row blocks of a 256-row tile and -- when the tile
-//                 is a single chunk (N <= 32: every tile shows a thread the same 32 columns) -- over ALL tiles of the CTA; the
-//                 transpose-sum runs once per 256 rows, or once per CTA.  The chunk is then read from TMEM in 16-column halves
-//                 (a 32-register load next to the 64 live sums spilled).  Measured (profiles/r02_gemm_bench3.txt): N=16: 118 ->
-//                 102 us, N=24: 46 -> 44 us; as the only flavour it cost the 128-row layers 7 %, hence the split.
-enum { TC_ST_NONE = 0, TC_ST_CHUNK = 1, TC_ST_LOCAL = 2 };
+// STATS: how the BatchNorm statistic sums of the epilogue are formed.  The epilogue warps bound every wide layer (the
+// shuffle transpose-sum of round 1 -- 62 shuffles + 124 selects + 62 adds per 32 x 32 chunk -- doubled the kernel time:
+// N=64, K=16: 151 us without statistics, 297 us with), so each flavour is its own instance:
+//   TC_ST_NONE  : no statistics (inference, data gradients without a BatchNorm behind them): 94-108 registers, no spill
+//   TC_ST_LOCAL : N <= 32 -- every tile shows a thread (lane = row) the same 32 columns, so it keeps its contributions in 64
+//                 registers over ALL tiles of the CTA and the transpose-sum runs once per CTA (N=16: 158 -> 100 us together
+//                 with the 256-row tiles).  The chunk is read from TMEM in 16-column halves (a 32-register load next to the
+//                 64 live sums spilled).
+//   TC_ST_SMEM  : per chunk, the warp writes its packed bf16 rows (and the saved-y rows of the data-gradient flavour) into a
+//                 private shared-memory tile, then lane j adds up column j: 4-8 STS.128 + 32-64 LDS.U16 + 64 FADD / FFMA
+//                 (N=64, K=16: 297 -> 217 us; 72 x 24: 102 -> 75; 240 x 40: 84 -> 61; profiles/r02_gemm_bench3.txt)
+// The statistics always describe the stored bf16 values; an fp32 output has no statistics flavour.
+enum { TC_ST_NONE = 0, TC_ST_LOCAL = 2, TC_ST_SMEM = 3 };
+static const int TC_RED_ROW = 80;                 // bytes per row of the reduction tile: 64 B of bf16 + 16 B pad (conflict-free STS.128 / LDS.U16)
+static const int TC_RED_WARP = 2 * 32 * TC_RED_ROW;   // per epilogue warp: one tile for y, one for the saved y
 template <bool EPI_ACT, int STATS>
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -367,6 +372,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float (*gstat)[2][256] = s_stat[eg];
     const ActK eak = make_actk(EPI_ACT ? p.act : TD3D_ACT_NONE);
     const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
+    // TC_ST_SMEM: this warp's reduction tiles (after the TMA-store staging area)
+    const uint32_t red_y = ystage + (p.tma_store ? (uint32_t)(TC_EPI_GROUPS * 4 * 2 * 2048) : 0u) + (uint32_t)((eg * 4 + q) * TC_RED_WARP);
+    const uint32_t red_s = red_y + 32u * TC_RED_ROW;
     uint32_t ysel = 0;
     int as = eg % p.n_acc;
     uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
@@ -375,7 +383,6 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float v[NV], w2[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) { v[i] = 0.f; w2[i] = 0.f; }
-    const bool persist = n_chunks == 1;
     // Accumulator hand-off safety (root cause of the round-1 "launch failure at batch >= 1024" and of the rare aborts of
     // stat-less GEMMs): tile ti uses barrier s_tfull[ti % n_acc]; a group that finished tile ti waits next for tile
     // ti + G on barrier (ti + G) % n_acc with a PARITY wait, which is only meaningful if the previous phase of that
@@ -404,9 +411,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           __syncwarp();
         }
         const int nb = n0 + ch * 32;
-        constexpr int NR = STATS == TC_ST_LOCAL ? 16 : 32, NC = STATS == TC_ST_CHUNK ? 32 : 1;
+        constexpr int NR = STATS == TC_ST_LOCAL ? 16 : 32;
         uint32_t r[NR];
-        float vc[NC], wc[NC];
         const uint32_t t_chunk = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.stage_cols + h * p.acc_stride + ch * 32);
         if (STATS != TC_ST_LOCAL && !(p.dbg & 16)) tmem_ld32(t_chunk, *reinterpret_cast<uint32_t(*)[32]>(r));
 #pragma unroll
@@ -441,31 +447,29 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const uint4 pk = pack8_bf16(x);
               if (via_tma) sts_v4(ybuf + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4), pk);
               else if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.y + off) = pk;
-              if (STATS != TC_ST_NONE) {     // the statistics describe the stored (rounded) values
+              if (STATS == TC_ST_SMEM) {
+                sts_v4(red_y + (uint32_t)(lane * TC_RED_ROW + g * 16), pk);
+                if (p.ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), __ldg(reinterpret_cast<const uint4*>(p.ysaved + off)));
+              }
+              if (STATS == TC_ST_LOCAL) {     // the statistics describe the stored (rounded) values
                 x[0] = __uint_as_float(pk.x << 16); x[1] = __uint_as_float(pk.x & 0xffff0000u);
                 x[2] = __uint_as_float(pk.y << 16); x[3] = __uint_as_float(pk.y & 0xffff0000u);
                 x[4] = __uint_as_float(pk.z << 16); x[5] = __uint_as_float(pk.z & 0xffff0000u);
                 x[6] = __uint_as_float(pk.w << 16); x[7] = __uint_as_float(pk.w & 0xffff0000u);
               }
             }
-            if (STATS != TC_ST_NONE) {
+            if (STATS == TC_ST_LOCAL) {
               float ys[8];
               if (p.ysaved) load8(p.ysaved + off, ys);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float other = p.ysaved ? ys[i] : x[i];
-                if (STATS == TC_ST_LOCAL) {
-                  v[(g * 8 + i) % NV] += x[i];
-                  w2[(g * 8 + i) % NV] = fmaf(x[i], other, w2[(g * 8 + i) % NV]);
-                } else {
-                  vc[(g * 8 + i) % NC] = x[i];
-                  wc[(g * 8 + i) % NC] = x[i] * other;
-                }
+                v[(g * 8 + i) % NV] += x[i];
+                w2[(g * 8 + i) % NV] = fmaf(x[i], p.ysaved ? ys[i] : x[i], w2[(g * 8 + i) % NV]);
               }
             }
-          } else if (STATS == TC_ST_CHUNK) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { vc[(g * 8 + i) % NC] = 0.f; wc[(g * 8 + i) % NC] = 0.f; }
+          } else if (STATS == TC_ST_SMEM) {
+            sts_v4(red_y + (uint32_t)(lane * TC_RED_ROW + g * 16), make_uint4(0u, 0u, 0u, 0u));      // rows / columns outside the matrix add nothing
+            if (p.ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), make_uint4(0u, 0u, 0u, 0u));
           }
         }
         if (via_tma) {
@@ -479,19 +483,33 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         // column sums of this warp's rows, accumulated over ALL tiles of the CTA in the warp's own shared-memory
         // row (every tile of a CTA covers the same N tile, see the launcher): no barrier, no atomics per tile
-        if (STATS == TC_ST_CHUNK && !(p.dbg & 2)) {
-          const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(vc));
-          const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(wc));
-          gstat[q][0][ch * 32 + lane] += t1;
-          gstat[q][1][ch * 32 + lane] += t2;
-        }
-        if (STATS == TC_ST_LOCAL && !persist && h == p.m_sub - 1 && !(p.dbg & 2)) {
-          const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(v));
-          const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(w2));
-          gstat[q][0][ch * 32 + lane] += t1;
-          gstat[q][1][ch * 32 + lane] += t2;
+        if (STATS == TC_ST_SMEM && !(p.dbg & 2)) {
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+          const uint32_t cy = red_y + (uint32_t)(lane * 2), cs = red_s + (uint32_t)(lane * 2);
+          if (p.ysaved) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i) { v[i] = 0.f; w2[i] = 0.f; }
+            for (int i = 0; i < 32; ++i) {
+              uint32_t a, b;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(cy + (uint32_t)(i * TC_RED_ROW)));
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(b) : "r"(cs + (uint32_t)(i * TC_RED_ROW)));
+              const float fa = __uint_as_float(a << 16);
+              s1 += fa;
+              s2 = fmaf(fa, __uint_as_float(b << 16), s2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              uint32_t a;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(cy + (uint32_t)(i * TC_RED_ROW)));
+              const float fa = __uint_as_float(a << 16);
+              s1 += fa;
+              s2 = fmaf(fa, fa, s2);
+            }
+          }
+          gstat[q][0][ch * 32 + lane] += s1;
+          gstat[q][1][ch * 32 + lane] += s2;
+          __syncwarp();                                   // the tile is rewritten by the next chunk
         }
       }
       tc_fence_before();
@@ -502,7 +520,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
     if (p.tma_store && lane == 0) bulk_wait_all();
-    if (STATS == TC_ST_LOCAL && persist && eg < G && !(p.dbg & 2)) {
+    if (STATS == TC_ST_LOCAL && eg < G && !(p.dbg & 2)) {
       const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(v));
       const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(w2));
       gstat[q][0][lane] += t1;
@@ -751,22 +769,27 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.block_n = bn;
   p.n_tiles = ceil_div(g.N, bn);
   // 256-row tiles where every CTA still gets several of them.  Measured (scripts/gemm_bench3.py, profiles/r02_gemm_bench3.txt,
-  // M = 0.2 .. 3.2 M rows): they win for N <= 40 with or without statistics (N=16: 136 -> 86 us, N=24: 46 -> 36 us) and for
-  // N = 64 with statistics (297 -> 272 us: the transpose-sum runs once per 256 rows); they lose for N = 64 without statistics
-  // (151 -> 193 us) and for every N > 64 (two accumulators of 128 columns leave 2 TMEM stages, hence 2 epilogue groups).
+  // M = 0.2 .. 3.2 M rows): they win for N <= 40 with or without statistics (N=16: 137 -> 86 us, N=24: 47 -> 36 us, N=40:
+  // 24 -> 20 us); at N = 64 they tie with statistics (217 vs 220 us) and lose without (151 -> 195 us: two 64-column
+  // accumulators per tile leave 4 TMEM stages for 3 epilogue groups); for N > 64 they leave 2 stages, hence 2 groups, and lose.
   const bool long_m = (int64_t)ceil_div(g.M, 2 * TC_BLOCK_M) * p.n_tiles >= 3 * (int64_t)num_sms();
-  p.m_sub = kn.m_sub ? kn.m_sub : ((long_m && (bn <= 48 || (bn <= 64 && g.stats))) ? 2 : 1);
+  p.m_sub = kn.m_sub ? kn.m_sub : ((long_m && bn <= 48) ? 2 : 1);
   if (bn > 128) p.m_sub = 1;
   p.m_tiles = ceil_div(g.M, TC_BLOCK_M * p.m_sub);
   p.a_stage_bytes = TC_BLOCK_M * p.m_sub * sw;
   p.b_stage_bytes = ceil_div(bn * sw, 1024) * 1024;
   p.tx_bytes = p.a_stage_bytes + bn * sw;
+  // statistics flavour (see the kernel): lane-local sums where a thread keeps seeing the same 32 columns, else the
+  // shared-memory column reduction
+  TD3D_REQUIRE(!(g.stats && g.out_f32), "gemm_nt_tc: the statistics epilogue describes the stored bf16 values (no fp32 output)");
+  const int st_flavour = !g.stats ? TC_ST_NONE : (bn <= 32 ? TC_ST_LOCAL : TC_ST_SMEM);
   const int k_blocks = ceil_div(g.K, p.block_k);
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
-  p.w_resident = (wres_bytes <= 96 * 1024 && !kn.no_wres) ? 1 : 0;
+  p.w_resident = (wres_bytes <= (st_flavour == TC_ST_SMEM ? 48 : 96) * 1024 && !kn.no_wres) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
   p.tma_store = (!g.out_f32 && kn.tma_store) ? 1 : 0;   // measured slower than st.global (fence + 2-deep staging): off
-  const int ystage_bytes = p.tma_store ? TC_EPI_GROUPS * 4 * 2 * 2048 + 1024 : 0;
+  const int ystage_bytes = (p.tma_store ? TC_EPI_GROUPS * 4 * 2 * 2048 : 0) + (st_flavour == TC_ST_SMEM ? TC_EPI_GROUPS * 4 * TC_RED_WARP : 0) +
+                           ((p.tma_store || st_flavour == TC_ST_SMEM) ? 1024 : 0);
   int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0) - ystage_bytes;
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
@@ -797,11 +820,12 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   if (p.tma_store) TD3D_TRY(make_map_2d(&map_y, g.y, g.M, g.N, 32, 32, 64));
   else map_y = map_a;
   size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + ystage_bytes + 1024;
+  TD3D_REQUIRE(smem <= 190 * 1024, "gemm_nt_tc: %zu bytes of shared memory for M=%d N=%d K=%d", smem, g.M, g.N, g.K);
   static bool attr_set = false;
   if (!attr_set) {
     TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     attr_set = true;
   }
@@ -811,11 +835,10 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // a CTA lies in the same N tile, which lets the statistics epilogue keep one accumulator row per CTA (flushed once)
   grid -= grid % p.n_tiles;
   TD3D_REQUIRE(p.act == TD3D_ACT_NONE || !p.stats, "gemm_nt_tc: the activation epilogue (inference) has no statistics flavour");
-  const bool lane_local = p.m_sub == 2 || bn <= 32;
   if (p.act != TD3D_ACT_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<true, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else if (!p.stats) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else if (lane_local) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_CHUNK>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else if (st_flavour == TC_ST_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else if (st_flavour == TC_ST_LOCAL) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_SMEM>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }

@@ -43,10 +43,12 @@ def run(M, N, Kd, slots, msub):
     return us, (M * Kd + M * N) * 2 / 1e3 / us
 
 
-print(f"{'M':>9s} {'N':>4s} {'K':>4s} {'stats':>5s} | {'128-row us':>10s} {'GB/s':>6s} | {'256-row us':>10s} {'GB/s':>6s}")
+print(f"{'M':>9s} {'N':>4s} {'K':>4s} {'stats':>5s} | {'128-row us':>10s} {'GB/s':>6s} | {'256-row us':>10s} {'GB/s':>6s} | {'default us':>10s}")
+SHAPES += [(B * 3136, 72, 24), (B * 784, 120, 40), (B * 784, 240, 40), (B * 196, 480, 80), (B * 196, 672, 112), (B * 49, 960, 160)]
 for M, N, Kd in SHAPES:
     for slots in (32, 0):
         u1, g1 = run(M, N, Kd, slots, 1)
         u2, g2 = run(M, N, Kd, slots, 2) if N <= 128 else (float("nan"), float("nan"))
-        print(f"{M:9d} {N:4d} {Kd:4d} {slots:5d} | {u1:10.1f} {g1:6.0f} | {u2:10.1f} {g2:6.0f}", flush=True)
+        u3, _ = run(M, N, Kd, slots, 0)
+        print(f"{M:9d} {N:4d} {Kd:4d} {slots:5d} | {u1:10.1f} {g1:6.0f} | {u2:10.1f} {g2:6.0f} | {u3:10.1f}", flush=True)
 os.environ["TD3D_TC_MSUB"] = "0"

@@ -48,10 +48,15 @@ def main():
             yf = y.float()
             es = max(rel_err(st.sum(0)[0], yf.sum(0)) if yf.sum(0).abs().max() > 1e-3 else 0.0,
                      rel_err(st.sum(0)[1], (yf * yf).sum(0)))
-            y2, st2 = K.gemm_nt(a, w, L.BF16, L.GEMM_TCGEN05, addend=add, bias=bias, ysaved=ys, slots=3, out_f32=True)
+            y2, _ = K.gemm_nt(a, w, L.BF16, L.GEMM_TCGEN05, addend=add, bias=bias, slots=0, out_f32=True)
             torch.cuda.synchronize()
             e2 = rel_err(y2, ref + add.float() + bias)
-            es2 = rel_err(st2.sum(0)[1], (y2 * ys.float()).sum(0))
+            # data-gradient flavour: bf16 output + residual addend, sums of g and g * saved-y of the stored (rounded) values
+            y3, st3 = K.gemm_nt(a, w, L.BF16, L.GEMM_TCGEN05, addend=add, ysaved=ys, slots=3)
+            torch.cuda.synchronize()
+            y3f = y3.float()
+            es2 = max(rel_err(st3.sum(0)[1], (y3f * ys.float()).sum(0)), rel_err(st3.sum(0)[0], y3f.sum(0)) if y3f.sum(0).abs().max() > 1e-3 else 0.0,
+                      rel_err(y3f, ref + add.float()) / 3.0)
             out["nt"][f"{M}x{N}x{Kd}"] = [e1, es, e2, es2]
     if which in ("all", "tn"):
         for M, N1, N2 in TN:
