@@ -113,16 +113,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- TMA store path of the epilogue (bulk async group per epilogue warp) ----
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -178,7 +168,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define TC_STAMP(ev, idx)                                                                         \
   do {                                                                                            \
-    if ((p.dbg & 32) && blockIdx.x == 0 && (idx) < 64) g_tc_timeline[(ev) * 64 + (idx)] = gtimer(); \
+    if (EPI < 0 && (p.dbg & 32) && blockIdx.x == 0 && (idx) < 64) g_tc_timeline[(ev) * 64 + (idx)] = gtimer(); \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -215,20 +205,16 @@ struct TcNtParams {
   int stage_cols;       // TMEM columns of one accumulator stage = acc_stride * m_sub
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
-  int tma_store;        // 1: bf16 output leaves through swizzled smem + cp.async.bulk.tensor (coalesced), else st.global
   int epi_groups;       // active epilogue groups = min(TC_EPI_GROUPS, n_acc), see the hand-off note in the epilogue
   int mma_warps;        // 1 or 2 MMA issuer warps (2 only when a tile's k blocks of both issuers fit the smem ring at once:
                         // a parity wait must never be more than one phase away from its barrier)
-  int dbg;              // TD3D_TC_DBG bit mask (profiling experiments only): 1 no global stores, 2 no stats,
-                        // 8 no global reductions, 16 no TMEM load
+  int dbg;              // TD3D_TC_DBG: 32 = CTA 0 records the pipeline timeline (TC_EPI_ANY instances only)
 };
 
 // Measured on B200 (TD3D_TC_DBG=32 timeline): with a single 4-warp epilogue group every 32-column chunk
 // costs ~1 us of one-warp-per-scheduler latency-bound issue, the MMA/TMA side idles, and the kernel
 // runs at ~1 TB/s.  Hence TC_EPI_GROUPS groups work on different tiles concurrently, each draining its
 // own TMEM accumulator stage (tile sequence number ti -> stage ti % n_acc, group ti % TC_EPI_GROUPS).
-// EPI_ACT: the bias + activation epilogue of the inference path is a template parameter so that the training GEMMs carry
-// none of its registers (the epilogue warps sit at the 128-register limit: every extra live value spills).
 // STATS: how the BatchNorm statistic sums of the epilogue are formed.  The epilogue warps bound every wide layer (the
 // shuffle transpose-sum of round 1 -- 62 shuffles + 124 selects + 62 adds per 32 x 32 chunk -- doubled the kernel time:
 // N=64, K=16: 151 us without statistics, 297 us with), so each flavour is its own instance:
@@ -244,10 +230,19 @@ struct TcNtParams {
 enum { TC_ST_NONE = 0, TC_ST_LOCAL = 2, TC_ST_SMEM = 3 };
 static const int TC_RED_ROW = 80;                 // bytes per row of the reduction tile: 64 B of bf16 + 16 B pad (conflict-free STS.128 / LDS.U16)
 static const int TC_RED_WARP = 2 * 32 * TC_RED_ROW;   // per epilogue warp: one tile for y, one for the saved y
-template <bool EPI_ACT, int STATS>
+// EPI: which optional epilogue terms exist, as a compile-time bit mask -- or TC_EPI_ANY: every term tested at run time (the
+// instance behind td3d_k_gemm_nt's odd combinations, fp32 outputs and the debug timeline).  ncu on the all-run-time kernel
+// (profiles/r02_ncu_gemm_nt.txt) showed the predicated-off bias / addend / saved-y code of a plain forward GEMM taking a
+// quarter of the issued instructions of the epilogue warps, which bound the kernel.
+enum { TC_EPI_BIAS = 1, TC_EPI_ADDEND = 2, TC_EPI_YSAVED = 4, TC_EPI_ACT = 8, TC_EPI_ANY = -1 };
+template <int EPI, int STATS>
 __global__ void __launch_bounds__(TC_NT_THREADS, 1)
-gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                  const __grid_constant__ CUtensorMap map_y, TcNtParams p) {
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcNtParams p) {
+  const bool has_bias = EPI < 0 ? p.bias != nullptr : (EPI & TC_EPI_BIAS) != 0;
+  const bool has_addend = EPI < 0 ? p.addend != nullptr : (EPI & TC_EPI_ADDEND) != 0;
+  const bool has_ysaved = EPI < 0 ? p.ysaved != nullptr : (EPI & TC_EPI_YSAVED) != 0;
+  const bool has_act = EPI < 0 ? p.act != TD3D_ACT_NONE : (EPI & TC_EPI_ACT) != 0;
+  const bool out_f32 = EPI < 0 && p.yf != nullptr;
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES], s_empty[TC_MAX_STAGES], s_tfull[TC_MAX_ACC], s_tempty[TC_MAX_ACC];
@@ -271,7 +266,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < TC_EPI_GROUPS * 4 * 2 * 256; i += blockDim.x) (&s_stat[0][0][0][0])[i] = 0.f;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); if (p.tma_store) tma_prefetch_desc(&map_y); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem_base), TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -370,12 +365,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int et = (threadIdx.x - 32 * (1 + TC_MMA_WARPS)) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
-    const ActK eak = make_actk(EPI_ACT ? p.act : TD3D_ACT_NONE);
-    const uint32_t ybuf0 = ystage + (uint32_t)((eg * 4 + q) * 2) * 2048u;
-    // TC_ST_SMEM: this warp's reduction tiles (after the TMA-store staging area)
-    const uint32_t red_y = ystage + (p.tma_store ? (uint32_t)(TC_EPI_GROUPS * 4 * 2 * 2048) : 0u) + (uint32_t)((eg * 4 + q) * TC_RED_WARP);
+    const ActK eak = make_actk(has_act ? p.act : TD3D_ACT_NONE);
+    // TC_ST_SMEM: this warp's reduction tiles
+    const uint32_t red_y = ystage + (uint32_t)((eg * 4 + q) * TC_RED_WARP);
     const uint32_t red_s = red_y + 32u * TC_RED_ROW;
-    uint32_t ysel = 0;
     int as = eg % p.n_acc;
     uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
     // lane = row, v[j] / w2[j] = this row's contribution to the two sums of column j of the current 32-column chunk
@@ -402,54 +395,45 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int m0 = (m_tile * p.m_sub + h) * TC_BLOCK_M;
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < p.M;
-        // a full 32-column box may be stored by TMA (it clips at M and N); a chunk that would spill into the
-        // next N tile keeps the masked st.global path
-        const bool via_tma = p.tma_store && (p.n_tiles == 1 || ch * 32 + 32 <= p.block_n);
-        const uint32_t ybuf = ybuf0 + ysel * 2048u;
-        if (via_tma) {
-          if (lane == 0) bulk_wait_read_1();          // the store issued from this buffer two chunks ago has read it
-          __syncwarp();
-        }
         const int nb = n0 + ch * 32;
         constexpr int NR = STATS == TC_ST_LOCAL ? 16 : 32;
         uint32_t r[NR];
         const uint32_t t_chunk = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.stage_cols + h * p.acc_stride + ch * 32);
-        if (STATS != TC_ST_LOCAL && !(p.dbg & 16)) tmem_ld32(t_chunk, *reinterpret_cast<uint32_t(*)[32]>(r));
+        if (STATS != TC_ST_LOCAL) tmem_ld32(t_chunk, *reinterpret_cast<uint32_t(*)[32]>(r));
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (STATS == TC_ST_LOCAL && (g & 1) == 0 && !(p.dbg & 16)) tmem_ld16(t_chunk + g * 8, *reinterpret_cast<uint32_t(*)[16]>(r));
+          if (STATS == TC_ST_LOCAL && (g & 1) == 0) tmem_ld16(t_chunk + g * 8, *reinterpret_cast<uint32_t(*)[16]>(r));
           const int n = nb + g * 8;
           const bool ok = row_ok && n < p.N && (n - n0) < p.block_n;
           float x[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[(STATS == TC_ST_LOCAL ? (g & 1) : g) * 8 + i]);
           if (ok) {
-            if (p.bias) {
+            if (has_bias) {
               float bb[8];
               loadf8(p.bias + n, bb);
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += bb[i];
             }
-            if (EPI_ACT) {
+            if (has_act) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] = actk_fwd(x[i], eak);
             }
             const size_t off = (size_t)m * p.N + n;
-            if (p.addend) {
+            if (has_addend) {
               float ad[8];
               load8(p.addend + off, ad);
 #pragma unroll
               for (int i = 0; i < 8; ++i) x[i] += ad[i];
             }
-            if (p.yf) {
-              if (!(p.dbg & 1)) store8(p.yf + off, x);
+            if (out_f32) {
+              store8(p.yf + off, x);
             } else {
               const uint4 pk = pack8_bf16(x);
-              if (via_tma) sts_v4(ybuf + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4), pk);
-              else if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.y + off) = pk;
+              *reinterpret_cast<uint4*>(p.y + off) = pk;
               if (STATS == TC_ST_SMEM) {
                 sts_v4(red_y + (uint32_t)(lane * TC_RED_ROW + g * 16), pk);
-                if (p.ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), __ldg(reinterpret_cast<const uint4*>(p.ysaved + off)));
+                if (has_ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), __ldg(reinterpret_cast<const uint4*>(p.ysaved + off)));
               }
               if (STATS == TC_ST_LOCAL) {     // the statistics describe the stored (rounded) values
                 x[0] = __uint_as_float(pk.x << 16); x[1] = __uint_as_float(pk.x & 0xffff0000u);
@@ -460,34 +444,25 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             if (STATS == TC_ST_LOCAL) {
               float ys[8];
-              if (p.ysaved) load8(p.ysaved + off, ys);
+              if (has_ysaved) load8(p.ysaved + off, ys);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 v[(g * 8 + i) % NV] += x[i];
-                w2[(g * 8 + i) % NV] = fmaf(x[i], p.ysaved ? ys[i] : x[i], w2[(g * 8 + i) % NV]);
+                w2[(g * 8 + i) % NV] = fmaf(x[i], has_ysaved ? ys[i] : x[i], w2[(g * 8 + i) % NV]);
               }
             }
           } else if (STATS == TC_ST_SMEM) {
             sts_v4(red_y + (uint32_t)(lane * TC_RED_ROW + g * 16), make_uint4(0u, 0u, 0u, 0u));      // rows / columns outside the matrix add nothing
-            if (p.ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), make_uint4(0u, 0u, 0u, 0u));
+            if (has_ysaved) sts_v4(red_s + (uint32_t)(lane * TC_RED_ROW + g * 16), make_uint4(0u, 0u, 0u, 0u));
           }
-        }
-        if (via_tma) {
-          fence_async_smem();                         // generic-proxy writes -> visible to the async (TMA) proxy
-          __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
-            tma_store_2d(&map_y, ybuf, nb, m0 + q * 32);
-            bulk_commit();
-          }
-          ysel ^= 1u;
         }
         // column sums of this warp's rows, accumulated over ALL tiles of the CTA in the warp's own shared-memory
         // row (every tile of a CTA covers the same N tile, see the launcher): no barrier, no atomics per tile
-        if (STATS == TC_ST_SMEM && !(p.dbg & 2)) {
+        if (STATS == TC_ST_SMEM) {
           __syncwarp();
           float s1 = 0.f, s2 = 0.f;
           const uint32_t cy = red_y + (uint32_t)(lane * 2), cs = red_s + (uint32_t)(lane * 2);
-          if (p.ysaved) {
+          if (has_ysaved) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               uint32_t a, b;
@@ -519,8 +494,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       as += G;                                   // stage / phase of tile ti + G
       while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
     }
-    if (p.tma_store && lane == 0) bulk_wait_all();
-    if (STATS == TC_ST_LOCAL && eg < G && !(p.dbg & 2)) {
+    if (STATS == TC_ST_LOCAL && eg < G) {
       const float t1 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(v));
       const float t2 = warp_transpose_sum32_tc(*reinterpret_cast<float(*)[32]>(w2));
       gstat[q][0][lane] += t1;
@@ -535,7 +509,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int j = et; j < 2 * p.block_n; j += 128) {
         const int which = j / p.block_n, nn = j % p.block_n;
         const float tot = (gstat[0][which][nn] + gstat[1][which][nn]) + (gstat[2][which][nn] + gstat[3][which][nn]);
-        if (n0 + nn < p.N && !(p.dbg & 8)) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
+        if (n0 + nn < p.N) atomicAdd(&p.stats[((size_t)slot * 2 + which) * p.N + n0 + nn], tot);
       }
     }
   }
@@ -704,12 +678,11 @@ static int env_raw(const char* name, int dflt) {
 }
 // Tuning / debugging knobs of the NT GEMM.  Read ONCE (getenv on every eager launch showed up in host profiles);
 // TD3D_TC_LIVE_ENV=1 (micro-benchmarks that flip knobs inside one process) re-reads them on every launch.
-struct TcKnobs { int force_sw128, no_wres, tma_store, lbo, dbg, two_issuers, max_bn, tn_swap, m_sub; };
+struct TcKnobs { int force_sw128, no_wres, lbo, dbg, two_issuers, max_bn, tn_swap, m_sub; };
 static TcKnobs read_knobs() {
   TcKnobs k;
   k.force_sw128 = env_raw("TD3D_TC_FORCE_SW128", 0);
   k.no_wres = env_raw("TD3D_TC_NO_WRES", 0);
-  k.tma_store = env_raw("TD3D_TC_TMA_STORE", 0);
   k.lbo = env_raw("TD3D_TC_LBO", 16);
   k.dbg = env_raw("TD3D_TC_DBG", 0);
   k.two_issuers = env_raw("TD3D_TC_TWO_ISSUERS", 0);
@@ -744,6 +717,25 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+
+typedef void (*NtKernel)(const CUtensorMap, const CUtensorMap, TcNtParams);
+struct NtInstance { int epi, stats; NtKernel fn; };
+#define TD3D_NT(E, S) {E, S, gemm_nt_tc_kernel<E, S>}
+static const NtInstance kNtInstances[] = {
+    // training forward (1x1 convs), data gradient of the projection conv
+    TD3D_NT(0, TC_ST_NONE), TD3D_NT(0, TC_ST_SMEM), TD3D_NT(0, TC_ST_LOCAL),
+    // data gradient of the expansion conv: + sums of g and g * saved-y for the previous block's BatchNorm (+ residual gradient)
+    TD3D_NT(TC_EPI_YSAVED, TC_ST_SMEM), TD3D_NT(TC_EPI_YSAVED, TC_ST_LOCAL),
+    TD3D_NT(TC_EPI_YSAVED | TC_EPI_ADDEND, TC_ST_SMEM), TD3D_NT(TC_EPI_YSAVED | TC_EPI_ADDEND, TC_ST_LOCAL),
+    TD3D_NT(TC_EPI_ADDEND, TC_ST_NONE),
+    // classifier Linear (bias) with BatchNorm1d statistics
+    TD3D_NT(TC_EPI_BIAS, TC_ST_SMEM),
+    // inference: folded BatchNorm bias (+ activation | + residual)
+    TD3D_NT(TC_EPI_BIAS | TC_EPI_ACT, TC_ST_NONE), TD3D_NT(TC_EPI_BIAS, TC_ST_NONE), TD3D_NT(TC_EPI_BIAS | TC_EPI_ADDEND, TC_ST_NONE),
+    // everything else (fp32 output, td3d_k_gemm_nt combinations, debug timeline)
+    TD3D_NT(TC_EPI_ANY, TC_ST_NONE), TD3D_NT(TC_EPI_ANY, TC_ST_SMEM), TD3D_NT(TC_EPI_ANY, TC_ST_LOCAL),
+};
+#undef TD3D_NT
 
 int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   TD3D_REQUIRE(tc_gemm_supported(g.M, g.N, g.K), "gemm_nt_tc: unsupported shape M=%d N=%d K=%d", g.M, g.N, g.K);
@@ -787,9 +779,9 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
   p.w_resident = (wres_bytes <= (st_flavour == TC_ST_SMEM ? 48 : 96) * 1024 && !kn.no_wres) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
-  p.tma_store = (!g.out_f32 && kn.tma_store) ? 1 : 0;   // measured slower than st.global (fence + 2-deep staging): off
-  const int ystage_bytes = (p.tma_store ? TC_EPI_GROUPS * 4 * 2 * 2048 : 0) + (st_flavour == TC_ST_SMEM ? TC_EPI_GROUPS * 4 * TC_RED_WARP : 0) +
-                           ((p.tma_store || st_flavour == TC_ST_SMEM) ? 1024 : 0);
+  // (a shared-memory staged TMA store of the output was measured twice, in round 1 and again with the lean epilogues of
+  // round 2, profiles/r02_gemm_bench4.txt: within +-3 % of the per-thread 16-byte stores on every layer, so it was removed)
+  const int ystage_bytes = st_flavour == TC_ST_SMEM ? TC_EPI_GROUPS * 4 * TC_RED_WARP + 1024 : 0;
   int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0) - ystage_bytes;
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
@@ -814,19 +806,21 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the second issuer
   // is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
   p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
-  CUtensorMap map_a, map_w, map_y;
+  CUtensorMap map_a, map_w;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M * p.m_sub, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
-  if (p.tma_store) TD3D_TRY(make_map_2d(&map_y, g.y, g.M, g.N, 32, 32, 64));
-  else map_y = map_a;
   size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + ystage_bytes + 1024;
   TD3D_REQUIRE(smem <= 190 * 1024, "gemm_nt_tc: %zu bytes of shared memory for M=%d N=%d K=%d", smem, g.M, g.N, g.K);
+  // instance: the exact epilogue mask where it is one of the plan's combinations, else the all-run-time kernel
+  int epi = (g.bias ? TC_EPI_BIAS : 0) | (g.addend ? TC_EPI_ADDEND : 0) | (g.ysaved ? TC_EPI_YSAVED : 0) | (g.act != TD3D_ACT_NONE ? TC_EPI_ACT : 0);
+  if (g.out_f32 || kn.dbg) epi = TC_EPI_ANY;
+  const NtInstance* inst = nullptr;
+  for (const NtInstance& c : kNtInstances)
+    if (c.stats == st_flavour && (c.epi == epi || (!inst && c.epi == TC_EPI_ANY))) { inst = &c; if (c.epi == epi) break; }
+  TD3D_REQUIRE(inst != nullptr, "gemm_nt_tc: no kernel instance for statistics flavour %d", st_flavour);
   static bool attr_set = false;
   if (!attr_set) {
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, TC_ST_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
-    TD3D_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, TC_ST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    for (const NtInstance& c : kNtInstances) TD3D_CUDA(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     attr_set = true;
   }
   int grid = p.m_tiles * p.n_tiles;
@@ -835,10 +829,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   // a CTA lies in the same N tile, which lets the statistics epilogue keep one accumulator row per CTA (flushed once)
   grid -= grid % p.n_tiles;
   TD3D_REQUIRE(p.act == TD3D_ACT_NONE || !p.stats, "gemm_nt_tc: the activation epilogue (inference) has no statistics flavour");
-  if (p.act != TD3D_ACT_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<true, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else if (st_flavour == TC_ST_NONE) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_NONE>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else if (st_flavour == TC_ST_LOCAL) TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_LOCAL>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
-  else TD3D_CUDA(launch_kernel(gemm_nt_tc_kernel<false, TC_ST_SMEM>, grid, TC_NT_THREADS, smem, st, map_a, map_w, map_y, p));
+  TD3D_CUDA(launch_kernel(inst->fn, grid, TC_NT_THREADS, smem, st, map_a, map_w, p));
   TD3D_LAUNCH_CHECK();
   return TD3D_OK;
 }
