@@ -229,7 +229,7 @@ struct TcNtParams {
 // The statistics always describe the stored bf16 values; an fp32 output has no statistics flavour.
 enum { TC_ST_NONE = 0, TC_ST_LOCAL = 2, TC_ST_SMEM = 3 };
 static const int TC_RED_ROW = 80;                 // bytes per row of the reduction tile: 64 B of bf16 + 16 B pad (conflict-free STS.128 / LDS.U16)
-static const int TC_RED_WARP = 2 * 32 * TC_RED_ROW;   // per epilogue warp: one tile for y, one for the saved y
+static const int TC_RED_TILE = 32 * TC_RED_ROW;       // per epilogue warp: one tile for y (+ one for the saved y)
 // EPI: which optional epilogue terms exist, as a compile-time bit mask -- or TC_EPI_ANY: every term tested at run time (the
 // instance behind td3d_k_gemm_nt's odd combinations, fp32 outputs and the debug timeline).  ncu on the all-run-time kernel
 // (profiles/r02_ncu_gemm_nt.txt) showed the predicated-off bias / addend / saved-y code of a plain forward GEMM taking a
@@ -367,8 +367,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float (*gstat)[2][256] = s_stat[eg];
     const ActK eak = make_actk(has_act ? p.act : TD3D_ACT_NONE);
     // TC_ST_SMEM: this warp's reduction tiles
-    const uint32_t red_y = ystage + (uint32_t)((eg * 4 + q) * TC_RED_WARP);
-    const uint32_t red_s = red_y + 32u * TC_RED_ROW;
+    const uint32_t red_y = ystage + (uint32_t)((eg * 4 + q) * (has_ysaved ? 2 : 1) * TC_RED_TILE);
+    const uint32_t red_s = red_y + (uint32_t)TC_RED_TILE;
     int as = eg % p.n_acc;
     uint32_t aphase = (uint32_t)(eg / p.n_acc) & 1u;
     // lane = row, v[j] / w2[j] = this row's contribution to the two sums of column j of the current 32-column chunk
@@ -781,7 +781,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
   // (a shared-memory staged TMA store of the output was measured twice, in round 1 and again with the lean epilogues of
   // round 2, profiles/r02_gemm_bench4.txt: within +-3 % of the per-thread 16-byte stores on every layer, so it was removed)
-  const int ystage_bytes = st_flavour == TC_ST_SMEM ? TC_EPI_GROUPS * 4 * TC_RED_WARP + 1024 : 0;
+  const int ystage_bytes = st_flavour == TC_ST_SMEM ? TC_EPI_GROUPS * 4 * (g.ysaved ? 2 : 1) * TC_RED_TILE + 1024 : 0;
   int budget = 176 * 1024 - (p.w_resident ? wres_bytes : 0) - ystage_bytes;
   p.stages = budget / stage_bytes;
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;

@@ -34,8 +34,8 @@ for M, N, Kd in SHAPES:
 # ---- pipeline timeline of CTA 0 (ns since first event) ----
 import ctypes as C
 import numpy as np
-for M, N, Kd in [(256 * 112 * 112, 64, 16), (256 * 112 * 112, 16, 16)]:
-    for slots in (0, 256):
+for M, N, Kd in [(256 * 112 * 112, 64, 16), (256 * 28 * 28, 240, 40), (256 * 14 * 14, 672, 112)]:
+    for slots in (0, 32):
         os.environ["TD3D_TC_DBG"] = "32"
         a = torch.randn(M, Kd, device=dev).bfloat16(); w = torch.randn(N, Kd, device=dev).bfloat16()
         y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
