@@ -585,6 +585,26 @@ def main():
                     "share_of_step": top[1]["share"], "launches_per_step": top[1]["launches_per_step"],
                     "how": "CUDA events around every launch of this kernel kind on the launching stream, eager pass"}
 
+    if rank == 0 and args.skip_profile:
+        # the launch count is a claim of its own (gpu_launches): one eager step under the plan's launch counter
+        lib = L.lib()
+        plan = model._last_plan
+        saved, saved_ar = step.use_graph, step.allreduce
+        step.use_graph, step.allreduce = False, None
+        L.check(lib.td3d_plan_profile(plan.handle, 1))
+        step.run()
+        torch.cuda.synchronize(dev)
+        launches, k = 0, 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms_k, by_k, n_k = C.c_double(), C.c_double(), C.c_int64()
+            if lib.td3d_plan_profile_read(plan.handle, k, name, 64, C.byref(ms_k), C.byref(by_k), C.byref(n_k)) != 0:
+                break
+            launches += n_k.value
+            k += 1
+        L.check(lib.td3d_plan_profile(plan.handle, 0))
+        step.use_graph, step.allreduce = saved, saved_ar
+
     # ---- whole-step roofline (all layers are HBM-bound) ------------------------
     esz = 2 if args.dtype == "bf16" else 4
     step_bytes = algorithmic_bytes_per_crop(esz) * B + 28.0 * sum(p.numel() for p in model.parameters())

@@ -219,6 +219,9 @@ int td3d_k_dw_bwd(const void* g, const void* y_out, const float* alpha, const fl
 int td3d_k_dw_fwd_ex(const void* x, const float* scale, const float* shift, const float* se, int act,
                      const float* w_taps, const float* out_bias, int out_act, void* y, float* stats, int B, int H,
                      int W, int C, int k, int stride, int dtype, int impl, void* stream);
+/* Y[M,N] = A[M,K] W[N,K]^T (+ bias[n]) (+ addend[m,n]);  stats (optional): [stat_slots][2][N] += column sums of y and of
+ * y * ysaved (y * y when ysaved is null), taken on the stored values.  impl = TD3D_GEMM_TCGEN05: bf16 only, and the statistics
+ * need the bf16 output (out_f32 = 0); the slot a sum lands in is unspecified (consumers add all slots). */
 int td3d_k_gemm_nt(const void* a, const void* w, void* y, const void* addend, const float* bias,
                    const void* ysaved, float* stats, int stat_slots, int M, int N, int K, int dtype,
                    int out_f32, int impl, void* stream);

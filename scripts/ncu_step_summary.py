@@ -19,8 +19,8 @@ import sys
 KINDS = [
     (r"stem_fwd", "stem_fwd"), (r"stem_wgrad", "stem_wgrad"),
     (r"gemm_tn_", "gemm_wgrad"), (r"gemm_nt_", "gemm_nt"),
-    (r"dwc_fwd|d2_fwd|ww_conv_kernel<[^,]*, \d, 0,", "dw_fwd"),
-    (r"dwc_bwd|d2_bwd|ww_wgrad|ww_conv_kernel<[^,]*, \d, 1,", "dw_bwd"),
+    (r"dwc_fwd|d2_fwd|ww_conv_kernel", "dw_fwd"),
+    (r"dwc_bwd", "dw_bwd"),
     (r"bn_.*finalize", "bn_finalize"), (r"apply_xform", "apply_xform"), (r"affine2", "affine2"),
     (r"act_bwd_stats", "act_bwd_stats"), (r"se_", "se_fc"), (r"heads_", "heads"), (r"pool_finalize", "pool"),
     (r"optim_kernel", "optimizer"), (r"pack_table", "pack_weights"),
