@@ -176,8 +176,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // ------------------------------------------------------------------------------------------------
 static const int TC_THREADS = 192;          // 6 warps (TN kernel)
 static const int TC_EPI_GROUPS = 3;         // NT kernel: independent 4-warp epilogue groups (one warp per TMEM lane quarter)
-static const int TC_MMA_WARPS = 2;          // NT kernel: MMA issuer warps, tile ti is issued by warp 1 + ti % TC_MMA_WARPS
-static const int TC_NT_THREADS = 32 * (1 + TC_MMA_WARPS) + TC_EPI_GROUPS * 128;
+static const int TC_NT_THREADS = 32 * 2 + TC_EPI_GROUPS * 128;   // NT kernel: TMA producer warp, MMA issuer warp, epilogue groups
 static const int TC_MAX_ACC = 8;            // TMEM accumulator stages
 static const int TC_BLOCK_M = 128;
 static const int TC_MAX_STAGES = 12;
@@ -196,7 +195,6 @@ struct TcNtParams {
   const bf16* addend; const float* bias; const bf16* ysaved;
   float* stats; int slots;
   int act;              // epilogue activation after the bias (TD3D_ACT_*), before the addend
-  int lbo_field_bytes;  // value for the (ignored) LBO field of K-major swizzled descriptors
   int n_acc, acc_stride; // TMEM accumulator stages; columns of one 128-row accumulator (power of two >= block_n)
   int m_sub;            // 128-row MMA blocks per tile (1 or 2).  The single-thread producer / issuer loops and the epilogue
                         // hand-off cost ~0.8 us per tile whatever its size (timeline in profiles/r01_v3_gemm_bench_timeline.txt);
@@ -206,8 +204,6 @@ struct TcNtParams {
   int w_resident;       // 1: the whole W operand is loaded ONCE per CTA into its own smem region (all 148 CTAs
                         // re-fetching the same few-KB W tile for every 128-row tile hot-spots one L2 slice)
   int epi_groups;       // active epilogue groups = min(TC_EPI_GROUPS, n_acc), see the hand-off note in the epilogue
-  int mma_warps;        // 1 or 2 MMA issuer warps (2 only when a tile's k blocks of both issuers fit the smem ring at once:
-                        // a parity wait must never be more than one phase away from its barrier)
   int dbg;              // TD3D_TC_DBG: 32 = CTA 0 records the pipeline timeline (TC_EPI_ANY instances only)
 };
 
@@ -306,26 +302,23 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     }
-  } else if (warp <= TC_MMA_WARPS) {
-    // ===================== MMA issuers (one elected thread per warp) =====================
-    // Timeline (TD3D_TC_DBG=32): one thread needs ~650 ns per tile for wait / descriptors / tcgen05.mma /
-    // 2 x tcgen05.commit, which capped K=16 layers at ~1.7 TB/s.  The tiles are therefore dealt round-robin to
-    // TC_MMA_WARPS issuer warps; every tile has its own smem stages and TMEM accumulator stage, and a
-    // tcgen05.commit tracks the MMAs of its own thread, so the issuers never have to talk to each other.
-    const int mw = warp - 1;
-    if (lane == 0 && mw < p.mma_warps) {
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected thread) =====================
+    // Timeline (TD3D_TC_DBG=32, profiles/r02_gemm_timeline.txt): the thread needs ~0.8 us per tile for two barrier waits,
+    // descriptors, tcgen05.mma and 2 x tcgen05.commit, which bounds the K=16 layers.  A second issuer warp (round 1: +20 % on
+    // those layers) was removed: with two issuers the accumulator stages are committed out of tile order, nothing bounds how
+    // far one issuer may fall behind the other, and an epilogue group's parity wait could then alias a stage's
+    // previous-but-one phase.  The 256-row tiles (m_sub) are the safe way to halve the per-row cost.
+    if (lane == 0) {
       const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)p.block_n, 0, 0);
       const uint32_t layout_type = p.swizzle_bytes == 128 ? 2u : (p.swizzle_bytes == 64 ? 4u : 6u);
       const uint32_t sbo = 8u * (uint32_t)p.swizzle_bytes;     // 8 rows of one swizzle span
       int stage = 0; uint32_t phase = 0;
-      // smem stages / accumulator stage of this warp's first tile (ti = mw)
-      for (int i = 0; i < mw * k_blocks; ++i)
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       if (p.w_resident && blockIdx.x < num_tiles) mbar_wait(smem_u32(&s_wfull), 0);
-      int ti = mw;
-      int as = mw % p.n_acc;            // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
-      uint32_t aphase = (uint32_t)(mw / p.n_acc) & 1u;
-      for (int tile = blockIdx.x + mw * gridDim.x; tile < num_tiles; tile += p.mma_warps * gridDim.x, ti += p.mma_warps) {
+      int ti = 0;
+      int as = 0;                       // accumulator stage ti % n_acc and its phase (ti / n_acc) & 1, kept incrementally
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         const int n_tile = p.n_tiles == 1 ? 0 : tile % p.n_tiles;
         mbar_wait(smem_u32(&s_tempty[as]), aphase ^ 1u);          // epilogue drained this accumulator
         TC_STAMP(2, ti);
@@ -342,8 +335,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int h = 0; h < p.m_sub; ++h) {                      // rows h * 128 ... of the tile -> accumulator h of the stage
             const uint32_t a_h = a_src + (uint32_t)(h * TC_BLOCK_M * p.swizzle_bytes);
             for (int ks = 0; ks < k_steps; ++ks) {
-              const uint64_t da = make_smem_desc(a_h + ks * 32, p.lbo_field_bytes, sbo, layout_type);
-              const uint64_t db = make_smem_desc(b_src + ks * 32, p.lbo_field_bytes, sbo, layout_type);
+              const uint64_t da = make_smem_desc(a_h + ks * 32, 16, sbo, layout_type);     // LBO is ignored for K-major swizzled operands
+              const uint64_t db = make_smem_desc(b_src + ks * 32, 16, sbo, layout_type);
               umma_bf16(d_tmem + (uint32_t)(h * p.acc_stride), da, db, idesc, (kb | ks) != 0 ? 1u : 0u);
             }
           }
@@ -352,17 +345,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           TC_STAMP(4, ti);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        for (int i = 0; i < (p.mma_warps - 1) * k_blocks; ++i)      // skip the stages of the other issuer's tiles
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        as += p.mma_warps;
-        while (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1u; }
+        if (++as == p.n_acc) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int eg = (warp - 1 - TC_MMA_WARPS) >> 2;         // epilogue group (any 4 consecutive warps cover the 4 quarters)
-    const int et = (threadIdx.x - 32 * (1 + TC_MMA_WARPS)) & 127;   // 0..127 within the epilogue group
+    const int eg = (warp - 2) >> 2;         // epilogue group (any 4 consecutive warps cover the 4 quarters)
+    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the epilogue group
     const int n_chunks = (p.block_n + 31) >> 5;
     float (*gstat)[2][256] = s_stat[eg];
     const ActK eak = make_actk(has_act ? p.act : TD3D_ACT_NONE);
@@ -534,7 +524,6 @@ struct TcTnParams {
   int n2_boxes;         // ceil(n2_block / 64)
   int m_per_part;       // multiple of TN_BK
   float* c;
-  int swap_lbo_sbo;     // debugging aid: exchange the LBO/SBO roles
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -585,8 +574,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t idesc = make_idesc(128, (uint32_t)p.n2_block, 1, 1);
       // MN-major, 128B swizzle: atom = 64 channels x 8 rows (1024 B). Rows (the contraction index)
       // advance by 128 B; 8-row groups are SBO apart; 64-channel blocks are LBO apart.
-      uint32_t lbo = TN_BOX_BYTES, sbo = 1024;
-      if (p.swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+      const uint32_t lbo = TN_BOX_BYTES, sbo = 1024;
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(smem_u32(&s_full[stage]), phase);
@@ -678,18 +666,13 @@ static int env_raw(const char* name, int dflt) {
 }
 // Tuning / debugging knobs of the NT GEMM.  Read ONCE (getenv on every eager launch showed up in host profiles);
 // TD3D_TC_LIVE_ENV=1 (micro-benchmarks that flip knobs inside one process) re-reads them on every launch.
-struct TcKnobs { int force_sw128, no_wres, lbo, dbg, two_issuers, max_bn, tn_swap, m_sub; };
+struct TcKnobs { int dbg, max_bn, m_sub; };
 static TcKnobs read_knobs() {
   TcKnobs k;
-  k.force_sw128 = env_raw("TD3D_TC_FORCE_SW128", 0);
-  k.no_wres = env_raw("TD3D_TC_NO_WRES", 0);
-  k.lbo = env_raw("TD3D_TC_LBO", 16);
   k.dbg = env_raw("TD3D_TC_DBG", 0);
-  k.two_issuers = env_raw("TD3D_TC_TWO_ISSUERS", 0);
   k.m_sub = env_raw("TD3D_TC_MSUB", 0);            // 0 auto, 1 / 2 force (A/B measurements)
   if (k.m_sub < 0 || k.m_sub > 2) k.m_sub = 0;
   k.max_bn = env_raw("TD3D_TC_MAXBN", 0);        // 0 = rule in launch_gemm_nt_tc
-  k.tn_swap = env_raw("TD3D_TC_TN_SWAP", 0);
   return k;
 }
 static const TcKnobs& knobs() {
@@ -744,10 +727,8 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   const TcKnobs& kn = knobs();
   int sw = 128;
-  if (!kn.force_sw128) {
-    if (g.K <= 16) sw = 32;
-    else if (g.K <= 32) sw = 64;
-  }
+  if (g.K <= 16) sw = 32;
+  else if (g.K <= 32) sw = 64;
   p.swizzle_bytes = sw;
   p.block_k = sw / 2;
   // N tiling: equal tiles of <= 256 columns, each a multiple of 16
@@ -777,7 +758,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   const int st_flavour = !g.stats ? TC_ST_NONE : (bn <= 32 ? TC_ST_LOCAL : TC_ST_SMEM);
   const int k_blocks = ceil_div(g.K, p.block_k);
   const int wres_bytes = p.n_tiles * k_blocks * p.b_stage_bytes;
-  p.w_resident = (wres_bytes <= (st_flavour == TC_ST_SMEM ? 48 : 96) * 1024 && !kn.no_wres) ? 1 : 0;
+  p.w_resident = (wres_bytes <= (st_flavour == TC_ST_SMEM ? 48 : 96) * 1024 ) ? 1 : 0;
   int stage_bytes = p.a_stage_bytes + (p.w_resident ? 0 : p.b_stage_bytes);
   // (a shared-memory staged TMA store of the output was measured twice, in round 1 and again with the lean epilogues of
   // round 2, profiles/r02_gemm_bench4.txt: within +-3 % of the per-thread 16-byte stores on every layer, so it was removed)
@@ -791,7 +772,6 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.addend = (const bf16*)g.addend; p.bias = g.bias; p.ysaved = (const bf16*)g.ysaved;
   p.stats = g.stats; p.slots = g.slots > 0 ? g.slots : 1;
   p.act = g.act;
-  p.lbo_field_bytes = kn.lbo;
   p.dbg = kn.dbg;
   p.acc_stride = 32;
   while (p.acc_stride < bn) p.acc_stride <<= 1;
@@ -799,13 +779,6 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
   p.n_acc = TC_TMEM_COLS / p.stage_cols;
   if (p.n_acc > TC_MAX_ACC) p.n_acc = TC_MAX_ACC;
   p.epi_groups = p.n_acc < TC_EPI_GROUPS ? p.n_acc : TC_EPI_GROUPS;
-  // measured (scripts/gemm_bench.py): a second issuer lifts the light-epilogue K=16 layers from 1.7 to 2.05 TB/s, but
-  // costs the statistics epilogue 4-8 % of its issue slots, and with two issuers the accumulator stages are no longer
-  // committed in tile order: nothing bounds how far one issuer may fall behind the other (up to the smem ring depth), so an
-  // epilogue group that runs >= n_acc - G tiles ahead of the slower issuer could see the parity of a stage's
-  // previous-but-one phase and read it early.  Until the accumulator hand-off carries a full phase counter the second issuer
-  // is opt-in (TD3D_TC_TWO_ISSUERS=1, statistic-free GEMMs whose k blocks fit the ring twice).
-  p.mma_warps = (kn.two_issuers && !g.stats && TC_MMA_WARPS * k_blocks <= p.stages) ? TC_MMA_WARPS : 1;
   CUtensorMap map_a, map_w;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.K, TC_BLOCK_M * p.m_sub, p.block_k, sw));
   TD3D_TRY(make_map_2d(&map_w, g.w, g.N, g.K, bn, p.block_k, sw));
@@ -869,7 +842,6 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   p.m_per_part = ceil_div(ceil_div(g.M, parts), TN_BK) * TN_BK;
   parts = ceil_div(g.M, p.m_per_part);
   p.c = g.c;
-  p.swap_lbo_sbo = knobs().tn_swap;
   CUtensorMap map_a, map_b;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.N1, TN_BK, 64, 128));
   TD3D_TRY(make_map_2d(&map_b, g.b, g.M, g.N2, TN_BK, 64, 128));
