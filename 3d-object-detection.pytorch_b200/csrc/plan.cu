@@ -1319,6 +1319,14 @@ int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int f
 }
 
 // ---- per-kernel entry points ----------------------------------------------------------------
+int td3d_lift_2d(const float* kp, int n, int portrait, const double* cam_ndc, double* out, void* stream) {
+  pdl_break_all();
+  return launch_lift_2d(kp, n, portrait, cam_ndc, out, (cudaStream_t)stream);
+}
+int td3d_iou_2d_based(const float* pred_kp, const float* gt_kp, int n, int portrait, const double* cam_ndc, double* iou, void* stream) {
+  pdl_break_all();
+  return launch_iou_2d_based(pred_kp, gt_kp, n, portrait, cam_ndc, iou, (cudaStream_t)stream);
+}
 int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W, int C, int dtype,
                     void* stream) {
   pdl_break_all();                           // other libraries' work may precede this call on the stream

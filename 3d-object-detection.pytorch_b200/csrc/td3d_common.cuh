@@ -88,7 +88,10 @@ inline cudaError_t launch_kernel(void (*kern)(P...), dim3 grid, dim3 block, size
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cap);
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {      // e.g. the legacy stream while another stream captures: the launch
+    cudaGetLastError();                                      // itself will report it; do not leave a stale error behind
+    cap = cudaStreamCaptureStatusActive;
+  }
   cfg.numAttrs = (cap == cudaStreamCaptureStatusNone && pdl_take(st)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
 }

@@ -96,6 +96,11 @@ int launch_dw_fwd_walker(const DwArgs& a, int dtype, cudaStream_t st);
 int launch_dw_bwd_fused(const DwBwdArgs& a, int dtype, cudaStream_t st);  // k_dwc.cu: one pass (data + weight gradient + sums)
 int launch_dw_fwd_cw(const DwArgs& a, int dtype, cudaStream_t st);        // k_dwc.cu: column walker (optional bias + activation epilogue)
 
+// ---- k_iou.cu (evaluation: 2D-keypoint based 3D IoU, EPnP lift) ----
+int launch_iou_2d_based(const float* pred_kp, const float* gt_kp, int n, int portrait, const double* cam_ndc, double* iou,
+                        cudaStream_t st);
+int launch_lift_2d(const float* kp, int n, int portrait, const double* cam_ndc, double* out, cudaStream_t st);
+
 // ---- k_gemm_simple.cu / k_gemm_tc.cu ----
 struct GemmNT {              // Y[M,N] = A[M,K] * W[N,K]^T (+bias[n]) (+addend[m,n])
   const void* a; const void* w; void* y;

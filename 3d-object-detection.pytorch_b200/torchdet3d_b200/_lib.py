@@ -65,7 +65,7 @@ SYMBOLS = [
     "td3d_pack_weights",
     "td3d_forward", "td3d_forward_export", "td3d_backward_stages", "td3d_backward",
     "td3d_backward_ready_range", "td3d_loss_fwd_bwd", "td3d_metrics_accum", "td3d_optim_step", "td3d_roi_crop_resize",
-    "td3d_k_stem_fwd", "td3d_k_stem_wgrad", "td3d_k_dw_fwd", "td3d_k_dw_bwd", "td3d_k_dw_fwd_ex", "td3d_k_gemm_nt",
+    "td3d_lift_2d", "td3d_iou_2d_based", "td3d_k_stem_fwd", "td3d_k_stem_wgrad", "td3d_k_dw_fwd", "td3d_k_dw_bwd", "td3d_k_dw_fwd_ex", "td3d_k_gemm_nt",
     "td3d_k_gemm_tn", "td3d_k_apply_xform", "td3d_k_affine2", "td3d_k_act_bwd_stats", "td3d_debug_tc_timeline",
 ]
 

@@ -3,14 +3,12 @@
 Drop-in for torchdet3d/evaluation/metrics.py:10-68 (`compute_average_distance`, `compute_accuracy`,
 `compute_metrics_per_cls`).  The reference runs a 9x9 Python loop of tiny kernels plus three host
 syncs per call; here one launch (one warp per sample) accumulates everything -- totals and the
-per-class breakdown -- into a device-side f64 accumulator.  The 3D-IoU column (EPnP lift + Qhull,
-metrics.py:70-89) is CPU numpy/scipy per sample in the reference and outside the B200 hot path
-(SURVEY.md 8f-4): `compute_iou=True` keeps working for unmodified callers (scripts/main.py:105) by
-delegating to an IoU backend -- the reference's own `compute_2d_based_iou` when `torchdet3d` is
-importable, or whatever `set_iou_backend` installed -- and otherwise warns once and reports 0.
+per-class breakdown -- into a device-side f64 accumulator.  The 3D-IoU column (metrics.py:70-89: EPnP lift
++ Objectron box fit / clipping + Qhull volume, a Python loop over the batch on the CPU in the reference) is the
+CUDA kernel `td3d_iou_2d_based` (csrc/k_iou.cu), one thread per sample pair, so
+`compute_iou=True` of unmodified callers (scripts/main.py:105) stays on the device; `set_iou_backend(fn)`
+swaps in another implementation (e.g. the reference's CPU function for a cross-check).
 """
-import warnings
-
 import torch
 
 from .. import _lib as L
@@ -77,35 +75,44 @@ def compute_accuracy(pred_cats, gt_cats, reduce_mean=True, **kwargs):
     return a[2] / B if reduce_mean else a[2]
 
 
-_iou_backend = None          # callable(pred_kp[n,9,2], gt_kp[n,9,2], reduce_mean=False) -> summed IoU
-_iou_probe_done = False
+@torch.no_grad()
+def compute_2d_based_iou(pred_kp, gt_kp, reduce_mean=True):
+    """Reference metrics.py:70-89 (lift both keypoint sets in portrait mode, fit boxes, intersect them) as ONE launch of
+    `td3d_iou_2d_based` over the batch: no device -> host copy of the keypoints, no per-sample Python loop, no scipy.
+    pred_kp / gt_kp: CUDA tensors [n, 9, 2].  A pair the reference drops (Qhull / LinAlg error) contributes 0 here too."""
+    assert pred_kp.dim() == 3
+    n = pred_kp.shape[0]
+    if n == 0:
+        return 0
+    L.require_b200()
+    p = pred_kp.detach().float().contiguous()
+    g = gt_kp.detach().float().contiguous()
+    out = torch.empty(n, dtype=torch.float64, device=p.device)
+    with torch.cuda.device(p.device):
+        L.check(L.lib().td3d_iou_2d_based(L.ptr(p), L.ptr(g), n, 1, None, L.ptr(out), L.stream()))
+    total = float(out.sum().item())
+    return total / n if reduce_mean else total
+
+
+_iou_backend = None          # callable(pred_kp[n,9,2], gt_kp[n,9,2], reduce_mean=False) -> summed IoU; None = the CUDA kernel
 
 
 def set_iou_backend(fn):
-    """Install the 3D-IoU implementation used when `compute_iou=True` (signature of the reference's
-    `compute_2d_based_iou`, metrics.py:70-89).  `None` restores the default lookup."""
-    global _iou_backend, _iou_probe_done
-    _iou_backend, _iou_probe_done = fn, fn is not None
+    """Replace the 3D-IoU implementation used when `compute_iou=True` (signature of the reference's
+    `compute_2d_based_iou`, metrics.py:70-89), e.g. with the reference's own CPU function for a cross-check.
+    `None` restores the built-in CUDA kernel."""
+    global _iou_backend
+    _iou_backend = fn
 
 
 def _iou_fn():
-    global _iou_backend, _iou_probe_done
-    if not _iou_probe_done:
-        _iou_probe_done = True
-        try:
-            from torchdet3d.evaluation.metrics import compute_2d_based_iou   # the reference package, if installed
-            _iou_backend = compute_2d_based_iou
-        except Exception as ex:                                              # noqa: BLE001
-            warnings.warn("compute_iou=True: no 3D-IoU backend (the reference's EPnP + Qhull CPU path, torchdet3d."
-                          f"evaluation.metrics.compute_2d_based_iou, is not importable: {type(ex).__name__}); the IOU "
-                          "column is reported as 0. Install one with torchdet3d_b200.evaluation.set_iou_backend(fn).")
-    return _iou_backend
+    return _iou_backend if _iou_backend is not None else compute_2d_based_iou
 
 
 @torch.no_grad()
 def compute_metrics_per_cls(pred_kp, gt_kp, pred_cats, gt_cats, compute_iou=True, **kwargs):
     """-> ([(cls, ADD, SADD, IOU, acc)], ADD, SADD, IOU, acc) as metrics.py:39-68.  ADD / SADD / acc come
-    from one kernel launch; the IOU column from the CPU backend (see module docstring) or 0."""
+    from one kernel launch; the IOU column from `compute_2d_based_iou` (one more launch per class present)."""
     a = _run(pred_kp, gt_kp, pred_cats, gt_cats)
     B = pred_kp.shape[0]
     iou = _iou_fn() if compute_iou else None

@@ -199,6 +199,18 @@ int td3d_roi_crop_resize(const uint8_t* frames, int n_frames, int frame_h, int f
                          int n_boxes, int out_h, int out_w, const float* mean255, const float* inv_std255,
                          int swap_rb, float* out, void* stream);
 
+/* ---- evaluation post-processing: the step after the path ------------------------
+ * td3d_lift_2d replaces torchdet3d/utils/geometry.py:51-108 (lift_2d: EPnP-style lift of nine normalised 2D keypoints to
+ * 3D box points in camera coordinates, up to scale; 16 x 12 system, eigenvector of the smallest eigenvalue).
+ * td3d_iou_2d_based replaces the per-sample loop of torchdet3d/evaluation/metrics.py:70-89 (compute_2d_based_iou: lift both
+ * keypoint sets in portrait mode, fit boxes and intersect them -- Objectron box.py:123-156,207-225 and iou.py:22-35,74-211
+ * vendored under the reference's 3rdparty/); a pair the reference drops on a Qhull / LinAlg error yields 0 here too.
+ * kp / pred_kp / gt_kp  device f32 [n, 9, 2];  cam_ndc  HOST f64 {fx, fy, cx, cy} of the NDC camera matrix or NULL for the
+ * reference's default (2, 2, 0, 0);  out device f64 [n, 9, 3];  iou device f64 [n] (the caller sums or averages).     */
+int td3d_lift_2d(const float* kp, int n, int portrait, const double* cam_ndc, double* out, void* stream);
+int td3d_iou_2d_based(const float* pred_kp, const float* gt_kp, int n, int portrait, const double* cam_ndc,
+                      double* iou, void* stream);
+
 /* ---- per-kernel entry points (unit tests / profiling) -------------------------------------- */
 int td3d_k_stem_fwd(const float* img, const float* w27x16, void* y, float* stats, int B, int H, int W,
                     int C, int dtype, void* stream);

@@ -260,6 +260,41 @@ def run_effnet_golden():
     print("effnet_b0 ->", sum(v.nbytes for v in out.values()) // 1024, "KiB")
 
 
+def run_iou_golden():
+    """the reference's own lift_2d (utils/geometry.py:51-108) and compute_2d_based_iou (evaluation/metrics.py:70-89,
+    Objectron box / iou vendored under 3rdparty/) on jittered copies of the known-answer keypoints of tests/test_geometry.py:13-21,
+    plus the edge cases: identical sets, disjoint boxes, a degenerate (all-equal) set."""
+    sys.path.insert(0, os.path.join(refshim.REFERENCE_ROOT, "3rdparty", "Objectron"))
+    from torchdet3d.utils import lift_2d
+    from objectron.dataset import box as obox, iou as oiou
+    base = np.array([[0.47714591, 0.47491544], [0.73884577, 0.39749265], [0.18508956, 0.40002537], [0.74114597, 0.48664019],
+                     [0.18273196, 0.48833901], [0.64639187, 0.46719882], [0.32766378, 0.46827659], [0.64726073, 0.51853681],
+                     [0.32699507, 0.51933688]])
+    rng = np.random.default_rng(1234)
+    pred, gt = [], []
+    for i in range(96):
+        sig = [0.002, 0.01, 0.03, 0.08][i % 4]
+        gt.append(np.clip(base + rng.normal(0, 0.02, base.shape), 0, 1))
+        pred.append(np.clip(gt[-1] + rng.normal(0, sig, base.shape), 0, 1))
+    pred.append(base.copy()); gt.append(base.copy())                                  # identical -> IoU 1
+    pred.append(np.clip(base * 0.3, 0, 1)); gt.append(np.clip(base * 0.3 + 0.6, 0, 1))  # far apart
+    pred.append(np.full_like(base, 0.5)); gt.append(base.copy())                        # degenerate prediction
+    pred.append(rng.random(base.shape)); gt.append(rng.random(base.shape))              # arbitrary (non-box) keypoints
+    pred, gt = np.array(pred, dtype=np.float32), np.array(gt, dtype=np.float32)
+    lifted_p, lifted_g, ious = [], [], []
+    for p_, g_ in zip(pred, gt):
+        l = lift_2d([p_, g_], portrait=True)
+        lifted_p.append(l[0]); lifted_g.append(l[1])
+        try:
+            ious.append(oiou.IoU(obox.Box(vertices=l[0]), obox.Box(vertices=l[1])).iou())
+        except Exception:                      # the reference swallows QhullError / LinAlgError and adds 0 (metrics.py:83-86)
+            ious.append(0.0)
+    out = dict(pred=pred, gt=gt, lifted_pred=np.array(lifted_p), lifted_gt=np.array(lifted_g), iou=np.array(ious),
+               lifted_landscape=np.array(lift_2d([base], portrait=False)[0]))
+    np.savez_compressed(os.path.join(OUT, "iou.npz"), **out)
+    print("iou ->", len(ious), "pairs, mean IoU", float(np.mean(ious)), "min", float(np.min(ious)), "max", float(np.max(ious)))
+
+
 def main():
     refshim.install()
     os.makedirs(OUT, exist_ok=True)
@@ -271,6 +306,8 @@ def main():
         run_loss_metric_golden()
     if only in (None, "effnet"):
         run_effnet_golden()
+    if only in (None, "iou"):
+        run_iou_golden()
     for case in CASES:
         if only in (None, case[0]):
             run_case(*case)

@@ -32,6 +32,7 @@ fi
 timeout 600 python scripts/dw_bench.py 256 > gpurun_out/dw_bench.txt 2>&1; tail -n 17 gpurun_out/dw_bench.txt | cut -c1-200
 timeout 600 python scripts/gemm_bench3.py > gpurun_out/gemm_bench3.txt 2>&1; tail -n 5 gpurun_out/gemm_bench3.txt | cut -c1-200
 timeout 600 python scripts/gemm_bench_tn.py > gpurun_out/gemm_bench_tn.txt 2>&1; tail -n 3 gpurun_out/gemm_bench_tn.txt | cut -c1-200
+timeout 600 python scripts/iou_bench.py > gpurun_out/iou_bench.txt 2>&1; cat gpurun_out/iou_bench.txt | cut -c1-200
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip 800 -c 800 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --skip-cpu --skip-profile --skip-infer > gpurun_out/ncu_bench.out 2>&1
 python scripts/ncu_step_summary.py gpurun_out/launches.csv gpurun_out/launches_summary.txt gpurun_out/ncu_traffic.json | tail -24
 ls -la gpurun_out/ | tail -5

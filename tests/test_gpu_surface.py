@@ -204,13 +204,23 @@ def test_evaluator_runs_as_reference_main_calls_it(tmp_path):
     cfg, model = make_model(case)
     batches = [tuple(t for t in train_batch(case, s)[:3]) for s in range(2)]
     ev = Evaluator(model=model, val_loader=batches, test_loader=None, cfg=cfg, writer=None, max_epoch=2, device=DEV)
-    set_iou_backend(None)
-    with warnings.catch_warnings(record=True) as w:
+    set_iou_backend(None)                      # the built-in CUDA kernel (td3d_iou_2d_based)
+    with warnings.catch_warnings(record=True):
         warnings.simplefilter("always")
         r = ev.val(1, True)
-        assert ev.visual_test() is None
-    assert r["IOU"] == 0.0 and 0 <= r["ADD"] <= 2 and len(r["per_class"]) == 9
-    assert any("IoU" in str(x.message) or "IOU" in str(x.message) for x in w)
+        assert ev.visual_test() is None        # drawing is out of scope: delegates to the reference or warns, never raises
+    assert 0 <= r["ADD"] <= 2 and len(r["per_class"]) == 9
+    # the IOU column against the oracle (oracle/iou_port.py restates lift_2d + Objectron IoU) on the same predictions
+    from oracle import iou_port
+    model.eval()
+    tot, n = 0.0, 0
+    with torch.no_grad():
+        for imgs, gt_kp, gt_cats in batches:
+            imgs, gt_kp, gt_cats = imgs.to(DEV), gt_kp.to(DEV), gt_cats.to(DEV)
+            pred_kp, _ = model(imgs, gt_cats)
+            tot += iou_port.compute_2d_based_iou(pred_kp.float().cpu().numpy(), gt_kp.float().cpu().numpy(), reduce_mean=False)
+            n += imgs.shape[0]
+    assert abs(r["IOU"] - tot / n) < 1e-4, (r["IOU"], tot / n)
     calls = []
 
     def fake_iou(pred_kp, gt_kp, reduce_mean=True):
