@@ -233,13 +233,12 @@ def run_infer(args, rank, world, local):
     ms_step = t.item() / args.steps
     value = world * IB / (ms_step / 1e3)
 
-    # end to end: pinned host crops -> H2D -> graph -> D2H of keypoints + labels, every step
+    # end to end: pinned host crops -> H2D (per micro-batch, on a staging stream) -> forward -> D2H of keypoints + labels, every step
     kp_h = torch.zeros(IB, 9, 2).pin_memory()
     lab_h = torch.zeros(IB, dtype=torch.int64).pin_memory()
 
     def e2e_step():
-        sess.load(imgs_h)
-        kp, labels, _ = sess.run()
+        kp, labels, _ = sess(imgs_h)           # InferSession.run_from_host: micro-batch copies overlapped with compute
         kp_h.copy_(kp, non_blocking=True)
         lab_h.copy_(labels, non_blocking=True)
 

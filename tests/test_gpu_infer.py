@@ -36,6 +36,30 @@ def test_infer_session_fp32_matches_oracle_bit_exact_labels(name):
     assert np.array_equal(lab2.cpu().numpy(), ref_lab.numpy()) and rel(t2n(kp2), ref_sel.numpy()) < 1e-3
 
 
+def test_infer_session_pipelined_host_path_matches_device_path():
+    """Pinned host crops take InferSession.run_from_host (micro-batch copies on a staging stream overlapped with compute): same
+    results as the staged + graph path, also when calls alternate and the buffer is overwritten by the next call's copies."""
+    case = dict(model="mobilenetv3_small", optim=dict(name="adam"), loss=None)
+    _, model = make_model(case)
+    B, res = 40, 96
+    xs = [torch.rand(B, 3, res, res, generator=torch.Generator().manual_seed(10 + i)) for i in range(3)]
+    sess = InferSession(model, B, res, res, chunk=16)
+    want = []
+    for x in xs:
+        for _ in range(3):
+            kp, labels, logits = sess(x)                      # pageable host tensor: load() + run() (graph after warm-up)
+        want.append((kp.clone(), labels.clone(), logits.clone()))
+    pinned = [x.pin_memory() for x in xs]
+    for rounds in range(2):
+        for x, (kp_w, lab_w, lg_w) in zip(pinned, want):
+            kp, labels, logits = sess(x)                      # back-to-back pipelined calls, no synchronisation in between
+            got = (kp.clone(), labels.clone(), logits.clone())
+            assert torch.equal(got[1], lab_w) and torch.allclose(got[0], kp_w, atol=1e-6) and torch.allclose(got[2], lg_w, atol=1e-5)
+        sess.load(xs[0].to(DEV))                              # a device-path call in between must be ordered against the copies
+        kp, labels, _ = sess.run()
+        assert torch.equal(labels, want[0][1]) and torch.allclose(kp, want[0][0], atol=1e-6)
+
+
 def test_infer_session_weights_refresh_without_recapture():
     case = dict(model="mobilenetv3_small", optim=dict(name="adam"), loss=None)
     _, model = make_model(case)
