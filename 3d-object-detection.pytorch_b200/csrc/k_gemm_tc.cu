@@ -600,11 +600,16 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
       if (n1 < p.N1) {
+        // 16-byte vector reductions (red.global.add.v4.f32, sm_90+): the split over M ends in 128 x n2_block atomics per CTA,
+        // which bounded the short-M layers (3 M scalar atomics on a 50176 x 480 x 80 problem); N2 and the chunk starts are
+        // multiples of 8, so every group of 4 columns is 16-byte aligned and either entirely inside the matrix or outside
+        float* row = p.c + (size_t)n1 * p.N2 + n2_0 + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; i += 4) {
           const int nn = ch * 32 + i;
-          const int n2 = n2_0 + nn;
-          if (nn < p.n2_block && n2 < p.N2) atomicAdd(&p.c[(size_t)n1 * p.N2 + n2], __uint_as_float(r[i]));
+          if (nn < p.n2_block && n2_0 + nn < p.N2)
+            atomicAdd(reinterpret_cast<float4*>(row + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
         }
       }
     }
@@ -809,6 +814,7 @@ int launch_gemm_nt_tc(const GemmNT& g, cudaStream_t st) {
 
 int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   TD3D_REQUIRE(g.M > 0 && g.N1 % 8 == 0 && g.N2 % 8 == 0, "gemm_tn_tc: unsupported shape M=%d N1=%d N2=%d", g.M, g.N1, g.N2);
+  TD3D_REQUIRE(((uintptr_t)g.c & 15) == 0, "gemm_tn_tc: the output must be 16-byte aligned (vector reductions)");
   TcTnParams p;
   p.M = g.M; p.N1 = g.N1; p.N2 = g.N2;
   int n2_tiles = ceil_div(g.N2, 256);
@@ -820,7 +826,7 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   // M split: every part ends with 128 x n2_block fp32 atomics into the same tile, so more parts buy
   // streaming parallelism at the price of atomic traffic (measured: 196 parts of 256 rows spent 60 us on a
   // 27 MB problem).  Pick the split that minimises a simple cost model: operand streaming at
-  // ring-bytes / latency per CTA and ~5 TB/s per chip, plus ~150 G atomics/s, plus waves of 1 CTA per SM.
+  // ring-bytes / latency per CTA and ~5 TB/s per chip, plus ~300 G reduced elements/s, plus waves of 1 CTA per SM.
   int parts = 1;
   {
     const int max_parts = ceil_div(g.M, TN_BK * 4);
@@ -834,7 +840,8 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
       const double cap = TN_STAGES * TN_BK * row_bytes / 1.5e3;   // TMA ring keeps in flight over ~1.5 us of latency
       if (rate > cap) rate = cap;
       const double stream_us = (double)ceil_div(n_ctas, num_sms()) * rows * row_bytes / (rate * 1e3);
-      const double atom_us = (double)n_ctas * 128.0 * p.n2_block / 1.5e5;
+      const double atom_us = (double)n_ctas * 128.0 * p.n2_block / 3e5;      // fp32 elements per us through 16-byte reductions (the
+                                                                             // total is flat between 1.5e5 and 1.2e6: 570-598 us)
       const double cost = stream_us + atom_us;
       if (cost < best) { best = cost; parts = cand; }
     }
