@@ -163,8 +163,8 @@ apply_xform_kernel(const T* __restrict__ y, XForm xf, const T* __restrict__ res,
   }
   if (stats) {
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x)
-      atomicAdd(&stats[((size_t)b * 2 + 0) * C + i], s_acc[i]);
+    for (int i = threadIdx.x * 4; i < C; i += blockDim.x * 4)      // C % 8 == 0: 16-byte vector reductions
+      atomicAdd(reinterpret_cast<float4*>(&stats[((size_t)b * 2 + 0) * C + i]), make_float4(s_acc[i], s_acc[i + 1], s_acc[i + 2], s_acc[i + 3]));
   }
 }
 
@@ -331,8 +331,8 @@ act_bwd_stats_kernel(const T* g, const float* __restrict__ g_pooled, float g_sca
   }
   if (stats) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-      atomicAdd(&stats[(size_t)b * 2 * C + i], s_acc[i]);
+    for (int i = threadIdx.x * 4; i < 2 * C; i += blockDim.x * 4)      // C % 8 == 0: 16-byte vector reductions
+      atomicAdd(reinterpret_cast<float4*>(&stats[(size_t)b * 2 * C + i]), make_float4(s_acc[i], s_acc[i + 1], s_acc[i + 2], s_acc[i + 3]));
   }
 }
 
