@@ -522,6 +522,8 @@ struct TcTnParams {
   int M, N1, N2;
   int n2_block;         // UMMA N (multiple of 16, <= 256)
   int n2_boxes;         // ceil(n2_block / 64)
+  int a_boxes;          // 64-channel boxes of the A operand (1 when N1 <= 64: the MMA still multiplies 128 channel rows, the
+                        // upper 64 read the neighbouring B box and their results are never stored)
   int m_per_part;       // multiple of TN_BK
   float* c;
 };
@@ -534,7 +536,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = 2 * TN_BOX_BYTES, b_bytes = (uint32_t)p.n2_boxes * TN_BOX_BYTES;
+  const uint32_t a_bytes = (uint32_t)p.a_boxes * TN_BOX_BYTES, b_bytes = (uint32_t)p.n2_boxes * TN_BOX_BYTES;
   const uint32_t stage_bytes = a_bytes + b_bytes;
 
   if (threadIdx.x == 0) {
@@ -564,7 +566,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_expect_tx(full, stage_bytes);
         const int row = ms + kb * TN_BK;
         tma_load_2d(a_dst, &map_a, full, n1_0, row);
-        tma_load_2d(a_dst + TN_BOX_BYTES, &map_a, full, n1_0 + 64, row);
+        if (p.a_boxes == 2) tma_load_2d(a_dst + TN_BOX_BYTES, &map_a, full, n1_0 + 64, row);
         for (int j = 0; j < p.n2_boxes; ++j) tma_load_2d(b_dst + j * TN_BOX_BYTES, &map_b, full, n2_0 + j * 64, row);
         if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -821,6 +823,7 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   p.n2_block = ceil_div(ceil_div(g.N2, n2_tiles), 16) * 16;
   n2_tiles = ceil_div(g.N2, p.n2_block);
   p.n2_boxes = ceil_div(p.n2_block, 64);
+  p.a_boxes = g.N1 <= 64 ? 1 : 2;
   int n1_tiles = ceil_div(g.N1, 128);
   int tiles = n1_tiles * n2_tiles;
   // M split: every part ends with 128 x n2_block fp32 atomics into the same tile, so more parts buy
@@ -852,7 +855,7 @@ int launch_gemm_tn_tc(const GemmTN& g, cudaStream_t st) {
   CUtensorMap map_a, map_b;
   TD3D_TRY(make_map_2d(&map_a, g.a, g.M, g.N1, TN_BK, 64, 128));
   TD3D_TRY(make_map_2d(&map_b, g.b, g.M, g.N2, TN_BK, 64, 128));
-  size_t smem = (size_t)TN_STAGES * (2 + p.n2_boxes) * TN_BOX_BYTES + 1024;
+  size_t smem = (size_t)TN_STAGES * (p.a_boxes + p.n2_boxes) * TN_BOX_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     TD3D_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
