@@ -13,8 +13,7 @@
 //     once per CTA;
 //   * PREFETCHED: the raw (bf16/fp32) tile of item i+1 is fetched with cp.async into a private
 //     staging area while item i is computed; the producer's lazily applied transform (BatchNorm fold
-//     + SE gate + activation, or the BatchNorm-backward affine of the gradient) is then evaluated
-//     ONCE per staged element into an fp32 shared-memory tile;
+//     + SE gate + activation) is then evaluated ONCE per staged element into an fp32 shared-memory tile;
 //   * a thread owns 4 channels x (2x4 | 1x4) outputs and walks the window row by row with 128-bit
 //     conflict-free shared loads; multiply-adds are packed fp32x2 (FFMA2, sm_100);
 //   * statistics (BatchNorm sums / SE squeeze) stay in registers across the tiles of a sample block

@@ -8,11 +8,16 @@
 // HBM-bound (arithmetic intensity 9-140 flop/B vs a ridge of ~217), so the design goal is bytes in
 // flight, not tensor-pipe occupancy:
 //   * persistent CTAs, one per SM, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer
-//     (one elected thread, tcgen05.mma), warps 2-5 = epilogue (tcgen05.ld -> registers -> global)
+//     (one elected thread, tcgen05.mma), warps 2-13 = three 4-warp epilogue groups (tcgen05.ld ->
+//     registers -> global), each draining its own TMEM accumulator stage
 //   * operands are staged by TMA (cp.async.bulk.tensor, hardware swizzle chosen from K so that a
-//     16-channel layer does not waste 7/8 of each shared-memory row) in a multi-stage mbarrier ring
-//   * the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
-//     tile i+1; BatchNorm statistics are reduced in the epilogue with a 31-shuffle transpose-sum
+//     16-channel layer does not waste 7/8 of each shared-memory row) in a multi-stage mbarrier ring;
+//     the whole W operand stays resident in shared memory when it fits
+//   * up to 8 accumulator stages in TMEM so the epilogues of tiles i .. i+2 overlap the MMAs of the
+//     next tiles; BatchNorm statistics are reduced in the epilogue (lane-local registers or a per-warp
+//     shared-memory column reduction) and leave as one vector of atomics per CTA
+//   * the optional epilogue terms (bias, addend, saved-y, activation) are compile-time: one kernel
+//     instance per combination the plan uses
 //   * M/N/K tails are handled by TMA out-of-bounds zero fill + masked epilogue stores
 // Every mbarrier wait is bounded (trap instead of hanging the GPU).
 #include "td3d_kernels.h"
