@@ -61,8 +61,8 @@ template <int CG> struct D2C {
 };
 
 template <int CG> struct D2Consts {
-  float sc[CG], sh[CG], be[CG];
-  float se[D2_MAXNB][CG], al[D2_MAXNB][CG], ga[D2_MAXNB][CG];
+  float sc[CG], sh[CG];
+  float se[D2_MAXNB][CG];
 };
 
 // ---- small vector helpers ---------------------------------------------------------------------
@@ -167,34 +167,23 @@ __device__ __forceinline__ float act_f(float u, int act) {
   if (act == TD3D_ACT_HSWISH) return u * __saturatef(fmaf(u, 1.f / 6.f, 0.5f));
   return u;
 }
-__device__ __forceinline__ float act_d(float u, int act) {
-  if (act == TD3D_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-  if (act == TD3D_ACT_HSWISH) return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : fmaf(u, 1.f / 3.f, 0.5f));
-  return 1.f;
-}
-
 // ---- per-CTA constants ------------------------------------------------------------------------
 template <int CG>
-__device__ __forceinline__ void d2_load_chan_consts(D2Consts<CG>& k, const XForm& xf, const float* __restrict__ beta, int c0,
-                                                    int C) {
+__device__ __forceinline__ void d2_load_chan_consts(D2Consts<CG>& k, const XForm& xf, int c0, int C) {
   for (int i = threadIdx.x; i < CG; i += D2_THREADS) {
     const int c = c0 + i;
     const bool on = c < C;
     k.sc[i] = (on && xf.scale) ? xf.scale[c] : 1.f;
     k.sh[i] = (on && xf.scale) ? xf.shift[c] : 0.f;
-    k.be[i] = (on && beta) ? beta[c] : 0.f;
   }
 }
 template <int CG>
-__device__ __forceinline__ void d2_load_sample_consts(D2Consts<CG>& k, const XForm& xf, const float* __restrict__ alpha,
-                                                      const float* __restrict__ gamma, int b0, int nb, int B, int c0, int C) {
+__device__ __forceinline__ void d2_load_sample_consts(D2Consts<CG>& k, const XForm& xf, int b0, int nb, int B, int c0, int C) {
   for (int i = threadIdx.x; i < nb * CG; i += D2_THREADS) {
     const int n = i / CG, cc = i % CG;
     const int c = c0 + cc, b = b0 + n;
     const bool on = c < C && b < B;
     k.se[n][cc] = (on && xf.se) ? xf.se[(size_t)b * C + c] : 1.f;
-    k.al[n][cc] = (on && alpha) ? alpha[(size_t)b * C + c] : 0.f;
-    k.ga[n][cc] = (on && gamma) ? gamma[(size_t)b * C + c] : 0.f;
   }
 }
 
@@ -277,42 +266,6 @@ __device__ __forceinline__ void d2_xform_x(float* __restrict__ tile, const uint8
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = act_f(v[i], act);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      }
-      sts4(dst, v[0], v[1], v[2], v[3]);
-      sts4(dst + 4, v[4], v[5], v[6], v[7]);
-    }
-  }
-}
-
-// raw (g, y) -> tile = alpha*g + beta*y + gamma; zero outside the tensor
-template <typename T, int CG>
-__device__ __forceinline__ void d2_xform_gy(float* __restrict__ tile, const uint8_t* __restrict__ raw_g,
-                                            const uint8_t* __restrict__ raw_y, uint32_t mask, const uint32_t (&rc)[D2_NIT],
-                                            int nit, int rows, int cols, const D2Consts<CG>& k) {
-  const int v8 = D2C<CG>::v8();
-  float be[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) be[i] = k.be[v8 * 8 + i];
-#pragma unroll
-  for (int u = 0; u < D2_NIT; ++u) {
-    if (u < nit && rc[u] != D2_DEAD) {
-      const int r = rc[u] & 0xffu, c = (rc[u] >> 8) & 0xffu, n = rc[u] >> 16;
-      float* dst = tile + ((n * rows + r) * cols + c) * D2C<CG>::PS + v8 * 8;
-      float v[8];
-      if ((mask >> u) & 1u) {
-        float yv[8];
-        const size_t slot = (size_t)(u * D2_THREADS + threadIdx.x) * Raw8<T>::BYTES;
-        Raw8<T>::read(raw_g + slot, v);
-        Raw8<T>::read(raw_y + slot, yv);
-        const float4 a0 = lds4(&k.al[n][v8 * 8]), a1 = lds4(&k.al[n][v8 * 8 + 4]);
-        const float4 g0 = lds4(&k.ga[n][v8 * 8]), g1 = lds4(&k.ga[n][v8 * 8 + 4]);
-        v[0] = fmaf(a0.x, v[0], fmaf(be[0], yv[0], g0.x)); v[1] = fmaf(a0.y, v[1], fmaf(be[1], yv[1], g0.y));
-        v[2] = fmaf(a0.z, v[2], fmaf(be[2], yv[2], g0.z)); v[3] = fmaf(a0.w, v[3], fmaf(be[3], yv[3], g0.w));
-        v[4] = fmaf(a1.x, v[4], fmaf(be[4], yv[4], g1.x)); v[5] = fmaf(a1.y, v[5], fmaf(be[5], yv[5], g1.y));
-        v[6] = fmaf(a1.z, v[6], fmaf(be[6], yv[6], g1.z)); v[7] = fmaf(a1.w, v[7], fmaf(be[7], yv[7], g1.w));
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -414,7 +367,7 @@ d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T*
   const int c0 = blockIdx.y * CG;
   const int n_items = t.b_blocks * t.tiles_y * t.tiles_x;
   const int it0 = blockIdx.x * t.items_per_cta, it1 = min(n_items, it0 + t.items_per_cta);
-  d2_load_chan_consts<CG>(kc, xf, nullptr, c0, C);
+  d2_load_chan_consts<CG>(kc, xf, c0, C);
   d2_load_w<K, CG>(s_w, w, c0, C, false);
   uint32_t rc[D2_NIT];
   d2_items<CG>(rc, t.ih, t.iw, t.nb);
@@ -439,7 +392,7 @@ d2_fwd_kernel(const T* __restrict__ x, XForm xf, const float* __restrict__ w, T*
       if (has_se || (stats && cur_bb >= 0)) __syncthreads();     // previous tile fully consumed (kc.se, part)
       if (stats && cur_bb >= 0)
         d2_flush_stats<CG>(part, s1, s2, m.sp, m.q, t.tyt * t.txt, t.nb, stats, cur_bb * t.nb, B, c0, C);
-      if (has_se) d2_load_sample_consts<CG>(kc, xf, nullptr, nullptr, b0, t.nb, B, c0, C);
+      if (has_se) d2_load_sample_consts<CG>(kc, xf, b0, t.nb, B, c0, C);
       cur_bb = cur.bb;
     }
     cp_async_wait_all();
